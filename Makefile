@@ -1,0 +1,35 @@
+# Builds libforagax_b200.so (sm_100a only) in-tree and the C oracle used by tests/bench.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
+CSRC      := foragax_b200/csrc
+BUILD     := build/obj
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(SRCS))
+LIB       := foragax_b200/libforagax_b200.so
+
+# geometry kernels must not contract mul+add into FMA (discrete orientation predicates)
+NOFMA     := raycast
+
+all: $(LIB) oracle
+
+$(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/foragax_b200.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) $(if $(filter $*,$(NOFMA)),-fmad=false,) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared --cudart static -o $@ $(OBJS)
+
+oracle: oracle/_build/libfgx_oracle.so
+
+oracle/_build/libfgx_oracle.so: oracle/c/fgx_oracle.c
+	@mkdir -p oracle/_build
+	gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off -fno-fast-math -o $@ $< -lm
+
+ptxas-info:
+	@for f in $(SRCS); do echo "== $$f"; $(NVCC) $(NVFLAGS) -Xptxas -v -c $$f -o /dev/null 2>&1 | grep -E "Compiling|registers|spill" ; done
+
+clean:
+	rm -rf build $(LIB) oracle/_build
+
+.PHONY: all oracle clean ptxas-info

@@ -1,0 +1,130 @@
+"""ctypes binding of ``libforagax_b200.so`` (the C ABI declared in ``include/foragax_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, importing this module raises.
+PyTorch is used only as plumbing -- it owns device memory (``tensor.data_ptr()``) and the
+CUDA stream the kernels are enqueued on.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libforagax_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`) "
+        "-- foragax_b200 has no CPU fallback")
+
+lib = C.CDLL(LIB_PATH)
+
+FGX_U8, FGX_I32, FGX_F32, FGX_U32 = 0, 1, 2, 3
+OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_NONZERO = range(7)
+MAX_LEAVES = 32
+
+vp, i64, i32, u32, f32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float, C.c_size_t
+
+
+class PredTerm(C.Structure):
+    _fields_ = [("data", vp), ("dtype", i32), ("op", i32), ("imm_bits", u32), ("stride", i32)]
+
+
+class Predicate(C.Structure):
+    _fields_ = [("term", PredTerm * 4), ("n_terms", i32), ("lut", u32)]
+
+
+class Leaf(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("row_bytes", i64)]
+
+
+class Walls(C.Structure):
+    _fields_ = [("x1", vp), ("y1", vp), ("x2", vp), ("y2", vp), ("n", i64)]
+
+
+def _decl(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_decl("fgx_last_error", C.c_char_p)
+_decl("fgx_version", C.c_int)
+_decl("fgx_device_info", C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))
+_decl("fgx_threefry_split", C.c_int, vp, i64, i32, vp, vp)
+_decl("fgx_threefry_random_bits", C.c_int, vp, i64, i32, vp, vp)
+_decl("fgx_threefry_uniform", C.c_int, vp, i64, i32, f32, f32, vp, vp)
+_decl("fgx_threefry_randint", C.c_int, vp, i64, i32, i32, i32, vp, vp)
+_decl("fgx_threefry_normal", C.c_int, vp, i64, i32, vp, vp)
+_decl("fgx_select_scratch_bytes", sz, i64)
+_decl("fgx_select", C.c_int, C.POINTER(Predicate), i64, vp, vp, vp, sz, vp)
+_decl("fgx_argsort_scratch_bytes", sz, i64)
+_decl("fgx_argsort", C.c_int, vp, i32, i64, i32, vp, vp, sz, vp)
+_decl("fgx_gather_rows", C.c_int, C.POINTER(Leaf), i32, vp, i64, vp)
+_decl("fgx_count_active", C.c_int, vp, i64, vp, vp)
+_decl("fgx_create_base", C.c_int, C.POINTER(u32), i64, i64, i32, vp, vp, vp, vp, vp)
+_decl("fgx_dice_create", C.c_int, i64, i32, vp, vp, vp, vp, vp, vp)
+_decl("fgx_dice_step", C.c_int, i64, i32, vp, vp, vp, vp, vp)
+_decl("fgx_dice_remove", C.c_int, i64, vp, vp, vp, vp, vp)
+_decl("fgx_dice_add", C.c_int, i64, i32, vp, vp, vp, vp, vp, vp)
+
+
+class FgxError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise FgxError(lib.fgx_last_error().decode() + f" (code {rc})")
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise FgxError("foragax_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FgxError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise FgxError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return FGX_F32
+    if t.dtype == torch.int32:
+        return FGX_I32
+    if t.dtype in (torch.bool, torch.uint8):
+        return FGX_U8
+    if t.dtype == torch.uint32:
+        return FGX_U32
+    raise FgxError(f"unsupported leaf dtype {t.dtype}")
+
+
+def scratch(nbytes):
+    """Scratch buffer from torch's caching allocator (512-byte aligned)."""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device())
+
+
+def device_i32(v):
+    """A traced count: int32 device scalar from a Python int or a device tensor."""
+    if isinstance(v, torch.Tensor):
+        if v.dtype != torch.int32 or not v.is_cuda:
+            v = v.to(device=device(), dtype=torch.int32)
+        return v.reshape(-1)[:1].contiguous()
+    return torch.tensor([int(v)], dtype=torch.int32, device=device())

@@ -1,0 +1,186 @@
+"""Agent manipulation -- the B200 mirror of ``foragax/base/agent_methods.py:9-79``.
+
+Same function names, argument order and return values as the reference
+(``create_agents, step_agents, (jit_)add_agents, (jit_)remove_agents, (jit_)set_agents,
+(jit_)select_agents, (jit_)sort_agents``).  Every function enqueues CUDA kernels of
+``libforagax_b200.so`` on the current stream and returns without synchronising; counts
+(``num_agents_*``, the count returned by ``select_agents``) are int32 *device* scalars so a
+select -> remove -> sort -> select -> add chain never round-trips to the host.
+
+Where the reference runs a serial ``lax.fori_loop`` over a per-agent callback
+(``agent_methods.py:29-35,43-49,55-61``) the native op processes all ``k`` rows in one
+launch; it receives the rows as a :class:`RowRange` / :class:`RowIds` instead of one
+``idx`` at a time.  Rows touched by one call are distinct (they come from a permutation),
+so the parallel result equals the serial one.
+
+Buffers are updated in place where the reference would return an updated copy (the usual
+``set.agents = step_agents(..., set)`` pattern drops the old value); ``sort_agents``
+gathers into fresh buffers.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+from .. import random as fgx_random
+from .. import struct
+from .agent_classes import Agent, Agent_Set, Params, Policy, Signal, State, native, require_native  # noqa: F401
+from .predicates import P, Pred, as_pred  # noqa: F401
+
+
+class RowRange:
+    """Rows ``[start, start+count)``; both are int32 device scalars (add_agents)."""
+
+    def __init__(self, start, count):
+        self.start, self.count = start, count
+
+
+class RowIds:
+    """Rows ``ids[0:count]``; ``count`` is an int32 device scalar (remove / set)."""
+
+    def __init__(self, ids, count):
+        self.ids, self.count = ids, count
+
+
+def num_slots(agents):
+    return int(agents.unique_id.shape[0])
+
+
+# agent_methods.py:9-17
+def create_agents(params, agent_set, key):
+    n = int(agent_set.num_total_agents)
+    n_active = int(agent_set.num_active_agents)
+    dev = L.device()
+    k0, k1 = fgx_random.key_to_host(key)
+    key_host = (C.c_uint32 * 2)(k0, k1)
+    uniq_ids = torch.empty(n, dtype=torch.int32, device=dev)
+    create_keys = torch.empty((n, 2), dtype=torch.uint32, device=dev)
+    active_states = torch.empty(n, dtype=torch.float32, device=dev)
+    agent_types = torch.empty(n, dtype=torch.int32, device=dev)
+    L.check(L.lib.fgx_create_base(key_host, n, n_active, int(agent_set.agent_type), L.ptr(uniq_ids),
+                                  L.ptr(create_keys), L.ptr(active_states), L.ptr(agent_types), L.stream()))
+    return agent_set.create_agents(params, uniq_ids, active_states, agent_types, create_keys)
+
+
+# agent_methods.py:20-24
+def step_agents(params, input, agent_set):
+    try:
+        return agent_set.step_agents(params, input, agent_set.agents)
+    except ValueError:
+        print("Error in step_agents")
+
+
+def count_active(agents):
+    """``jnp.sum(agents.active_state, dtype=jnp.int32)`` as an int32[1] device tensor."""
+    a = agents.active_state
+    out = torch.empty(1, dtype=torch.int32, device=a.device)
+    L.check(L.lib.fgx_count_active(L.ptr(a), a.shape[0], L.ptr(out), L.stream()))
+    return out
+
+
+# agent_methods.py:26-38
+def add_agents(add_func, num_agents_add, add_params, agents, key):
+    require_native(add_func, "add_func")
+    id_last_active = count_active(agents)
+    rows = RowRange(id_last_active, L.device_i32(num_agents_add))
+    new_agents, key = add_func(add_params, agents, rows, key)
+    return new_agents, key
+
+
+jit_add_agents = add_agents
+
+
+# agent_methods.py:41-52
+def remove_agents(remove_func, num_agents_remove, remove_params, agents):
+    require_native(remove_func, "remove_func")
+    rows = RowIds(remove_params.content['remove_ids'], L.device_i32(num_agents_remove))
+    return remove_func(remove_params, agents, rows)
+
+
+jit_remove_agents = remove_agents
+
+
+# agent_methods.py:54-63
+def set_agents(set_func, num_agents_set, set_params, agents, key):
+    require_native(set_func, "set_func")
+    rows = RowIds(set_params.content['set_ids'], L.device_i32(num_agents_set))
+    new_agents, key = set_func(set_params, agents, rows, key)
+    return new_agents, key
+
+
+jit_set_agents = set_agents
+
+
+# agent_methods.py:66-72
+def select_agents(select_func, select_params, agents):
+    """Returns ``(selected_ids_len int32[], sort_selected_ids int32[N])``: the stable
+    partition "selected ascending, then unselected ascending" (== ``argsort(-mask)``)."""
+    pred = as_pred(select_func(agents, select_params))
+    if isinstance(agents, Agent) or hasattr(agents, "unique_id"):
+        n = num_slots(agents)
+    else:
+        n = int(pred.terms[0].tensor.shape[0])
+    dev = L.device()
+    pstruct, keep = pred.to_struct(n)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = L.lib.fgx_select_scratch_bytes(n)
+    scr = L.scratch(nbytes)
+    L.check(L.lib.fgx_select(C.byref(pstruct), n, L.ptr(perm), L.ptr(count), L.ptr(scr), nbytes, L.stream()))
+    del keep
+    return count.reshape(()), perm
+
+
+jit_select_agents = select_agents
+
+
+def argsort(quantity, ascend=True):
+    """Stable ``jnp.argsort(q)`` / ``jnp.argsort(-q)`` of a float32 / int32 key -> int32[N]."""
+    q = quantity.reshape(-1)
+    if q.dtype == torch.bool:
+        q = q.to(torch.int32)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    n = q.shape[0]
+    if isinstance(ascend, torch.Tensor):
+        ascend = bool(ascend.item())
+    perm = torch.empty(n, dtype=torch.int32, device=q.device)
+    nbytes = L.lib.fgx_argsort_scratch_bytes(n)
+    scr = L.scratch(nbytes)
+    L.check(L.lib.fgx_argsort(L.ptr(q), L.dtype_code(q), n, 0 if ascend else 1, L.ptr(perm), L.ptr(scr), nbytes,
+                              L.stream()))
+    return perm
+
+
+def take_rows(agents, ids):
+    """``tree_map(lambda x: jnp.take(x, ids, axis=0), agents)`` in one launch per 32 leaves."""
+    n = ids.shape[0]
+    leaves = struct.tree_leaves(agents)
+    outs = []
+    table = []
+    for x in leaves:
+        if x.shape[0] != n:
+            raise L.FgxError("every agent leaf must have the slot axis first")
+        src = x if x.is_contiguous() else x.contiguous()
+        dst = torch.empty_like(src)
+        outs.append(dst)
+        row_bytes = src.element_size() * (src.numel() // n) if n else 0
+        table.append((src, dst, row_bytes))
+    if n:
+        for s in range(0, len(table), L.MAX_LEAVES):
+            part = table[s:s + L.MAX_LEAVES]
+            arr = (L.Leaf * len(part))()
+            for k, (src, dst, rb) in enumerate(part):
+                arr[k].src, arr[k].dst, arr[k].row_bytes = L.ptr(src), L.ptr(dst), rb
+            L.check(L.lib.fgx_gather_rows(arr, len(part), L.ptr(ids), n, L.stream()))
+    it = iter(outs)
+    return struct.tree_map(lambda x: next(it), agents)
+
+
+# agent_methods.py:74-79
+def sort_agents(quantity, ascend, agents):
+    sorted_ids = argsort(quantity, ascend)
+    return take_rows(agents, sorted_ids), sorted_ids
+
+
+jit_sort_agents = sort_agents

@@ -1,0 +1,134 @@
+// K3 (part 3): row movement of a struct-of-arrays agent pytree, and the active count.
+//
+// fgx_gather_rows is the payload half of sort_agents (agent_methods.py:77:
+// tree_map(lambda x: jnp.take(x, sorted_ids, axis=0), agents)): every leaf is
+// gathered by the same permutation in ONE launch (gridDim.y = leaf).  A row of
+// a leaf is copied in the widest vector its size and alignment allow; threads
+// of a warp copy consecutive chunks of one row (wide leaves: the per-agent RNN
+// weights, 6.4 KB rows) or consecutive rows (scalar leaves).  HBM-bound:
+// 2 * row_bytes per slot + 4 B of index.
+#include "common.cuh"
+#include "threefry.cuh"
+
+namespace fgx {
+
+struct LeafTable {
+  fgx_leaf_t leaf[FGX_MAX_LEAVES];
+  int32_t vec[FGX_MAX_LEAVES];  // bytes per copy chunk: 16 / 8 / 4 / 2 / 1
+};
+
+template <typename T>
+__device__ __forceinline__ void gather_leaf(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n) {
+  const int64_t chunks = lf.row_bytes / (int64_t)sizeof(T);
+  const int64_t total = n * chunks;
+  const T* __restrict__ src = reinterpret_cast<const T*>(lf.src);
+  T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / chunks;
+    const int64_t c = t - row * chunks;
+    int64_t s = __ldg(perm + row);
+    s = s < 0 ? 0 : (s >= n ? n - 1 : s);  // jnp.take clamps
+    dst[t] = __ldg(src + s * chunks + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ LeafTable tab,
+                                                          const int32_t* __restrict__ perm, int64_t n) {
+  const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
+  switch (tab.vec[blockIdx.y]) {
+    case 16: gather_leaf<uint4>(lf, perm, n); break;
+    case 8: gather_leaf<uint2>(lf, perm, n); break;
+    case 4: gather_leaf<uint32_t>(lf, perm, n); break;
+    case 2: gather_leaf<uint16_t>(lf, perm, n); break;
+    default: gather_leaf<uint8_t>(lf, perm, n); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) count_active_kernel(const float* __restrict__ active, int64_t n,
+                                                           int32_t* __restrict__ out) {
+  int c = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c += (int)active[i];  // sum(x, dtype=int32) converts each element first
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += ws[k];
+    if (t) atomicAdd(out, t);
+  }
+}
+
+// create_agents' argument construction (agent_methods.py:10-15)
+__global__ void __launch_bounds__(256) create_base_kernel(Key root, int64_t n_total, int64_t n_active, int32_t type,
+                                                          int32_t* __restrict__ uid, uint2* __restrict__ ckeys,
+                                                          float* __restrict__ active, int32_t* __restrict__ atype) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+    const Key ck = split_child(root, (uint32_t)(n_total + 1), (uint32_t)(i + 1));
+    uid[i] = (int32_t)i;
+    ckeys[i] = make_uint2(ck.a, ck.b);
+    active[i] = i < n_active ? 1.0f : 0.0f;
+    atype[i] = type;
+  }
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
+                    fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31), "fgx_gather_rows: n out of range");
+  FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_LEAVES, "fgx_gather_rows: at most %d leaves per call",
+              FGX_MAX_LEAVES);
+  if (n == 0 || n_leaves == 0) return FGX_OK;
+  FGX_REQUIRE(leaves_host && perm, "fgx_gather_rows: null pointer");
+  LeafTable tab;
+  int64_t max_chunks = 1;
+  for (int k = 0; k < n_leaves; ++k) {
+    const fgx_leaf_t& lf = leaves_host[k];
+    FGX_REQUIRE(lf.src && lf.dst && lf.row_bytes > 0, "fgx_gather_rows: leaf %d is malformed", k);
+    FGX_REQUIRE(lf.src != lf.dst, "fgx_gather_rows: leaf %d aliases its destination", k);
+    tab.leaf[k] = lf;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | reinterpret_cast<uintptr_t>(lf.dst) |
+                           (uintptr_t)lf.row_bytes;
+    int v = 16;
+    while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
+    tab.vec[k] = v;
+    const int64_t ch = lf.row_bytes / v;
+    if (ch > max_chunks) max_chunks = ch;
+  }
+  dim3 grid(grid_for(n * max_chunks, 256, 8), n_leaves);
+  gather_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(tab, perm, n);
+  return check_launch("fgx_gather_rows");
+}
+
+int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && out, "fgx_count_active: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int32_t), s);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_count_active: %s", cudaGetErrorString(e));
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state, "fgx_count_active: null pointer");
+  count_active_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(active_state, n, out);
+  return check_launch("fgx_count_active");
+}
+
+int fgx_create_base(const uint32_t key_host[2], int64_t n_total, int64_t n_active, int32_t agent_type,
+                    int32_t* unique_id, uint32_t* create_keys, float* active_state, int32_t* agent_types,
+                    fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(key_host, "fgx_create_base: null key");
+  FGX_REQUIRE(n_total >= 0 && n_active >= 0 && n_active <= n_total, "fgx_create_base: bad counts");
+  FGX_REQUIRE(n_total < (1ll << 30), "fgx_create_base: n_total too large for split(key, n+1)");
+  if (n_total == 0) return FGX_OK;
+  FGX_REQUIRE(unique_id && create_keys && active_state && agent_types, "fgx_create_base: null pointer");
+  create_base_kernel<<<grid_for(n_total, 256, 8), 256, 0, as_stream(stream)>>>(
+      Key{key_host[0], key_host[1]}, n_total, n_active, agent_type, unique_id, reinterpret_cast<uint2*>(create_keys),
+      active_state, agent_types);
+  return check_launch("fgx_create_base");
+}
+}

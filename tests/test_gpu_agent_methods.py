@@ -1,0 +1,203 @@
+"""K3 + Dice K2 parity through the foragax.base-shaped API (which calls the C ABI):
+G1 end to end, multi-tick churn vs the oracle, select / sort edge cases -- all bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agent_methods as oam
+from oracle import dice as odice
+from oracle import jax_random as jr
+
+pytestmark = pytest.mark.gpu
+
+G1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "g1_hello_world.json")))
+
+
+def to_np(agents):
+    c = agents.state.content
+    return {"state": {"draw": c["draw"].cpu().numpy(), "key": c["key"].cpu().numpy()},
+            "unique_id": agents.unique_id.cpu().numpy(), "agent_type": agents.agent_type.cpu().numpy(),
+            "active_state": agents.active_state.cpu().numpy(), "age": agents.age.cpu().numpy()}
+
+
+def assert_same(dev_agents, ref):
+    got = to_np(dev_agents)
+    for k in ("unique_id", "agent_type", "active_state", "age"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(got["state"]["draw"], ref["state"]["draw"])
+    np.testing.assert_array_equal(got["state"]["key"], ref["state"]["key"])
+
+
+def test_g1_end_to_end(cuda):
+    """The hello-world script of the reference (README.md:93-129), same calls, same prints."""
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples.hello_world import Dice, is_one, is_six
+
+    printed = []
+    draws = lambda s: s.agents.state.content['draw'].reshape(-1).cpu().numpy().tolist()  # noqa: E731
+    Dice_set = fgx_classes.Agent_Set(agent=Dice, num_total_agents=10, num_active_agents=5, agent_type=0)
+    Dice_set.agents = fgx_methods.create_agents(params=None, agent_set=Dice_set, key=fgx_random.PRNGKey(0))
+    printed.append(draws(Dice_set))
+    Dice_set.agents = fgx_methods.step_agents(params=None, agent_set=Dice_set, input=None)
+    printed.append(draws(Dice_set))
+    num_agents_dead, remove_indices = fgx_methods.jit_select_agents(select_func=is_one, select_params=None,
+                                                                    agents=Dice_set.agents)
+    dice_remove_params = fgx_classes.Params(content={'remove_ids': remove_indices})
+    Dice_set.agents = fgx_methods.jit_remove_agents(remove_func=Dice.remove_agent, num_agents_remove=num_agents_dead,
+                                                    remove_params=dice_remove_params, agents=Dice_set.agents)
+    printed.append(draws(Dice_set))
+    Dice_set.agents, sorted_indices = fgx_methods.jit_sort_agents(quantity=Dice_set.agents.active_state, ascend=False,
+                                                                  agents=Dice_set.agents)
+    printed.append(draws(Dice_set))
+    printed.append(Dice_set.agents.active_state.cpu().numpy().tolist())
+    num_agents_add, add_indices = fgx_methods.jit_select_agents(select_func=is_six, select_params=None,
+                                                                agents=Dice_set.agents)
+    num_active_agents = fgx_methods.count_active(Dice_set.agents)
+    num_agents_add = torch.minimum(num_agents_add, Dice_set.num_total_agents - num_active_agents)
+    Dice_set.agents, key = fgx_methods.jit_add_agents(add_func=Dice.add_agent, num_agents_add=num_agents_add,
+                                                      add_params=None, agents=Dice_set.agents, key=None)
+    printed.append(draws(Dice_set))
+    printed.append(Dice_set.agents.active_state.cpu().numpy().tolist())
+    assert printed == G1["printed"]
+    assert sorted_indices.cpu().numpy().tolist() == [0, 1, 2, 4, 3, 5, 6, 7, 8, 9]
+    assert int(num_agents_dead) == 1
+
+
+@pytest.mark.parametrize("n,n_active,sides,ticks", [(10, 5, 6, 6), (1000, 500, 6, 5), (5000, 2500, 20, 4),
+                                                    (20000, 9000, 20, 3)])
+def test_churn_ticks_match_oracle(cuda, n, n_active, sides, ticks):
+    """create -> (step -> select -> remove -> sort -> select -> clip -> add) x ticks, compared
+    leaf by leaf with the oracle after every tick."""
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples.hello_world import is_value, make_dice
+    import functools
+
+    D = make_dice(sides)
+    s = fgx_classes.Agent_Set(agent=D, num_total_agents=n, num_active_agents=n_active, agent_type=3)
+    s.agents = fgx_methods.create_agents(None, s, fgx_random.PRNGKey(n))
+    ref = oam.create_agents(functools.partial(odice.create_agent, sides=sides), None, n, n_active, 3, jr.PRNGKey(n))
+    assert_same(s.agents, ref)
+    for _ in range(ticks):
+        s.agents = fgx_methods.step_agents(None, None, s)
+        n_dead, rem = fgx_methods.jit_select_agents(is_value(1), None, s.agents)
+        s.agents = fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}),
+                                                 s.agents)
+        s.agents, _ = fgx_methods.jit_sort_agents(s.agents.active_state, False, s.agents)
+        n_add, _ = fgx_methods.jit_select_agents(is_value(sides), None, s.agents)
+        n_act = fgx_methods.count_active(s.agents)
+        n_add = torch.minimum(n_add, n - n_act)
+        s.agents, _ = fgx_methods.jit_add_agents(D.add_agent, n_add, None, s.agents, None)
+        ref = odice.churn_tick(ref, n, sides)
+        assert_same(s.agents, ref)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2047, 2048, 2049, 16384, 16385, 100003, 1 << 20])
+@pytest.mark.parametrize("frac", [0.0, 0.3, 1.0])
+def test_select_partition(cuda, n, frac):
+    import foragax_b200.base.agent_methods as fgx_methods
+    rng = np.random.default_rng(n)
+    mask = rng.random(n) < frac
+    for arr in (mask, mask.astype(np.int32) * 7, mask.astype(np.float32) * 0.5):
+        t = torch.from_numpy(arr).to(cuda)
+        cnt, perm = fgx_methods.select_agents(lambda a, p: t, None, None)
+        rc, rp = oam.select_from_mask(mask)
+        assert int(cnt) == int(rc)
+        np.testing.assert_array_equal(perm.cpu().numpy(), rp)
+
+
+def test_select_fused_predicates(cuda):
+    """The compound predicates of the reference's examples (sim.py:477-481,513-515;
+    wolf_sheep_grass/sim.ipynb select_dead_sheeps), evaluated in-kernel."""
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200.base.predicates import P
+    rng = np.random.default_rng(3)
+    n = 50021
+    active = (rng.random(n) < 0.6).astype(np.float32)
+    tb = rng.random(n).astype(np.float32) * 6
+    age = rng.random(n).astype(np.float32) * 1200
+    energy = rng.integers(-3, 5, n).astype(np.int32)
+    eaten = rng.random(n) < 0.2
+    d = lambda a: torch.from_numpy(a).to(cuda)  # noqa: E731
+    A, TB, AGE, EN, EAT = d(active), d(tb).reshape(n, 1), d(age), d(energy).reshape(n, 1), d(eaten)
+    cases = [
+        (((P(A) == 1.0) & (P(TB) > 3.0)) | (P(AGE) > 1000.0), ((active == 1.0) & (tb > 3.0)) | (age > 1000.0)),
+        ((P(A) == 1.0) & (P(TB) > 0.4), (active == 1.0) & (tb > np.float32(0.4))),
+        (((P(EN) <= 0) | P(EAT).nonzero()) & P(A).nonzero(), ((energy <= 0) | eaten) & (active != 0)),
+        (~(P(EN) == 2), energy != 2),
+    ]
+    for pred, mask in cases:
+        cnt, perm = fgx_methods.select_agents(lambda a, p: pred, None, None)
+        rc, rp = oam.select_from_mask(mask)
+        assert int(cnt) == int(rc)
+        np.testing.assert_array_equal(perm.cpu().numpy(), rp)
+
+
+@pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 50000, 1 << 20])
+@pytest.mark.parametrize("kind", ["flag", "float", "float_special", "int", "int_small", "const"])
+@pytest.mark.parametrize("ascend", [True, False])
+def test_argsort(cuda, n, kind, ascend):
+    import foragax_b200.base.agent_methods as fgx_methods
+    rng = np.random.default_rng(n + len(kind))
+    if kind == "flag":
+        q = (rng.random(n) < 0.5).astype(np.float32)
+    elif kind == "float":
+        q = rng.standard_normal(n).astype(np.float32) * 100
+    elif kind == "float_special":
+        q = rng.standard_normal(n).astype(np.float32)
+        q[rng.random(n) < 0.2] = 0.0
+        q[rng.random(n) < 0.1] = -0.0
+        q[rng.random(n) < 0.05] = np.nan
+        q[rng.random(n) < 0.05] = np.inf
+        q[rng.random(n) < 0.05] = -np.inf
+        q = np.round(q, 1)  # many ties
+    elif kind == "int":
+        q = rng.integers(-2**31, 2**31 - 1, n).astype(np.int32)
+        q[0] = -2**31
+    elif kind == "int_small":
+        q = rng.integers(0, 2, n).astype(np.int32)
+    else:
+        q = np.full(n, 3.5, np.float32)
+    got = fgx_methods.argsort(torch.from_numpy(q).to(cuda).reshape(n, 1), ascend).cpu().numpy()
+    np.testing.assert_array_equal(got, oam.sort_ids(q, ascend))
+
+
+def test_sort_agents_moves_every_leaf(cuda):
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200.base.agent_classes import Agent, Params, Policy, State
+    n = 3001
+    rng = np.random.default_rng(0)
+    leaves = {
+        "a": rng.standard_normal((n, 1)).astype(np.float32),
+        "w": rng.standard_normal((n, 40, 40)).astype(np.float32),   # 6400-byte rows
+        "k": rng.integers(0, 2**32, (n, 2), dtype=np.uint32),
+        "b": rng.random(n) < 0.5,                                   # 1-byte rows
+        "odd": rng.integers(0, 255, (n, 3)).astype(np.uint8),       # 3-byte rows
+    }
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in leaves.items()}
+    ag = Agent(params=Params(content={"w": d["w"]}), state=State(content={"a": d["a"], "k": d["k"], "b": d["b"]}),
+               unique_id=torch.arange(n, dtype=torch.int32, device=cuda), agent_type=torch.zeros(n, dtype=torch.int32, device=cuda),
+               active_state=torch.ones(n, device=cuda), age=torch.zeros(n, device=cuda),
+               policy=Policy(state=State(content={"odd": d["odd"]}), params=None, deterministic=True))
+    new, ids = fgx_methods.jit_sort_agents(ag.state.content["a"], True, ag)
+    ref_ids = oam.sort_ids(leaves["a"], True)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids)
+    np.testing.assert_array_equal(new.state.content["a"].cpu().numpy(), leaves["a"][ref_ids])
+    np.testing.assert_array_equal(new.params.content["w"].cpu().numpy(), leaves["w"][ref_ids])
+    np.testing.assert_array_equal(new.state.content["k"].cpu().numpy(), leaves["k"][ref_ids])
+    np.testing.assert_array_equal(new.state.content["b"].cpu().numpy(), leaves["b"][ref_ids])
+    np.testing.assert_array_equal(new.policy.state.content["odd"].cpu().numpy(), leaves["odd"][ref_ids])
+    np.testing.assert_array_equal(new.unique_id.cpu().numpy(), ref_ids)
+    assert new.policy.deterministic is True
+
+
+def test_non_native_callbacks_are_rejected(cuda):
+    import foragax_b200.base.agent_methods as fgx_methods
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        fgx_methods.jit_remove_agents(lambda p, a, i: a, 1, None, None)
