@@ -24,7 +24,7 @@ oracle: oracle/_build/libfgx_oracle.so
 
 oracle/_build/libfgx_oracle.so: oracle/c/fgx_oracle.c
 	@mkdir -p oracle/_build
-	gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off -fno-fast-math -o $@ $< -lm
+	gcc -O3 -mavx2 -mno-fma -fPIC -shared -fopenmp -ffp-contract=off -fno-fast-math -o $@ $< -lm
 
 ptxas-info:
 	@for f in $(SRCS); do echo "== $$f"; $(NVCC) $(NVFLAGS) -Xptxas -v -c $$f -o /dev/null 2>&1 | grep -E "Compiling|registers|spill" ; done

@@ -1,0 +1,142 @@
+"""Ray casting / wall detection -- the B200 mirror of ``foragax/base/space_methods.py:10-156``.
+
+Same names as the reference (``check_collision, wall_generator, RESOLUTION, ray_generator,
+ray_agent_sensor, ray_wall_sensor, create_space`` and their ``jit_*`` twins).  The
+reference functions handle ONE ray / ONE entity and are ``jax.vmap``-ed by the caller
+(``EcoEvoJax/sim.py:444,456,467``); here the same functions take batches -- tensors with
+leading ray / entity axes -- and run as CUDA kernels through the C ABI.  The fused
+agents x rays x walls hot loop is :func:`raycast_walls`.
+"""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .space_classes import NetworkSpace, Point, Ray, Space, Wall  # noqa: F401
+
+RESOLUTION = 9  # rays per agent; module-level knob as in the reference (space_methods.py:55)
+
+
+def _f32(x, dev=None):
+    if isinstance(x, torch.Tensor):
+        t = x.to(dtype=torch.float32)
+        if not t.is_cuda:
+            t = t.to(L.device())
+        return t.reshape(-1) if t.is_contiguous() else t.contiguous().reshape(-1)
+    return torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(-1), device=dev or L.device())
+
+
+def _wall_ptrs(walls):
+    if walls is None:
+        return None, None, None, None, 0, ()
+    x1, y1, x2, y2 = _f32(walls.p1.x), _f32(walls.p1.y), _f32(walls.p2.x), _f32(walls.p2.y)
+    return L.ptr(x1), L.ptr(y1), L.ptr(x2), L.ptr(y2), x1.shape[0], (x1, y1, x2, y2)
+
+
+# space_methods.py:10-43
+def check_collision(walls, old_position, new_position):
+    """Batched: ``old_position`` / ``new_position`` are Points of n moves -> bool[n]
+    (a single move returns a 0-d tensor, like the reference's ``jnp.any``)."""
+    ox, oy, nx, ny = _f32(old_position.x), _f32(old_position.y), _f32(new_position.x), _f32(new_position.y)
+    n = ox.shape[0]
+    out = torch.empty(n, dtype=torch.uint8, device=ox.device)
+    w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
+    L.check(L.lib.fgx_check_collision(w1, w2, w3, w4, nw, L.ptr(ox), L.ptr(oy), L.ptr(nx), L.ptr(ny), n, L.ptr(out),
+                                      L.stream()))
+    out = out.view(torch.bool)
+    return out.reshape(()) if n == 1 and not (isinstance(old_position.x, torch.Tensor) and old_position.x.dim()) else out
+
+
+jit_check_collision = check_collision
+
+
+# space_methods.py:45-53
+def wall_generator(wall_array):
+    w = np.asarray(wall_array.detach().cpu().numpy() if isinstance(wall_array, torch.Tensor) else wall_array,
+                   dtype=np.float32).reshape(-1, 2, 2)
+    dev = L.device()
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)  # noqa: E731
+    return Point(t(w[:, 0, 0]), t(w[:, 0, 1])), Point(t(w[:, 1, 0]), t(w[:, 1, 1]))
+
+
+# space_methods.py:56-69
+def ray_generator(agent_pos, ray_span, ray_length):
+    """``agent_pos = (x, y, angle)``, each ``[n]`` or ``[n,1]`` (or ``[1]`` for one agent).
+    Returns ``Ray`` with ``ray_origin`` Point [n], ``ray_direction`` Point [n, RESOLUTION]."""
+    x, y, ang = (_f32(a) for a in agent_pos)
+    n = ang.shape[0]
+    dx = torch.empty((n, RESOLUTION), dtype=torch.float32, device=ang.device)
+    dy = torch.empty_like(dx)
+    L.check(L.lib.fgx_ray_generator(L.ptr(ang), n, RESOLUTION, float(ray_span), L.ptr(dx), L.ptr(dy), L.stream()))
+    return Ray(Point(x, y), Point(dx, dy), float(ray_length))
+
+
+jit_ray_generator = ray_generator
+
+
+def _flat_rays(ray):
+    dx, dy = ray.ray_direction.x, ray.ray_direction.y
+    lead = tuple(dx.shape)
+    ox, oy = ray.ray_origin.x, ray.ray_origin.y
+    if dx.dim() == 2 and ox.numel() == dx.shape[0]:
+        ox = ox.reshape(-1, 1).expand_as(dx)
+        oy = oy.reshape(-1, 1).expand_as(dy)
+    return _f32(ox), _f32(oy), _f32(dx), _f32(dy), lead
+
+
+# space_methods.py:71-94
+def ray_agent_sensor(ray, data):
+    """Batched: rays [...], entities ``data = (x, y, rad, active)`` each [E] -> float32[..., E]."""
+    ox, oy, dx, dy, lead = _flat_rays(ray)
+    ex, ey, er, ea = (_f32(d) for d in data)
+    m, e = dx.shape[0], ex.shape[0]
+    out = torch.empty((m, e), dtype=torch.float32, device=dx.device)
+    L.check(L.lib.fgx_ray_agent_sensor(L.ptr(ox), L.ptr(oy), L.ptr(dx), L.ptr(dy), m, float(ray.ray_length),
+                                       L.ptr(ex), L.ptr(ey), L.ptr(er), L.ptr(ea), e, L.ptr(out), L.stream()))
+    return out.reshape(lead + (e,))
+
+
+jit_ray_agent_sensor = ray_agent_sensor
+
+
+# space_methods.py:96-143
+def ray_wall_sensor(ray, data):
+    """Batched: rays [...], walls ``data = (p1x, p1y, p2x, p2y)`` each [W] -> float32[..., W]."""
+    ox, oy, dx, dy, lead = _flat_rays(ray)
+    w1, w2, w3, w4 = (_f32(d) for d in data)
+    m, w = dx.shape[0], w1.shape[0]
+    out = torch.empty((m, w), dtype=torch.float32, device=dx.device)
+    L.check(L.lib.fgx_ray_wall_sensor(L.ptr(ox), L.ptr(oy), L.ptr(dx), L.ptr(dy), m, float(ray.ray_length),
+                                      L.ptr(w1), L.ptr(w2), L.ptr(w3), L.ptr(w4), w, L.ptr(out), L.stream()))
+    return out.reshape(lead + (w,))
+
+
+jit_ray_wall_sensor = ray_wall_sensor
+
+
+# space_methods.py:146-156
+def create_space(x_min, x_max, y_min, y_max, torous, wall_array):
+    if wall_array is None:
+        return Space(x_min, x_max, y_min, y_max, torous, None)
+    wall_begin_points, wall_end_points = wall_generator(wall_array)
+    return Space(x_min, x_max, y_min, y_max, torous, Wall(wall_begin_points, wall_end_points))
+
+
+def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_rays=None, want_hit=True,
+                  out=None):
+    """The fused hot loop: ``ray_generator`` + ``ray_wall_sensor`` over agents x rays x walls,
+    reduced per ray to (min distance, first wall index attaining it or -1) -- what
+    ``EcoEvoJax/sim.py:418-457`` computes for wall entities.  Returns
+    ``(dist float32[n,R], hit int32[n,R] | None)``; inactive agents get zeros / -1."""
+    x, y, ang = (_f32(a) for a in agent_pos)
+    n = x.shape[0]
+    r = int(RESOLUTION if n_rays is None else n_rays)
+    act = None if active_state is None else _f32(active_state)
+    if out is None:
+        dist = torch.empty((n, r), dtype=torch.float32, device=x.device)
+        hit = torch.empty((n, r), dtype=torch.int32, device=x.device) if want_hit else None
+    else:
+        dist, hit = out
+    w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
+    L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
+                                    float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))
+    return dist, hit

@@ -1,0 +1,396 @@
+// K1: ray casting -- agents x rays against wall segments.
+//
+// Reference: space_methods.py:56-69 (ray_generator), :96-143 (ray_wall_sensor), and the
+// min / first-argmin / "-1 if min >= L" reduction of the example-level composition
+// (examples/.../EcoEvoJax/sim.py:444-447).  Work = agents x rays x walls intersection
+// tests; FP32/issue bound (walls live in shared memory, 16 B/agent in, 8 B/(agent,ray) out).
+//
+// Kernel design (sm_100a)
+//  * wall segments are bulk-copied global -> shared with cp.async.bulk (TMA, completion on
+//    an mbarrier), then re-laid out once per CTA as float4 (p2x,p2y,q2x,q2y) + float2
+//    (q2-p2), so the inner loop issues one LDS.128 + one LDS.64 per wall (warp broadcast);
+//  * a thread owns RPT rays of one agent (q1 and q1-p1 in registers); per wall the
+//    agent-only determinant o3 is computed once and amortised over the RPT rays; o4
+//    reuses the two differences of o2 (fp negation is exact), so a test costs 13 rounded
+//    FP32 ops + 3 products + the sign/zero test;
+//  * every (ray, wall) pair evaluates all four orientation determinants.  A pair is a
+//    *candidate* unless the signs prove a miss: max(o1*o2, o3*o4) > 0 and no zero / NaN
+//    among them -- exactly the negation of c1||c2||c3||c4||c5 (space_methods.py:127-140).
+//    Candidates (a fraction of a percent) are queued per thread in shared memory and
+//    resolved after the scan by the op-for-op restatement ray_wall_exact(), in ascending
+//    wall order with a strict '<', which is jnp.argmin's first-minimum rule;
+//  * no FMA contraction anywhere (file compiled with -fmad=false, predicates use __f*_rn).
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace fgx {
+
+constexpr int RC_BLOCK = 256;
+constexpr int RC_CHUNK = 2048;  // walls resident in shared memory at a time
+constexpr int RC_QCAP = 16;     // queued candidate walls per thread before a flush
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FGX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FGX_DONE;\n"
+      "bra FGX_WAIT;\n"
+      "FGX_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared (SASS: UBLKCP); bytes % 16 == 0, both sides 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WallsSoA {
+  const float* x1;
+  const float* y1;
+  const float* x2;
+  const float* y2;
+};
+
+// Stage walls [base, base+cnt) into shared memory: TMA bulk copy of the four SoA rows into
+// `stage`, then one pass re-laying them out as wall4 / wdir.  Called by all threads.
+__device__ __forceinline__ void stage_walls(const WallsSoA& w, int64_t base, int cnt, bool tma_ok, float* stage,
+                                            float4* wall4, float2* wdir, uint64_t* bar, uint32_t& parity) {
+  const int vec = tma_ok ? (cnt & ~3) : 0;  // part moved by TMA (multiple of 16 bytes)
+  if (vec > 0 && threadIdx.x == 0) {
+    mbar_expect_tx(bar, 4u * vec * 4u);
+    tma_bulk_g2s(stage + 0 * RC_CHUNK, w.x1 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 1 * RC_CHUNK, w.y1 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 2 * RC_CHUNK, w.x2 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 3 * RC_CHUNK, w.y2 + base, vec * 4u, bar);
+  }
+  for (int i = vec + threadIdx.x; i < cnt; i += blockDim.x) {  // tail / unaligned fallback
+    stage[0 * RC_CHUNK + i] = __ldg(w.x1 + base + i);
+    stage[1 * RC_CHUNK + i] = __ldg(w.y1 + base + i);
+    stage[2 * RC_CHUNK + i] = __ldg(w.x2 + base + i);
+    stage[3 * RC_CHUNK + i] = __ldg(w.y2 + base + i);
+  }
+  if (vec > 0) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float ax = stage[i], ay = stage[RC_CHUNK + i], bx = stage[2 * RC_CHUNK + i], by = stage[3 * RC_CHUNK + i];
+    wall4[i] = make_float4(ax, ay, bx, by);
+    wdir[i] = make_float2(f_sub(bx, ax), f_sub(by, ay));
+  }
+  __syncthreads();
+}
+
+template <int RPT>
+struct RaySet {
+  float p1x, p1y, L;
+  float q1x[RPT], q1y[RPT], rx[RPT], ry[RPT];
+  float best[RPT];
+  int hit[RPT];
+};
+
+// resolve queued candidate walls exactly, in ascending wall order
+template <int RPT>
+__device__ __noinline__ void flush_queue(RaySet<RPT>& r, const uint32_t* q, int qn, const float4* wall4,
+                                         int64_t chunk_base) {
+  for (int e = 0; e < qn; ++e) {
+    const int wl = (int)q[e * RC_BLOCK];
+    const float4 w = wall4[wl];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float d = ray_wall_exact(r.p1x, r.p1y, r.q1x[j], r.q1y[j], r.L, w.x, w.y, w.z, w.w);
+      if (d < r.best[j]) {
+        r.best[j] = d;
+        r.hit[j] = (int)(chunk_base + wl);
+      }
+    }
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(RC_BLOCK)
+    raycast_walls_kernel(const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ aang,
+                         const float* __restrict__ aactive, int64_t n_agents, int n_rays, float span, float L,
+                         WallsSoA walls, int64_t n_walls, int tma_ok, float* __restrict__ dist,
+                         int32_t* __restrict__ hit) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage = reinterpret_cast<float*>(smem_raw + 16);
+  float4* wall4 = reinterpret_cast<float4*>(stage + 4 * RC_CHUNK);
+  float2* wdir = reinterpret_cast<float2*>(wall4 + RC_CHUNK);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(wdir + RC_CHUNK) + threadIdx.x;  // [RC_QCAP][RC_BLOCK]
+
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  uint32_t parity = 0;
+
+  const int groups = (n_rays + RPT - 1) / RPT;  // ray groups per agent
+  const int64_t total = n_agents * groups;
+  const int64_t num_tiles = (total + RC_BLOCK - 1) / RC_BLOCK;
+  const int n_chunks = (int)((n_walls + RC_CHUNK - 1) / RC_CHUNK);
+  if (n_chunks == 1) stage_walls(walls, 0, (int)n_walls, tma_ok, stage, wall4, wdir, bar, parity);
+
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t task = tile * RC_BLOCK + threadIdx.x;
+    const bool valid = task < total;
+    const int64_t agent = valid ? task / groups : 0;
+    const int ray0 = valid ? (int)(task - agent * groups) * RPT : 0;
+    const bool act = valid && (aactive == nullptr || aactive[agent] != 0.0f);
+
+    RaySet<RPT> r;
+    r.L = L;
+    r.p1x = valid ? ax[agent] : 0.0f;
+    r.p1y = valid ? ay[agent] : 0.0f;
+    {
+      // ray_generator (space_methods.py:56-69)
+      const float ang = valid ? aang[agent] : 0.0f;
+      const float lo = f_sub(ang, span), hi = f_add(ang, span);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int rj = min(ray0 + j, n_rays - 1);
+        float s, c;
+        sincosf(linspace_elem(lo, hi, n_rays, rj), &s, &c);
+        r.q1x[j] = f_add(r.p1x, f_mul(c, L));
+        r.q1y[j] = f_add(r.p1y, f_mul(s, L));
+        r.rx[j] = f_sub(r.q1x[j], r.p1x);
+        r.ry[j] = f_sub(r.q1y[j], r.p1y);
+        r.best[j] = L;
+        r.hit[j] = -1;
+      }
+    }
+
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int64_t base = (int64_t)ch * RC_CHUNK;
+      const int cnt = (int)min((int64_t)RC_CHUNK, n_walls - base);
+      if (n_chunks > 1) {
+        __syncthreads();  // everyone done with the previous chunk
+        stage_walls(walls, base, cnt, tma_ok, stage, wall4, wdir, bar, parity);
+      }
+      if (act) {
+        int qn = 0;
+#pragma unroll 2
+        for (int w = 0; w < cnt; ++w) {
+          const float4 wl = wall4[w];
+          const float2 wd = wdir[w];
+          // o3 = orientation(p2, q2, p1): agent-only, shared by the thread's rays
+          const float o3 = f_sub(f_mul(wd.y, f_sub(r.p1x, wl.z)), f_mul(wd.x, f_sub(r.p1y, wl.w)));
+          bool cand = false;
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) {
+            const float a = f_sub(wl.x, r.q1x[j]), b = f_sub(wl.y, r.q1y[j]);
+            const float o1 = f_sub(f_mul(r.ry[j], a), f_mul(r.rx[j], b));
+            const float u = f_sub(wl.z, r.q1x[j]), v = f_sub(wl.w, r.q1y[j]);
+            const float o2 = f_sub(f_mul(r.ry[j], u), f_mul(r.rx[j], v));
+            // o4 = wy*(q1x-q2x) - wx*(q1y-q2y) == wx*v - wy*u bit for bit (negation is exact)
+            const float o4 = f_sub(f_mul(wd.x, v), f_mul(wd.y, u));
+            const float A = f_mul(o1, o2), B = f_mul(o3, o4);
+            // sure miss <=> one pair has equal non-zero signs and nothing is zero / NaN
+            const bool miss = (fmaxf(A, B) > 0.0f) && (fabsf(f_mul(A, B)) > 0.0f);
+            cand |= !miss;
+          }
+          if (cand) {
+            queue[qn * RC_BLOCK] = (uint32_t)w;
+            if (++qn == RC_QCAP) {
+              flush_queue<RPT>(r, queue, qn, wall4, base);
+              qn = 0;
+            }
+          }
+        }
+        if (qn) flush_queue<RPT>(r, queue, qn, wall4, base);
+      }
+    }
+
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int rj = ray0 + j;
+        if (rj < n_rays) {
+          const int64_t o = agent * n_rays + rj;
+          // inactive agents sense nothing: zeros (sim.py:459-460), hit -1
+          dist[o] = act ? r.best[j] : 0.0f;
+          if (hit) hit[o] = act ? r.hit[j] : -1;
+        }
+      }
+    }
+  }
+}
+
+static size_t raycast_smem_bytes() {
+  return 16 + (size_t)RC_CHUNK * (16 + 16 + 8) + (size_t)RC_QCAP * RC_BLOCK * 4;
+}
+
+template <int RPT>
+static int launch_raycast(const float* x, const float* y, const float* ang, const float* active, int64_t n,
+                          int n_rays, float span, float L, WallsSoA w, int64_t n_walls, float* dist, int32_t* hit,
+                          cudaStream_t s) {
+  const size_t smem = raycast_smem_bytes();
+  auto kern = raycast_walls_kernel<RPT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls: %s", cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RC_BLOCK, smem);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int groups = (n_rays + RPT - 1) / RPT;
+  const int64_t tiles = ceil_div(n * groups, RC_BLOCK);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(w.x1) | reinterpret_cast<uintptr_t>(w.y1) |
+                       reinterpret_cast<uintptr_t>(w.x2) | reinterpret_cast<uintptr_t>(w.y2);
+  const int tma_ok = (al & 15) == 0;
+  kern<<<grid, RC_BLOCK, smem, s>>>(x, y, ang, active, n, n_rays, span, L, w, n_walls, tma_ok, dist, hit);
+  return check_launch("fgx_raycast_walls");
+}
+
+// ---- element-wise mirrors of the jit_* helpers (unit-level parity; not the hot loop) ----
+__global__ void __launch_bounds__(256) ray_generator_kernel(const float* __restrict__ ang, int64_t n, int n_rays,
+                                                            float span, float* __restrict__ dx,
+                                                            float* __restrict__ dy) {
+  const int64_t total = n * n_rays;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = t / n_rays;
+    const int j = (int)(t - a * n_rays);
+    const float g = ang[a];
+    float s, c;
+    sincosf(linspace_elem(f_sub(g, span), f_add(g, span), n_rays, j), &s, &c);
+    dx[t] = c;
+    dy[t] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) ray_wall_sensor_kernel(const float* __restrict__ ox, const float* __restrict__ oy,
+                                                              const float* __restrict__ dx, const float* __restrict__ dy,
+                                                              int64_t m, float L, WallsSoA w, int64_t n_walls,
+                                                              float* __restrict__ out) {
+  const int64_t total = m * n_walls;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n_walls, k = t - i * n_walls;
+    const float px = ox[i], py = oy[i];
+    const float qx = f_add(px, f_mul(dx[i], L)), qy = f_add(py, f_mul(dy[i], L));
+    out[t] = ray_wall_exact(px, py, qx, qy, L, w.x1[k], w.y1[k], w.x2[k], w.y2[k]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ray_agent_sensor_kernel(const float* __restrict__ ox, const float* __restrict__ oy,
+                                                               const float* __restrict__ dx, const float* __restrict__ dy,
+                                                               int64_t m, float L, const float* __restrict__ ex,
+                                                               const float* __restrict__ ey, const float* __restrict__ er,
+                                                               const float* __restrict__ eact, int64_t n_ent,
+                                                               float* __restrict__ out) {
+  const int64_t total = m * n_ent;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n_ent, k = t - i * n_ent;
+    out[t] = ray_agent_exact(ox[i], oy[i], dx[i], dy[i], L, ex[k], ey[k], er[k], eact[k]);
+  }
+}
+
+// check_collision (space_methods.py:10-43): one warp per move, lanes stride the walls, ballot = any()
+__global__ void __launch_bounds__(256) check_collision_kernel(WallsSoA w, int64_t n_walls, const float* __restrict__ oldx,
+                                                              const float* __restrict__ oldy,
+                                                              const float* __restrict__ newx,
+                                                              const float* __restrict__ newy, int64_t m,
+                                                              uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < m; i += nwarps) {
+    const float px = oldx[i], py = oldy[i], qx = newx[i], qy = newy[i];
+    bool any = false;
+    for (int64_t k = lane; k < n_walls; k += 32)
+      any |= segments_intersect(w.x1[k], w.y1[k], w.x2[k], w.y2[k], px, py, qx, qy);
+    const unsigned b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) out[i] = b ? 1 : 0;
+  }
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+int fgx_raycast_walls(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
+                      int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                      const float* wx2, const float* wy2, int64_t n_walls, float* dist, int32_t* hit,
+                      fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_agents >= 0 && n_walls >= 0, "fgx_raycast_walls: negative size");
+  FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls: n_rays must be > 0");
+  FGX_REQUIRE(n_walls < (1ll << 31), "fgx_raycast_walls: too many walls");
+  if (n_agents == 0) return FGX_OK;
+  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls: null pointer");
+  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_raycast_walls: null wall array");
+  WallsSoA w{wx1, wy1, wx2, wy2};
+  cudaStream_t s = as_stream(stream);
+  // rays per thread: the largest group size that divides the ray count well
+  if (n_rays % 8 == 0) return launch_raycast<8>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+  if (n_rays % 4 == 0) return launch_raycast<4>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+  if (n_rays % 3 == 0) return launch_raycast<3>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+  if (n_rays % 2 == 0) return launch_raycast<2>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+  if (n_rays >= 5) return launch_raycast<4>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+  return launch_raycast<1>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+}
+
+int fgx_ray_generator(const float* ang, int64_t n, int32_t n_rays, float ray_span, float* dir_x, float* dir_y,
+                      fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && n_rays > 0, "fgx_ray_generator: bad sizes");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(ang && dir_x && dir_y, "fgx_ray_generator: null pointer");
+  ray_generator_kernel<<<grid_for(n * n_rays, 256, 8), 256, 0, as_stream(stream)>>>(ang, n, n_rays, ray_span, dir_x,
+                                                                                  dir_y);
+  return check_launch("fgx_ray_generator");
+}
+
+int fgx_ray_wall_sensor(const float* ox, const float* oy, const float* dx, const float* dy, int64_t n_rays_total,
+                        float ray_length, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
+                        int64_t n_walls, float* out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_rays_total >= 0 && n_walls >= 0, "fgx_ray_wall_sensor: negative size");
+  if (n_rays_total == 0 || n_walls == 0) return FGX_OK;
+  FGX_REQUIRE(ox && oy && dx && dy && wx1 && wy1 && wx2 && wy2 && out, "fgx_ray_wall_sensor: null pointer");
+  WallsSoA w{wx1, wy1, wx2, wy2};
+  ray_wall_sensor_kernel<<<grid_for(n_rays_total * n_walls, 256, 8), 256, 0, as_stream(stream)>>>(
+      ox, oy, dx, dy, n_rays_total, ray_length, w, n_walls, out);
+  return check_launch("fgx_ray_wall_sensor");
+}
+
+int fgx_ray_agent_sensor(const float* ox, const float* oy, const float* dx, const float* dy, int64_t n_rays_total,
+                         float ray_length, const float* ex, const float* ey, const float* erad, const float* eactive,
+                         int64_t n_entities, float* out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_rays_total >= 0 && n_entities >= 0, "fgx_ray_agent_sensor: negative size");
+  if (n_rays_total == 0 || n_entities == 0) return FGX_OK;
+  FGX_REQUIRE(ox && oy && dx && dy && ex && ey && erad && eactive && out, "fgx_ray_agent_sensor: null pointer");
+  ray_agent_sensor_kernel<<<grid_for(n_rays_total * n_entities, 256, 8), 256, 0, as_stream(stream)>>>(
+      ox, oy, dx, dy, n_rays_total, ray_length, ex, ey, erad, eactive, n_entities, out);
+  return check_launch("fgx_ray_agent_sensor");
+}
+
+int fgx_check_collision(const float* wx1, const float* wy1, const float* wx2, const float* wy2, int64_t n_walls,
+                        const float* old_x, const float* old_y, const float* new_x, const float* new_y, int64_t n,
+                        uint8_t* out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && n_walls >= 0, "fgx_check_collision: negative size");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(old_x && old_y && new_x && new_y && out, "fgx_check_collision: null pointer");
+  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_check_collision: null wall array");
+  WallsSoA w{wx1, wy1, wx2, wy2};
+  check_collision_kernel<<<grid_for(n * 32, 256, 8), 256, 0, as_stream(stream)>>>(w, n_walls, old_x, old_y, new_x,
+                                                                                 new_y, n, out);
+  return check_launch("fgx_check_collision");
+}
+}

@@ -113,6 +113,39 @@ int fgx_create_base(const uint32_t key_host[2], int64_t n_total, int64_t n_activ
                     int32_t* unique_id, uint32_t* create_keys, float* active_state, int32_t* agent_types,
                     fgx_stream_t stream);
 
+/* ---- K1: ray casting (space_methods.py) ---------------------------------- */
+/* Walls are struct-of-arrays float32[n_walls]: (wx1,wy1) = Wall.p1, (wx2,wy2) = Wall.p2
+ * (space_classes.py:15-20, wall_generator space_methods.py:45-53).               */
+/* The agents x rays x walls hot loop: ray_generator (space_methods.py:56-69) +
+ * ray_wall_sensor (space_methods.py:96-143) for every (agent, ray, wall), reduced per ray
+ * as the example-level composition does (EcoEvoJax/sim.py:444-447): dist float32[n,R] =
+ * min over walls (ray_length if none), hit int32[n,R] = first wall index attaining it,
+ * -1 if dist >= ray_length (hit may be NULL).  x, y, ang float32[n]; active float32[n] or
+ * NULL: inactive agents get dist 0 and hit -1 (sim.py:459-460).                    */
+int fgx_raycast_walls(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
+                      int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                      const float* wx2, const float* wy2, int64_t n_walls, float* dist, int32_t* hit,
+                      fgx_stream_t stream);
+/* ray_generator (space_methods.py:56-69), directions only: dir_x, dir_y float32[n, n_rays]
+ * = cos / sin of linspace(ang - span, ang + span, n_rays).                          */
+int fgx_ray_generator(const float* ang, int64_t n, int32_t n_rays, float ray_span, float* dir_x, float* dir_y,
+                      fgx_stream_t stream);
+/* jit_ray_wall_sensor (space_methods.py:96-143) vmapped over rays x walls:
+ * out float32[n_rays_total, n_walls]; ray i = origin (ox,oy)[i], direction (dx,dy)[i].   */
+int fgx_ray_wall_sensor(const float* ox, const float* oy, const float* dx, const float* dy, int64_t n_rays_total,
+                        float ray_length, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
+                        int64_t n_walls, float* out, fgx_stream_t stream);
+/* jit_ray_agent_sensor (space_methods.py:71-94) vmapped over rays x entities
+ * (ex, ey, erad, eactive float32[n_entities]): out float32[n_rays_total, n_entities].    */
+int fgx_ray_agent_sensor(const float* ox, const float* oy, const float* dx, const float* dy, int64_t n_rays_total,
+                         float ray_length, const float* ex, const float* ey, const float* erad, const float* eactive,
+                         int64_t n_entities, float* out, fgx_stream_t stream);
+/* jit_check_collision (space_methods.py:10-43) vmapped over n moves old->new:
+ * out uint8[n] = any wall intersects the move segment.                               */
+int fgx_check_collision(const float* wx1, const float* wy1, const float* wx2, const float* wy2, int64_t n_walls,
+                        const float* old_x, const float* old_y, const float* new_x, const float* new_y, int64_t n,
+                        uint8_t* out, fgx_stream_t stream);
+
 /* ---- K2: hello-world Dice agent (README.md:35-129) ---------------------- */
 /* Leaves: draw int32[n] (state.content['draw'], shape [n,1]), key uint32[n,2],
  * unique_id int32[n], agent_type int32[n], active_state float32[n], age float32[n].

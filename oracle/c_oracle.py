@@ -1,0 +1,55 @@
+"""ctypes loader of the C oracle (``oracle/c/fgx_oracle.c`` -> ``oracle/_build/libfgx_oracle.so``).
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``): the multi-threaded CPU baseline timed by
+``bench.py`` and a second checker for the geometry.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "libfgx_oracle.so")
+
+
+def build():
+    import subprocess
+    os.makedirs(os.path.join(_HERE, "_build"), exist_ok=True)
+    subprocess.check_call(["gcc", "-O3", "-mavx2", "-mno-fma", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+                           "-fno-fast-math", "-o", LIB, os.path.join(_HERE, "c", "fgx_oracle.c"), "-lm"])
+
+
+def load():
+    if not os.path.exists(LIB):
+        build()
+    lib = C.CDLL(LIB)
+    lib.fgx_oracle_threads.restype = C.c_int
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def raycast_walls(x, y, ang, active, n_rays, span, length, w1x, w1y, w2x, w2y, want_hit=True):
+    lib = load()
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32).reshape(-1)  # noqa: E731
+    x, y, ang, active, w1x, w1y, w2x, w2y = (f(a) for a in (x, y, ang, active, w1x, w1y, w2x, w2y))
+    n = x.shape[0]
+    dist = np.empty((n, n_rays), np.float32)
+    hit = np.empty((n, n_rays), np.int32) if want_hit else None
+    lib.fgx_oracle_raycast_walls(_p(x), _p(y), _p(ang), _p(active), C.c_int64(n), C.c_int(n_rays), C.c_float(span),
+                                 C.c_float(length), _p(w1x), _p(w1y), _p(w2x), _p(w2y), C.c_int64(w1x.shape[0]),
+                                 _p(dist), _p(hit))
+    return dist, hit
+
+
+def dice_step(sides, active, draw, key, age):
+    """In place on contiguous arrays: draw int32[n], key uint32[n,2], age float32[n]."""
+    lib = load()
+    n = active.shape[0]
+    lib.fgx_oracle_dice_step(C.c_int64(n), C.c_int(sides), _p(active), _p(draw), _p(key), _p(age))
+
+
+def threads():
+    return load().fgx_oracle_threads()
