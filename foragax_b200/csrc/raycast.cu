@@ -20,13 +20,15 @@
 //    resolved after the scan by the op-for-op restatement ray_wall_exact(), in ascending
 //    wall order with a strict '<', which is jnp.argmin's first-minimum rule;
 //  * no FMA contraction anywhere (file compiled with -fmad=false, predicates use __f*_rn).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "geometry.cuh"
 
 namespace fgx {
 
 constexpr int RC_BLOCK = 256;
-constexpr int RC_CHUNK = 2048;  // walls resident in shared memory at a time
+constexpr int RC_CHUNK = 2048;  // max walls resident in shared memory at a time
 constexpr int RC_QCAP = 16;     // queued candidate walls per thread before a flush
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,22 +69,25 @@ struct WallsSoA {
 };
 
 // Stage walls [base, base+cnt) into shared memory: TMA bulk copy of the four SoA rows into
-// `stage`, then one pass re-laying them out as wall4 / wdir.  Called by all threads.
-__device__ __forceinline__ void stage_walls(const WallsSoA& w, int64_t base, int cnt, bool tma_ok, float* stage,
-                                            float4* wall4, float2* wdir, uint64_t* bar, uint32_t& parity) {
+// `stage` (row stride `chunk`), then one pass re-laying them out as
+//   wall4[i] = (p2x, p2y, q2x, q2y)       wdir[i] = (-(q2y-p2y), q2x-p2x)
+// the operand pairs of the packed f32x2 inner loop.  Called by all threads.
+__device__ __forceinline__ void stage_walls(const WallsSoA& w, int64_t base, int cnt, int chunk, bool tma_ok,
+                                            float* stage, float4* wall4, float2* wdir, uint64_t* bar,
+                                            uint32_t& parity) {
   const int vec = tma_ok ? (cnt & ~3) : 0;  // part moved by TMA (multiple of 16 bytes)
   if (vec > 0 && threadIdx.x == 0) {
     mbar_expect_tx(bar, 4u * vec * 4u);
-    tma_bulk_g2s(stage + 0 * RC_CHUNK, w.x1 + base, vec * 4u, bar);
-    tma_bulk_g2s(stage + 1 * RC_CHUNK, w.y1 + base, vec * 4u, bar);
-    tma_bulk_g2s(stage + 2 * RC_CHUNK, w.x2 + base, vec * 4u, bar);
-    tma_bulk_g2s(stage + 3 * RC_CHUNK, w.y2 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 0 * chunk, w.x1 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 1 * chunk, w.y1 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 2 * chunk, w.x2 + base, vec * 4u, bar);
+    tma_bulk_g2s(stage + 3 * chunk, w.y2 + base, vec * 4u, bar);
   }
   for (int i = vec + threadIdx.x; i < cnt; i += blockDim.x) {  // tail / unaligned fallback
-    stage[0 * RC_CHUNK + i] = __ldg(w.x1 + base + i);
-    stage[1 * RC_CHUNK + i] = __ldg(w.y1 + base + i);
-    stage[2 * RC_CHUNK + i] = __ldg(w.x2 + base + i);
-    stage[3 * RC_CHUNK + i] = __ldg(w.y2 + base + i);
+    stage[0 * chunk + i] = __ldg(w.x1 + base + i);
+    stage[1 * chunk + i] = __ldg(w.y1 + base + i);
+    stage[2 * chunk + i] = __ldg(w.x2 + base + i);
+    stage[3 * chunk + i] = __ldg(w.y2 + base + i);
   }
   if (vec > 0) {
     mbar_wait(bar, parity);
@@ -90,31 +95,34 @@ __device__ __forceinline__ void stage_walls(const WallsSoA& w, int64_t base, int
   }
   __syncthreads();
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const float ax = stage[i], ay = stage[RC_CHUNK + i], bx = stage[2 * RC_CHUNK + i], by = stage[3 * RC_CHUNK + i];
+    const float ax = stage[i], ay = stage[chunk + i], bx = stage[2 * chunk + i], by = stage[3 * chunk + i];
     wall4[i] = make_float4(ax, ay, bx, by);
-    wdir[i] = make_float2(f_sub(bx, ax), f_sub(by, ay));
+    wdir[i] = make_float2(-f_sub(by, ay), f_sub(bx, ax));
   }
-  __syncthreads();
+  __syncthreads();  // also: `stage` is free again (it doubles as the candidate queue)
 }
 
+// Per-thread ray state, laid out as the f32x2 operand pairs of the inner loop.
 template <int RPT>
 struct RaySet {
   float p1x, p1y, L;
-  float q1x[RPT], q1y[RPT], rx[RPT], ry[RPT];
+  float2 nq1[RPT];  // (-q1x, -q1y): ray end point, negated (negation is exact)
+  float2 rr[RPT];   // (q1y-p1y, -(q1x-p1x))
   float best[RPT];
   int hit[RPT];
 };
 
-// resolve queued candidate walls exactly, in ascending wall order
+// Resolve queued candidate walls exactly, in ascending wall order.  Inlined (one call site):
+// the ray state must stay in registers, so it is never passed by reference to a real call.
 template <int RPT>
-__device__ __noinline__ void flush_queue(RaySet<RPT>& r, const uint32_t* q, int qn, const float4* wall4,
-                                         int64_t chunk_base) {
+__device__ __forceinline__ void flush_queue(RaySet<RPT>& r, const uint32_t* q, int qn, const float4* wall4,
+                                            int64_t chunk_base) {
   for (int e = 0; e < qn; ++e) {
     const int wl = (int)q[e * RC_BLOCK];
     const float4 w = wall4[wl];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      const float d = ray_wall_exact(r.p1x, r.p1y, r.q1x[j], r.q1y[j], r.L, w.x, w.y, w.z, w.w);
+      const float d = ray_wall_exact(r.p1x, r.p1y, -r.nq1[j].x, -r.nq1[j].y, r.L, w.x, w.y, w.z, w.w);
       if (d < r.best[j]) {
         r.best[j] = d;
         r.hit[j] = (int)(chunk_base + wl);
@@ -123,18 +131,27 @@ __device__ __noinline__ void flush_queue(RaySet<RPT>& r, const uint32_t* q, int 
   }
 }
 
-template <int RPT>
-__global__ void __launch_bounds__(RC_BLOCK)
+// Blackwell packed FP32 (SASS FADD2 / FMUL2): two correctly rounded ops per issue slot
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
+// sure miss <=> one pair has equal non-zero signs and nothing is zero / NaN  (C = A*B)
+__device__ __forceinline__ bool sure_miss(float A, float B, float C) {
+  return (fmaxf(A, B) > 0.0f) && (fabsf(C) > 0.0f);
+}
+
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(RC_BLOCK, MINB)
     raycast_walls_kernel(const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ aang,
                          const float* __restrict__ aactive, int64_t n_agents, int n_rays, float span, float L,
-                         WallsSoA walls, int64_t n_walls, int tma_ok, float* __restrict__ dist,
+                         WallsSoA walls, int64_t n_walls, int chunk, int tma_ok, float* __restrict__ dist,
                          int32_t* __restrict__ hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  float* stage = reinterpret_cast<float*>(smem_raw + 16);
-  float4* wall4 = reinterpret_cast<float4*>(stage + 4 * RC_CHUNK);
-  float2* wdir = reinterpret_cast<float2*>(wall4 + RC_CHUNK);
-  uint32_t* queue = reinterpret_cast<uint32_t*>(wdir + RC_CHUNK) + threadIdx.x;  // [RC_QCAP][RC_BLOCK]
+  float4* wall4 = reinterpret_cast<float4*>(smem_raw + 16);
+  float2* wdir = reinterpret_cast<float2*>(wall4 + chunk);
+  float* stage = reinterpret_cast<float*>(wdir + chunk);                   // [4][chunk], staging only
+  uint32_t* queue = reinterpret_cast<uint32_t*>(stage) + threadIdx.x;      // [RC_QCAP][RC_BLOCK], scan only
 
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
@@ -143,8 +160,8 @@ __global__ void __launch_bounds__(RC_BLOCK)
   const int groups = (n_rays + RPT - 1) / RPT;  // ray groups per agent
   const int64_t total = n_agents * groups;
   const int64_t num_tiles = (total + RC_BLOCK - 1) / RC_BLOCK;
-  const int n_chunks = (int)((n_walls + RC_CHUNK - 1) / RC_CHUNK);
-  if (n_chunks == 1) stage_walls(walls, 0, (int)n_walls, tma_ok, stage, wall4, wdir, bar, parity);
+  const int n_chunks = (int)((n_walls + chunk - 1) / chunk);
+  if (n_chunks == 1) stage_walls(walls, 0, (int)n_walls, chunk, tma_ok, stage, wall4, wdir, bar, parity);
 
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t task = tile * RC_BLOCK + threadIdx.x;
@@ -157,6 +174,7 @@ __global__ void __launch_bounds__(RC_BLOCK)
     r.L = L;
     r.p1x = valid ? ax[agent] : 0.0f;
     r.p1y = valid ? ay[agent] : 0.0f;
+    const float2 np1 = make_float2(-r.p1x, -r.p1y);
     {
       // ray_generator (space_methods.py:56-69)
       const float ang = valid ? aang[agent] : 0.0f;
@@ -166,53 +184,81 @@ __global__ void __launch_bounds__(RC_BLOCK)
         const int rj = min(ray0 + j, n_rays - 1);
         float s, c;
         sincosf(linspace_elem(lo, hi, n_rays, rj), &s, &c);
-        r.q1x[j] = f_add(r.p1x, f_mul(c, L));
-        r.q1y[j] = f_add(r.p1y, f_mul(s, L));
-        r.rx[j] = f_sub(r.q1x[j], r.p1x);
-        r.ry[j] = f_sub(r.q1y[j], r.p1y);
+        const float q1x = f_add(r.p1x, f_mul(c, L));
+        const float q1y = f_add(r.p1y, f_mul(s, L));
+        r.nq1[j] = make_float2(-q1x, -q1y);
+        r.rr[j] = make_float2(f_sub(q1y, r.p1y), -f_sub(q1x, r.p1x));
         r.best[j] = L;
         r.hit[j] = -1;
       }
     }
 
     for (int ch = 0; ch < n_chunks; ++ch) {
-      const int64_t base = (int64_t)ch * RC_CHUNK;
-      const int cnt = (int)min((int64_t)RC_CHUNK, n_walls - base);
+      const int64_t base = (int64_t)ch * chunk;
+      const int cnt = (int)min((int64_t)chunk, n_walls - base);
       if (n_chunks > 1) {
-        __syncthreads();  // everyone done with the previous chunk
-        stage_walls(walls, base, cnt, tma_ok, stage, wall4, wdir, bar, parity);
+        __syncthreads();  // everyone done with the previous chunk (and its queue)
+        stage_walls(walls, base, cnt, chunk, tma_ok, stage, wall4, wdir, bar, parity);
       }
       if (act) {
         int qn = 0;
-#pragma unroll 2
-        for (int w = 0; w < cnt; ++w) {
-          const float4 wl = wall4[w];
-          const float2 wd = wdir[w];
-          // o3 = orientation(p2, q2, p1): agent-only, shared by the thread's rays
-          const float o3 = f_sub(f_mul(wd.y, f_sub(r.p1x, wl.z)), f_mul(wd.x, f_sub(r.p1y, wl.w)));
+        float4 wl = wall4[0];
+        float2 wd = wdir[0];
+        for (int w = 0;; ++w) {
+          if (qn == RC_QCAP || (w == cnt && qn)) {  // the only flush site
+            flush_queue<RPT>(r, queue, qn, wall4, base);
+            qn = 0;
+          }
+          if (w == cnt) break;
+          const float2 P2 = make_float2(wl.x, wl.y), Q2 = make_float2(wl.z, wl.w), WD = wd;
+          {  // prefetch the next wall while this one is tested
+            const int wn = min(w + 1, cnt - 1);
+            wl = wall4[wn];
+            wd = wdir[wn];
+          }
+          // o3 = orientation(p2, q2, p1) = wy*(p1x-q2x) - wx*(p1y-q2y): agent-only, shared by the rays
+          const float2 m3 = mul2(WD, add2(Q2, np1));
+          const float o3 = f_add(m3.x, m3.y);
           bool cand = false;
+          if constexpr (RPT % 2 == 0) {
+            const float2 o33 = make_float2(o3, o3);
 #pragma unroll
-          for (int j = 0; j < RPT; ++j) {
-            const float a = f_sub(wl.x, r.q1x[j]), b = f_sub(wl.y, r.q1y[j]);
-            const float o1 = f_sub(f_mul(r.ry[j], a), f_mul(r.rx[j], b));
-            const float u = f_sub(wl.z, r.q1x[j]), v = f_sub(wl.w, r.q1y[j]);
-            const float o2 = f_sub(f_mul(r.ry[j], u), f_mul(r.rx[j], v));
-            // o4 = wy*(q1x-q2x) - wx*(q1y-q2y) == wx*v - wy*u bit for bit (negation is exact)
-            const float o4 = f_sub(f_mul(wd.x, v), f_mul(wd.y, u));
-            const float A = f_mul(o1, o2), B = f_mul(o3, o4);
-            // sure miss <=> one pair has equal non-zero signs and nothing is zero / NaN
-            const bool miss = (fmaxf(A, B) > 0.0f) && (fabsf(f_mul(A, B)) > 0.0f);
-            cand |= !miss;
+            for (int j = 0; j < RPT; j += 2) {
+              float2 o1, o2, o4;
+              {
+                const float2 ab = add2(P2, r.nq1[j]), uv = add2(Q2, r.nq1[j]);
+                const float2 m1 = mul2(r.rr[j], ab), m2 = mul2(r.rr[j], uv), m4 = mul2(WD, uv);
+                o1.x = f_add(m1.x, m1.y);  // (q1y-p1y)*(p2x-q1x) - (q1x-p1x)*(p2y-q1y)
+                o2.x = f_add(m2.x, m2.y);
+                o4.x = f_add(m4.x, m4.y);  // wy*(q1x-q2x) - wx*(q1y-q2y)
+              }
+              {
+                const float2 ab = add2(P2, r.nq1[j + 1]), uv = add2(Q2, r.nq1[j + 1]);
+                const float2 m1 = mul2(r.rr[j + 1], ab), m2 = mul2(r.rr[j + 1], uv), m4 = mul2(WD, uv);
+                o1.y = f_add(m1.x, m1.y);
+                o2.y = f_add(m2.x, m2.y);
+                o4.y = f_add(m4.x, m4.y);
+              }
+              const float2 A = mul2(o1, o2), B = mul2(o33, o4);
+              const float2 C = mul2(A, B);
+              cand |= !sure_miss(A.x, B.x, C.x);
+              cand |= !sure_miss(A.y, B.y, C.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              const float2 ab = add2(P2, r.nq1[j]), uv = add2(Q2, r.nq1[j]);
+              const float2 m1 = mul2(r.rr[j], ab), m2 = mul2(r.rr[j], uv), m4 = mul2(WD, uv);
+              const float o1 = f_add(m1.x, m1.y), o2 = f_add(m2.x, m2.y), o4 = f_add(m4.x, m4.y);
+              const float A = f_mul(o1, o2), B = f_mul(o3, o4);
+              cand |= !sure_miss(A, B, f_mul(A, B));
+            }
           }
           if (cand) {
             queue[qn * RC_BLOCK] = (uint32_t)w;
-            if (++qn == RC_QCAP) {
-              flush_queue<RPT>(r, queue, qn, wall4, base);
-              qn = 0;
-            }
+            ++qn;
           }
         }
-        if (qn) flush_queue<RPT>(r, queue, qn, wall4, base);
       }
     }
 
@@ -231,17 +277,21 @@ __global__ void __launch_bounds__(RC_BLOCK)
   }
 }
 
-static size_t raycast_smem_bytes() {
-  return 16 + (size_t)RC_CHUNK * (16 + 16 + 8) + (size_t)RC_QCAP * RC_BLOCK * 4;
+static size_t raycast_smem_bytes(int chunk) {
+  const size_t stage = (size_t)chunk * 16, queue = (size_t)RC_QCAP * RC_BLOCK * 4;
+  return 16 + (size_t)chunk * (16 + 8) + (stage > queue ? stage : queue);
 }
 
-template <int RPT>
+template <int RPT, int MINB = 2>
 static int launch_raycast(const float* x, const float* y, const float* ang, const float* active, int64_t n,
                           int n_rays, float span, float L, WallsSoA w, int64_t n_walls, float* dist, int32_t* hit,
                           cudaStream_t s) {
-  const size_t smem = raycast_smem_bytes();
-  auto kern = raycast_walls_kernel<RPT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int chunk = (int)(n_walls < RC_CHUNK ? n_walls : RC_CHUNK);
+  chunk = chunk < 4 ? 4 : (chunk + 3) & ~3;  // stage rows stay 16-byte aligned
+  const size_t smem = raycast_smem_bytes(chunk);
+  auto kern = raycast_walls_kernel<RPT, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)raycast_smem_bytes(RC_CHUNK));
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls: %s", cudaGetErrorString(e));
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RC_BLOCK, smem);
@@ -253,7 +303,7 @@ static int launch_raycast(const float* x, const float* y, const float* ang, cons
   const uintptr_t al = reinterpret_cast<uintptr_t>(w.x1) | reinterpret_cast<uintptr_t>(w.y1) |
                        reinterpret_cast<uintptr_t>(w.x2) | reinterpret_cast<uintptr_t>(w.y2);
   const int tma_ok = (al & 15) == 0;
-  kern<<<grid, RC_BLOCK, smem, s>>>(x, y, ang, active, n, n_rays, span, L, w, n_walls, tma_ok, dist, hit);
+  kern<<<grid, RC_BLOCK, smem, s>>>(x, y, ang, active, n, n_rays, span, L, w, n_walls, chunk, tma_ok, dist, hit);
   return check_launch("fgx_raycast_walls");
 }
 
@@ -336,6 +386,17 @@ int fgx_raycast_walls(const float* x, const float* y, const float* ang, const fl
   WallsSoA w{wx1, wy1, wx2, wy2};
   cudaStream_t s = as_stream(stream);
   // rays per thread: the largest group size that divides the ray count well
+  if (const char* v = getenv("FGX_RC_VARIANT")) {  // tuning hook (profiles/): RPT x min CTAs per SM
+    switch (atoi(v)) {
+      case 1: return launch_raycast<8, 3>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 2: return launch_raycast<4, 3>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 3: return launch_raycast<4, 4>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 4: return launch_raycast<4, 5>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 5: return launch_raycast<2, 6>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 6: return launch_raycast<4, 2>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      default: break;
+    }
+  }
   if (n_rays % 8 == 0) return launch_raycast<8>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
   if (n_rays % 4 == 0) return launch_raycast<4>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
   if (n_rays % 3 == 0) return launch_raycast<3>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
