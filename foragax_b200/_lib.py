@@ -75,6 +75,52 @@ _decl("fgx_dice_remove", C.c_int, i64, vp, vp, vp, vp, vp)
 _decl("fgx_dice_add", C.c_int, i64, i32, vp, vp, vp, vp, vp, vp)
 
 
+class ForagerParams(C.Structure):
+    _fields_ = [("n_neurons", i32), ("n_obs", i32), ("n_act", i32), ("dt", f32), ("policy_dt", f32),
+                ("action_scale", f32), ("x_min", f32), ("x_max", f32), ("y_min", f32), ("y_max", f32),
+                ("repr_thresh", f32), ("die_thresh", f32), ("energy_min", f32), ("energy_max", f32),
+                ("energy_cost_dt", f32), ("clip_min", i32)]
+
+
+FORAGER_STATE_FIELDS = ("X", "X_vel", "X_acc", "Y", "Y_vel", "Y_acc", "ang", "energy", "rad",
+                        "time_above_rep_thresh", "time_below_die_thresh")
+
+
+class ForagerState(C.Structure):
+    _fields_ = [(k, vp) for k in FORAGER_STATE_FIELDS]
+
+
+class WcPolicy(C.Structure):
+    _fields_ = [(k, vp) for k in ("J", "tau", "E", "B", "D", "Z")]
+
+
+class ResourceParams(C.Structure):
+    _fields_ = [("dt", f32), ("x_min", f32), ("x_max", f32), ("blossom_thresh", f32)]
+
+
+class ResourceState(C.Structure):
+    _fields_ = [(k, vp) for k in ("X", "Y", "energy", "rad", "time_above_blossom", "blossom", "key")]
+
+
+_P = C.POINTER
+_decl("fgx_forager_step", C.c_int, _P(ForagerParams), i64, vp, vp, vp, _P(ForagerState), _P(WcPolicy), vp, vp)
+_decl("fgx_wilson_cowan_step", C.c_int, i64, i32, i32, i32, f32, f32, vp, vp, _P(WcPolicy), vp, vp)
+_decl("fgx_resource_step", C.c_int, _P(ResourceParams), i64, vp, vp, _P(ResourceState), vp, vp, vp, vp)
+_decl("fgx_forager_resource_interaction", C.c_int, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp)
+_decl("fgx_sensor_model", C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp,
+      i32, f32, f32, vp, vp)
+_decl("fgx_forager_create", C.c_int, _P(ForagerParams), i64, vp, vp, _P(ForagerState), vp, vp, vp, vp)
+_decl("fgx_forager_remove", C.c_int, i64, i32, vp, vp, _P(ForagerState), vp, vp, vp, vp)
+_decl("fgx_forager_add", C.c_int, i64, i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, _P(ForagerState), _P(WcPolicy),
+      vp, vp, vp, vp)
+_decl("fgx_forager_set", C.c_int, i64, vp, vp, _P(ForagerState), vp)
+_decl("fgx_resource_create", C.c_int, i64, f32, f32, f32, f32, vp, vp, _P(ResourceState), vp, vp, vp, vp)
+_decl("fgx_resource_remove", C.c_int, i64, vp, vp, _P(ResourceState), vp, vp, vp)
+_decl("fgx_resource_add", C.c_int, i64, f32, f32, f32, f32, vp, vp, vp, vp, vp, _P(ResourceState), vp, vp, vp, vp, vp,
+      vp)
+_decl("fgx_resource_set", C.c_int, i64, vp, vp, _P(ResourceState), vp)
+
+
 class FgxError(RuntimeError):
     pass
 

@@ -1,0 +1,414 @@
+// K2 for the foraging example (examples/many_agent_systems/foraging_agents/EcoEvoJax/sim.py):
+// the fused Forager step (WilsonCowan policy + point-mass physics + energy bookkeeping), the
+// Resource step, the all-pairs eating interaction and the ray-sensor composition.
+//
+// forager_step is HBM-bound: every agent owns its RNN weights (J n*n, E n*obs, D act*n, tau,
+// B, Z), so a step streams ~12 KB per active agent (n=40, obs=28) and does ~6 kFLOP on it --
+// a batched GEMV, no tensor-core shape.  One warp per agent: lane 0 pulls the agent's
+// weight rows global -> shared with cp.async.bulk (TMA, mbarrier completion; every byte is
+// read exactly once, fully coalesced), then lane r owns output row r and walks it with a
+// rotated column order so that the 32 lanes hit 32 different banks.  16 warps per SM keep
+// ~190 KB of weight rows in flight per SM.
+#include "common.cuh"
+#include "geometry.cuh"
+#include "threefry.cuh"
+#include "tma.cuh"
+
+namespace fgx {
+
+constexpr int FS_WARPS = 8;  // warps per CTA of the forager step
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ int align4(int x) { return (x + 3) & ~3; }
+
+struct WcLayout {  // per-warp shared-memory slots (in floats), each 16-byte aligned
+  int J, E, D, tau, B, Z, tz, tnz, obs, total;
+};
+__host__ __device__ inline WcLayout wc_layout(int n, int nobs, int nact) {
+  WcLayout l;
+  int o = 0;
+  auto take = [&](int cnt) { int r = o; o += (cnt + 3) & ~3; return r; };
+  l.J = take(n * n);
+  l.E = take(n * nobs);
+  l.D = take(nact * n);
+  l.tau = take(n);
+  l.B = take(n);
+  l.Z = take(n);
+  l.tz = take(n);
+  l.tnz = take(n);
+  l.obs = take(nobs);
+  l.total = o;
+  return l;
+}
+
+// one leaf row of one agent -> shared memory: TMA bulk copy when 16-byte clean, else lanes copy
+__device__ __forceinline__ uint32_t leaf_tma_bytes(const float* base, int row_floats) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_floats & 3) == 0) ? (uint32_t)row_floats * 4u : 0u;
+}
+
+__global__ void __launch_bounds__(FS_WARPS * 32)
+    forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
+                        const float* __restrict__ obs_in, const float* __restrict__ energy_in,
+                        const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
+                        float* __restrict__ actions_out) {
+  // actions_out != nullptr: policy-only mode (WilsonCowan.step_policy on its own): obs has all n_obs
+  // columns, actions are written out and the Forager physics is skipped
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = p.n_neurons, nobs = p.n_obs, nact = p.n_act;
+  const WcLayout L = wc_layout(n, nobs, nact);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+  float* sm = reinterpret_cast<float*>(smem_raw + 16 * ((FS_WARPS * 8 + 15) / 16)) + (size_t)warp * L.total;
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t parity = 0;
+
+  const uint32_t bJ = leaf_tma_bytes(pol.J, n * n), bE = leaf_tma_bytes(pol.E, n * nobs),
+                 bD = leaf_tma_bytes(pol.D, nact * n), bT = leaf_tma_bytes(pol.tau, n),
+                 bB = leaf_tma_bytes(pol.B, n), bZ = leaf_tma_bytes(pol.Z, n);
+  const uint32_t tx = bJ + bE + bD + bT + bB + bZ;
+
+  const int nwarps = blockDim.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
+  for (int64_t a = gw; a < n_agents; a += GW) {
+    if (active[a] == 0.0f) continue;  // lax.cond(active_state): inactive slots pass through
+    const float* gJ = pol.J + a * n * n;
+    const float* gE = pol.E + a * n * nobs;
+    const float* gD = pol.D + a * nact * n;
+    const float* gT = pol.tau + a * n;
+    const float* gB = pol.B + a * n;
+    float* gZ = pol.Z + a * n;
+    if (lane == 0 && tx) {
+      mbar_expect_tx(bar, tx);
+      if (bJ) tma_bulk_g2s(sm + L.J, gJ, bJ, bar);
+      if (bE) tma_bulk_g2s(sm + L.E, gE, bE, bar);
+      if (bD) tma_bulk_g2s(sm + L.D, gD, bD, bar);
+      if (bT) tma_bulk_g2s(sm + L.tau, gT, bT, bar);
+      if (bB) tma_bulk_g2s(sm + L.B, gB, bB, bar);
+      if (bZ) tma_bulk_g2s(sm + L.Z, gZ, bZ, bar);
+    }
+    if (!bJ) for (int i = lane; i < n * n; i += 32) sm[L.J + i] = __ldg(gJ + i);
+    if (!bE) for (int i = lane; i < n * nobs; i += 32) sm[L.E + i] = __ldg(gE + i);
+    if (!bD) for (int i = lane; i < nact * n; i += 32) sm[L.D + i] = __ldg(gD + i);
+    if (!bT) for (int i = lane; i < n; i += 32) sm[L.tau + i] = __ldg(gT + i);
+    if (!bB) for (int i = lane; i < n; i += 32) sm[L.B + i] = __ldg(gB + i);
+    if (!bZ) for (int i = lane; i < n; i += 32) sm[L.Z + i] = gZ[i];
+    // obs = concat(sensor obs, own energy) (sim.py:80-82)
+    const float energy = actions_out ? 0.0f : st.energy[a];
+    if (actions_out) {
+      for (int k = lane; k < nobs; k += 32) sm[L.obs + k] = __ldg(obs_in + a * nobs + k);
+    } else {
+      for (int k = lane; k < nobs - 1; k += 32) sm[L.obs + k] = __ldg(obs_in + a * (nobs - 1) + k);
+      if (lane == 0) sm[L.obs + nobs - 1] = energy;
+    }
+    __syncwarp();
+    if (tx) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    }
+    // WilsonCowan.step_policy (wilson_cowan.py:34-51)
+    for (int j = lane; j < n; j += 32) sm[L.tz + j] = tanhf(sm[L.Z + j]);
+    __syncwarp();
+    const int rotJ = (n & 1) ? 0 : 1, rotE = (nobs & 1) ? 0 : 1;  // odd bank stride for the row walk
+    for (int r = lane; r < n; r += 32) {
+      float sJ = 0.0f, sE = 0.0f;
+      const float* rowJ = sm + L.J + r * n;
+      int j = rotJ ? r % n : 0;
+      for (int t = 0; t < n; ++t) {
+        sJ += rowJ[j] * sm[L.tz + j];
+        j = j + 1 == n ? 0 : j + 1;
+      }
+      const float* rowE = sm + L.E + r * nobs;
+      int k = rotE ? r % nobs : 0;
+      for (int t = 0; t < nobs; ++t) {
+        sE += rowE[k] * sm[L.obs + k];
+        k = k + 1 == nobs ? 0 : k + 1;
+      }
+      const float z = sm[L.Z + r];
+      float dz = ((sJ + sE) + sm[L.B + r]) - z;
+      dz = dz * (10.0f * sigmoidf_(sm[L.tau + r]));
+      const float nz = z + p.policy_dt * dz;
+      gZ[r] = nz;
+      sm[L.tnz + r] = tanhf(nz);
+    }
+    __syncwarp();
+    float act0 = 0.0f, act1 = 0.0f;  // the Forager uses actions[0], actions[1] (sim.py:86-87)
+    for (int k = 0; k < nact; ++k) {
+      float s = 0.0f;
+      for (int j = lane; j < n; j += 32) s += sm[L.D + k * n + j] * sm[L.tnz + j];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      const float v = p.action_scale * tanhf(s);
+      if (k == 0) act0 = v;
+      if (k == 1) act1 = v;
+      if (actions_out && lane == 0) actions_out[a * nact + k] = v;
+    }
+    if (lane == 0 && !actions_out) {
+      // Forager.step_agent physics (sim.py:89-128)
+      const float dt = p.dt;
+      const float X = st.X[a], Y = st.Y[a], Xv = st.X_vel[a], Yv = st.Y_vel[a];
+      float Xn = f_add(X, f_mul(Xv, dt)), Yn = f_add(Y, f_mul(Yv, dt));
+      float Xvn = f_add(Xv, f_mul(act0, dt)), Yvn = f_add(Yv, f_mul(act1, dt));
+      if (Xn > p.x_max || Xn < p.x_min) { Xn = X; Xvn = -Xv; }
+      if (Yn > p.y_max || Yn < p.y_min) { Yn = Y; Yvn = -Yv; }
+      float en = f_sub(f_add(energy, energy_in[a]), f_mul(p.energy_cost_dt, f_add(fabsf(act0), fabsf(act1))));
+      en = fminf(en, p.energy_max);
+      if (p.clip_min) en = fmaxf(en, p.energy_min);
+      st.X[a] = Xn; st.Y[a] = Yn; st.X_vel[a] = Xvn; st.Y_vel[a] = Yvn;
+      st.X_acc[a] = act0; st.Y_acc[a] = act1;
+      st.ang[a] = atan2f(Yvn, Xvn);
+      st.energy[a] = en; st.rad[a] = en;
+      st.time_above_rep_thresh[a] = en > p.repr_thresh ? f_add(st.time_above_rep_thresh[a], dt) : 0.0f;
+      st.time_below_die_thresh[a] = en < p.die_thresh ? f_add(st.time_below_die_thresh[a], dt) : 0.0f;
+      age[a] = f_add(age[a], dt);
+    }
+    __syncwarp();  // all lanes are done with the slots before the next agent's copies land
+  }
+}
+
+// Resource.step_agent under vmap (sim.py:264-303)
+__global__ void __launch_bounds__(256)
+    resource_step_kernel(const fgx_resource_params_t p, int64_t n, const float* __restrict__ active,
+                         const float* __restrict__ energy_out, const fgx_resource_state_t st,
+                         const float* __restrict__ growth, const float* __restrict__ decay, float* __restrict__ age) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (active[i] == 0.0f) continue;
+    const float dt = p.dt, old = st.energy[i];
+    const float g = f_sub(f_mul(growth[i], old), f_mul(decay[i], f_mul(old, old)));
+    float en = f_sub(f_add(old, f_mul(dt, g)), energy_out[i]);
+    en = fminf(fmaxf(en, 0.0f), 5.0f);
+    const float prob = sigmoidf_(__fdiv_rn(f_mul(4.0f, f_sub(p.x_max, st.X[i])), f_sub(p.x_max, p.x_min)));
+    const uint2 kk = reinterpret_cast<const uint2*>(st.key)[i];
+    Key nk, bk;
+    split2(Key{kk.x, kk.y}, nk, bk);
+    const bool luck = uniform1(bk, 0.0f, 1.0f) < prob;  // bernoulli(key, p) = uniform(key) < p
+    const bool old_b = st.blossom[i] != 0;
+    const bool blossom = old_b ? true : (luck && en > p.blossom_thresh);
+    st.energy[i] = en;
+    st.rad[i] = en;
+    st.blossom[i] = blossom ? 1 : 0;
+    reinterpret_cast<uint2*>(st.key)[i] = make_uint2(nk.a, nk.b);
+    st.time_above_blossom[i] = blossom ? f_add(st.time_above_blossom[i], dt) : 0.0f;
+    age[i] = f_add(age[i], dt);
+  }
+}
+
+// forager_resource_interaction (sim.py:358-375): energy_in[f] = sum_r e(f,r), energy_out[r] = sum_f e(f,r),
+// e(f,r) = energy_r if |f - r| < rad_r + 0.1 else 0.  One thread per forager, resources tiled through
+// shared memory; energy_out is accumulated with atomics (all addends of one resource are equal, so
+// the sum does not depend on the order).
+__global__ void __launch_bounds__(256)
+    interaction_kernel(int64_t nf, const float* __restrict__ fx, const float* __restrict__ fy, int64_t nr,
+                       const float* __restrict__ rx, const float* __restrict__ ry, const float* __restrict__ rrad,
+                       const float* __restrict__ ren, float* __restrict__ energy_in, float* __restrict__ energy_out) {
+  __shared__ float4 tile[256];
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const float px = f < nf ? fx[f] : 0.0f, py = f < nf ? fy[f] : 0.0f;
+  float acc = 0.0f;
+  for (int64_t base = 0; base < nr; base += 256) {
+    const int64_t r = base + threadIdx.x;
+    tile[threadIdx.x] = r < nr ? make_float4(rx[r], ry[r], f_add(rrad[r], 0.1f), ren[r]) : make_float4(0, 0, -1, 0);
+    __syncthreads();
+    const int cnt = (int)min((int64_t)256, nr - base);
+    if (f < nf) {
+      for (int k = 0; k < cnt; ++k) {
+        const float4 t = tile[k];
+        const float d = norm2(f_sub(t.x, px), f_sub(t.y, py));
+        if (d < t.z) {
+          acc = f_add(acc, t.w);
+          atomicAdd(energy_out + base + k, t.w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (f < nf) energy_in[f] = acc;
+}
+
+// sensor_model (sim.py:388-468): one thread per (forager, ray); entities = [foragers, resources, walls].
+// The reference prefilters agent entity e with column e of a distance matrix ordered
+// [resources, foragers] (sim.py:381,416,435) -- reproduced: `partner` is that other agent.
+struct SensorArgs {
+  int64_t nf, nr, nw;
+  const float *fx, *fy, *fang, *frad, *fen, *fact;
+  const int32_t* ftype;
+  const float *rx, *ry, *rrad, *ren, *ract;
+  const int32_t* rtype;
+  const float *wx1, *wy1, *wx2, *wy2;
+  int n_rays;
+  float span, L;
+  float* obs;  // [nf, n_rays*3]
+};
+
+__global__ void __launch_bounds__(128) sensor_model_kernel(const SensorArgs a) {
+  __shared__ float4 ent[128];   // x, y, rad, active
+  __shared__ float2 part[128];  // partner x, y (the misaligned distance column)
+  const int64_t task = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = a.nf * a.n_rays;
+  const bool valid = task < total;
+  const int64_t f = valid ? task / a.n_rays : 0;
+  const int j = valid ? (int)(task - f * a.n_rays) : 0;
+  const bool act = valid && a.fact[f] != 0.0f;
+  const float ox = a.fx[f], oy = a.fy[f], L = a.L;
+  float s, c;
+  {
+    const float g = a.fang[f];
+    sincosf(linspace_elem(f_sub(g, a.span), f_add(g, a.span), a.n_rays, j), &s, &c);
+  }
+  float best = L;
+  int64_t bidx = -1;
+  const int64_t ne = a.nf + a.nr;
+  for (int64_t base = 0; base < ne; base += 128) {
+    const int64_t e = base + threadIdx.x;
+    if (e < ne) {
+      const bool isf = e < a.nf;
+      const int64_t k = isf ? e : e - a.nf;
+      ent[threadIdx.x] = isf ? make_float4(a.fx[k], a.fy[k], a.frad[k], a.fact[k])
+                             : make_float4(a.rx[k], a.ry[k], a.rrad[k], a.ract[k]);
+      // column e of concat(forager-resource dists, forager-forager dists)
+      part[threadIdx.x] = e < a.nr ? make_float2(a.rx[e], a.ry[e]) : make_float2(a.fx[e - a.nr], a.fy[e - a.nr]);
+    }
+    __syncthreads();
+    if (act) {
+      const int cnt = (int)min((int64_t)128, ne - base);
+      for (int k = 0; k < cnt; ++k) {
+        const float4 t = ent[k];
+        const float2 q = part[k];
+        const float pd = norm2(f_sub(q.x, ox), f_sub(q.y, oy));
+        if (pd < f_add(L, t.z)) {
+          const float d = ray_agent_exact(ox, oy, c, s, L, t.x, t.y, t.z, t.w);
+          if (d < best) { best = d; bidx = base + k; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (act) {
+    const float qx = f_add(ox, f_mul(c, L)), qy = f_add(oy, f_mul(s, L));
+    for (int64_t w = 0; w < a.nw; ++w) {
+      const float d = ray_wall_exact(ox, oy, qx, qy, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w]);
+      if (d < best) { best = d; bidx = ne + w; }
+    }
+  }
+  if (valid) {
+    float en = 0.0f, ty = 0.0f;
+    if (act && bidx >= 0 && bidx < ne) {
+      const bool isf = bidx < a.nf;
+      const int64_t k = isf ? bidx : bidx - a.nf;
+      en = isf ? a.fen[k] : a.ren[k];
+      ty = (float)(isf ? a.ftype[k] : a.rtype[k]);
+    }
+    float* o = a.obs + f * (a.n_rays * 3) + j * 3;
+    o[0] = act ? en : 0.0f;
+    o[1] = act ? ty : 0.0f;
+    o[2] = act ? best : 0.0f;
+  }
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+// shared launcher: as many warps per CTA (<= FS_WARPS) as the per-warp weight slots allow
+static int launch_forager_step(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
+                               const float* obs, const float* energy_in, const fgx_forager_state_t& st,
+                               const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
+  using namespace fgx;
+  const WcLayout L = wc_layout(p.n_neurons, p.n_obs, p.n_act);
+  const size_t head = 16 * ((FS_WARPS * 8 + 15) / 16), per_warp = (size_t)L.total * sizeof(float);
+  int warps = FS_WARPS;
+  while (warps > 1 && head + warps * per_warp > 113 * 1024) --warps;  // aim at 2 CTAs per SM
+  FGX_REQUIRE(head + warps * per_warp <= 227 * 1024,
+              "%s: policy too large for shared memory (%zu bytes per agent)", what, per_warp);
+  const size_t smem = head + warps * per_warp;
+  cudaError_t e = cudaFuncSetAttribute(forager_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forager_step_kernel, warps * 32, smem);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t need = ceil_div(n, warps);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  forager_step_kernel<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol,
+                                                                             age, actions);
+  return check_launch(what);
+}
+
+int fgx_forager_step(const fgx_forager_params_t* p, int64_t n, const float* active_state, const float* obs,
+                     const float* energy_in, const fgx_forager_state_t* state, const fgx_wc_policy_t* policy,
+                     float* age, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(p && state && policy, "fgx_forager_step: null struct");
+  FGX_REQUIRE(n >= 0, "fgx_forager_step: bad n");
+  FGX_REQUIRE(p->n_neurons > 0 && p->n_obs > 0 && p->n_act >= 2, "fgx_forager_step: bad policy shape");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state && obs && energy_in && age, "fgx_forager_step: null pointer");
+  return launch_forager_step("fgx_forager_step", *p, n, active_state, obs, energy_in, *state, *policy, age, nullptr,
+                             as_stream(stream));
+}
+
+int fgx_wilson_cowan_step(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, float policy_dt,
+                          float action_scale, const float* active_state, const float* obs,
+                          const fgx_wc_policy_t* policy, float* actions, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(policy && n >= 0, "fgx_wilson_cowan_step: bad arguments");
+  FGX_REQUIRE(n_neurons > 0 && n_obs > 0 && n_act > 0, "fgx_wilson_cowan_step: bad policy shape");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state && obs && actions, "fgx_wilson_cowan_step: null pointer");
+  fgx_forager_params_t p{};
+  p.n_neurons = n_neurons; p.n_obs = n_obs; p.n_act = n_act; p.policy_dt = policy_dt; p.action_scale = action_scale;
+  fgx_forager_state_t st{};
+  return launch_forager_step("fgx_wilson_cowan_step", p, n, active_state, obs, nullptr, st, *policy, nullptr, actions,
+                             as_stream(stream));
+}
+
+int fgx_resource_step(const fgx_resource_params_t* p, int64_t n, const float* active_state, const float* energy_out,
+                      const fgx_resource_state_t* state, const float* growth_rate, const float* decay_rate,
+                      float* age, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(p && state, "fgx_resource_step: null struct");
+  FGX_REQUIRE(n >= 0, "fgx_resource_step: bad n");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state && energy_out && growth_rate && decay_rate && age, "fgx_resource_step: null pointer");
+  resource_step_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(*p, n, active_state, energy_out, *state,
+                                                                          growth_rate, decay_rate, age);
+  return check_launch("fgx_resource_step");
+}
+
+int fgx_forager_resource_interaction(int64_t n_foragers, const float* fx, const float* fy, int64_t n_resources,
+                                     const float* rx, const float* ry, const float* rrad, const float* renergy,
+                                     float* energy_in, float* energy_out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_foragers >= 0 && n_resources >= 0, "fgx_forager_resource_interaction: bad sizes");
+  cudaStream_t s = as_stream(stream);
+  if (n_resources > 0) {
+    FGX_REQUIRE(energy_out, "fgx_forager_resource_interaction: null energy_out");
+    cudaError_t e = cudaMemsetAsync(energy_out, 0, sizeof(float) * n_resources, s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_forager_resource_interaction: %s", cudaGetErrorString(e));
+  }
+  if (n_foragers == 0) return FGX_OK;
+  FGX_REQUIRE(fx && fy && energy_in, "fgx_forager_resource_interaction: null pointer");
+  FGX_REQUIRE(n_resources == 0 || (rx && ry && rrad && renergy), "fgx_forager_resource_interaction: null pointer");
+  interaction_kernel<<<(int)ceil_div(n_foragers, 256), 256, 0, s>>>(n_foragers, fx, fy, n_resources, rx, ry, rrad,
+                                                                   renergy, energy_in, energy_out);
+  return check_launch("fgx_forager_resource_interaction");
+}
+
+int fgx_sensor_model(int64_t n_foragers, const float* fx, const float* fy, const float* fang, const float* frad,
+                     const float* fenergy, const float* factive, const int32_t* ftype, int64_t n_resources,
+                     const float* rx, const float* ry, const float* rrad, const float* renergy, const float* ractive,
+                     const int32_t* rtype, int64_t n_walls, const float* wx1, const float* wy1, const float* wx2,
+                     const float* wy2, int32_t n_rays, float ray_span, float ray_length, float* obs,
+                     fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_foragers >= 0 && n_resources >= 0 && n_walls >= 0 && n_rays > 0, "fgx_sensor_model: bad sizes");
+  if (n_foragers == 0) return FGX_OK;
+  FGX_REQUIRE(fx && fy && fang && frad && fenergy && factive && ftype && obs, "fgx_sensor_model: null forager leaf");
+  FGX_REQUIRE(n_resources == 0 || (rx && ry && rrad && renergy && ractive && rtype),
+              "fgx_sensor_model: null resource leaf");
+  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_sensor_model: null wall array");
+  SensorArgs a{n_foragers, n_resources, n_walls, fx, fy, fang, frad, fenergy, factive, ftype, rx, ry, rrad, renergy,
+               ractive, rtype, wx1, wy1, wx2, wy2, n_rays, ray_span, ray_length, obs};
+  sensor_model_kernel<<<(int)ceil_div(n_foragers * n_rays, 128), 128, 0, as_stream(stream)>>>(a);
+  return check_launch("fgx_sensor_model");
+}
+}

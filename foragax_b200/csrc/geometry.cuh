@@ -35,7 +35,7 @@ __device__ __forceinline__ float min_nan(float a, float b) {
 
 // ray_wall_sensor (space_methods.py:96-143) for ray p1->q1 (q1 = origin + dir*L already
 // rounded by the caller) and wall p2-q2.  Returns L when nothing is hit.
-__device__ __noinline__ float ray_wall_exact(float p1x, float p1y, float q1x, float q1y, float L, float p2x,
+static __device__ __noinline__ float ray_wall_exact(float p1x, float p1y, float q1x, float q1y, float L, float p2x,
                                              float p2y, float q2x, float q2y) {
   const int o1 = orient_cls(orient_val(p1x, p1y, q1x, q1y, p2x, p2y));
   const int o2 = orient_cls(orient_val(p1x, p1y, q1x, q1y, q2x, q2y));

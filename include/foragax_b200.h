@@ -166,6 +166,113 @@ int fgx_dice_remove(int64_t n, const int32_t* remove_ids, const int32_t* k, int3
 int fgx_dice_add(int64_t n, int32_t sides, const int32_t* n_active, const int32_t* k, int32_t* draw, uint32_t* key,
                  float* active_state, fgx_stream_t stream);
 
+/* ---- K2: foraging example (examples/many_agent_systems/foraging_agents/EcoEvoJax/sim.py) ---
+ * Forager = WilsonCowan policy (foragax/policy/wilson_cowan.py) + point-mass physics + energy;
+ * Resource = logistic growth + blossom.  All leaves are struct-of-arrays with the slot axis
+ * first; [n,1] leaves are passed as float32[n].                                          */
+typedef struct {
+  int32_t n_neurons, n_obs /* incl. the agent's own energy */, n_act;
+  float dt;             /* forager.params.content['dt'] (sim.py:94) */
+  float policy_dt;      /* policy.params.content['dt'] (wilson_cowan.py:44) */
+  float action_scale;   /* wilson_cowan.py:45 */
+  float x_min, x_max, y_min, y_max; /* space bounds (sim.py:100-104) */
+  float repr_thresh, die_thresh, energy_min, energy_max; /* step params (sim.py:659) */
+  float energy_cost_dt; /* float32(0.3)*dt in sim.py:109; dt in the notebook variant */
+  int32_t clip_min;     /* 1: clip(e, energy_min, energy_max) (sim.py:111); 0: minimum(e, energy_max) */
+} fgx_forager_params_t;
+typedef struct {
+  float *X, *X_vel, *X_acc, *Y, *Y_vel, *Y_acc, *ang, *energy, *rad, *time_above_rep_thresh, *time_below_die_thresh;
+} fgx_forager_state_t; /* each float32[n] */
+typedef struct {
+  float *J;   /* [n, neurons, neurons] */
+  float *tau; /* [n, neurons] */
+  float *E;   /* [n, neurons, n_obs] */
+  float *B;   /* [n, neurons] */
+  float *D;   /* [n, n_act, neurons] */
+  float *Z;   /* [n, neurons] policy state */
+} fgx_wc_policy_t;
+/* step_agents + vmapped Forager.step_agent (agent_methods.py:20-24, sim.py:74-136) with
+ * WilsonCowan.step_policy (wilson_cowan.py:34-51) fused; in place.  obs float32[n, n_obs-1]
+ * (sensor_model output), energy_in float32[n].  Inactive slots pass through.              */
+int fgx_forager_step(const fgx_forager_params_t* p, int64_t n, const float* active_state, const float* obs,
+                     const float* energy_in, const fgx_forager_state_t* state, const fgx_wc_policy_t* policy,
+                     float* age, fgx_stream_t stream);
+
+/* WilsonCowan.step_policy (wilson_cowan.py:34-51) on its own, vmapped: obs float32[n, n_obs],
+ * actions float32[n, n_act]; Z updated in place; inactive slots (active_state == 0) are skipped. */
+int fgx_wilson_cowan_step(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, float policy_dt,
+                          float action_scale, const float* active_state, const float* obs,
+                          const fgx_wc_policy_t* policy, float* actions, fgx_stream_t stream);
+
+typedef struct {
+  float dt, x_min, x_max, blossom_thresh; /* sim.py:266,278-279,660 */
+} fgx_resource_params_t;
+typedef struct {
+  float *X, *Y, *energy, *rad, *time_above_blossom; /* float32[n] */
+  uint8_t* blossom;                                 /* bool[n] */
+  uint32_t* key;                                    /* uint32[n,2] */
+} fgx_resource_state_t;
+/* step_agents + vmapped Resource.step_agent (sim.py:264-303); in place; energy_out float32[n] */
+int fgx_resource_step(const fgx_resource_params_t* p, int64_t n, const float* active_state, const float* energy_out,
+                      const fgx_resource_state_t* state, const float* growth_rate, const float* decay_rate,
+                      float* age, fgx_stream_t stream);
+/* forager_resource_interaction (sim.py:358-375): energy_in float32[n_foragers],
+ * energy_out float32[n_resources]                                                        */
+int fgx_forager_resource_interaction(int64_t n_foragers, const float* fx, const float* fy, int64_t n_resources,
+                                     const float* rx, const float* ry, const float* rrad, const float* renergy,
+                                     float* energy_in, float* energy_out, fgx_stream_t stream);
+/* sensor_model (sim.py:388-468): rays of every active forager against the entity table
+ * [foragers, resources, walls] with the reference's distance prefilter (sim.py:435) and
+ * min / first-argmin reduction; obs float32[n_foragers, 3*n_rays] = per ray (energy, type,
+ * distance) of the hit entity, zeros for inactive foragers.                               */
+int fgx_sensor_model(int64_t n_foragers, const float* fx, const float* fy, const float* fang, const float* frad,
+                     const float* fenergy, const float* factive, const int32_t* ftype, int64_t n_resources,
+                     const float* rx, const float* ry, const float* rrad, const float* renergy, const float* ractive,
+                     const int32_t* rtype, int64_t n_walls, const float* wx1, const float* wy1, const float* wx2,
+                     const float* wy2, int32_t n_rays, float ray_span, float ray_length, float* obs,
+                     fgx_stream_t stream);
+
+/* Row operations of the foraging example.  The reference runs these callbacks inside serial
+ * lax.fori_loops (agent_methods.py:29-35,43-49,55-61); here all k rows are processed in one
+ * call, k and n_active being int32 DEVICE scalars.  add_agents threads a PRNG key through its
+ * loop: key_in / key_out are uint32[2] device arrays and chain_scratch is uint32[n,2].        */
+/* vmapped Forager.create_agent (sim.py:27-71).  p->x_min..y_max hold the CREATE bounds of X, Y
+ * (sim.py:39,43).  init_keys uint32[5,n,2] receives the five WilsonCowan.create_policy keys
+ * (wilson_cowan.py:19-26), leaf-major; the caller draws J,tau,E,B,D with fgx_threefry_uniform. */
+int fgx_forager_create(const fgx_forager_params_t* p, int64_t n, const uint32_t* create_keys,
+                       const float* active_state, const fgx_forager_state_t* state, float* Z, uint32_t* init_keys,
+                       float* age, fgx_stream_t stream);
+/* remove_agents with Forager.remove_agent (sim.py:139-151) */
+int fgx_forager_remove(int64_t n, int32_t n_neurons, const int32_t* remove_ids, const int32_t* k,
+                       const fgx_forager_state_t* state, float* Z, float* active_state, float* age,
+                       fgx_stream_t stream);
+/* add_agents with Forager.add_agent (sim.py:154-210): rows [*n_active, *n_active + *k) become
+ * children of rows good_ids[0..*k): parent weights + noise_scale * normal() (noise_scale constant,
+ * or clip(0.1/(age+0.01), 0.001, 0.1) when adaptive_noise, the notebook variant)              */
+int fgx_forager_add(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, const int32_t* good_ids,
+                    const int32_t* n_active, const int32_t* k, const uint32_t* key_in, uint32_t* key_out,
+                    float noise_scale, int32_t adaptive_noise, const fgx_forager_state_t* state,
+                    const fgx_wc_policy_t* policy, float* active_state, float* age, uint32_t* chain_scratch,
+                    fgx_stream_t stream);
+/* set_agents with Forager.set_agent (sim.py:213-225) */
+int fgx_forager_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_forager_state_t* state,
+                    fgx_stream_t stream);
+/* vmapped Resource.create_agent (sim.py:231-261); x_lo..y_hi = create bounds of X, Y (sim.py:248-249) */
+int fgx_resource_create(int64_t n, float x_lo, float x_hi, float y_lo, float y_hi, const uint32_t* create_keys,
+                        const float* active_state, const fgx_resource_state_t* state, float* growth_rate,
+                        float* decay_rate, float* age, fgx_stream_t stream);
+/* remove_agents with Resource.remove_agent (sim.py:306-313) */
+int fgx_resource_remove(int64_t n, const int32_t* remove_ids, const int32_t* k, const fgx_resource_state_t* state,
+                        float* active_state, float* age, fgx_stream_t stream);
+/* add_agents with Resource.add_agent (sim.py:316-344); x_min..y_max = the clip bounds */
+int fgx_resource_add(int64_t n, float x_min, float x_max, float y_min, float y_max, const int32_t* good_ids,
+                     const int32_t* n_active, const int32_t* k, const uint32_t* key_in, uint32_t* key_out,
+                     const fgx_resource_state_t* state, float* growth_rate, float* decay_rate, float* active_state,
+                     float* age, uint32_t* chain_scratch, fgx_stream_t stream);
+/* set_agents with Resource.set_agent (sim.py:347-355) */
+int fgx_resource_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_resource_state_t* state,
+                     fgx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

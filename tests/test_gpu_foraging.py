@@ -1,0 +1,172 @@
+"""K2 parity: the foraging example (Forager / Resource / interaction / sensor_model /
+Neuroevolution) on the CUDA path vs the oracle and vs the reference's golden vector G2.
+
+Tolerances (north star): RNG draws, keys, active masks, selected indices, sort order and counts
+bit-exact; fp32 state within 1e-5 relative (the policy's dot products are summed in a different
+order and tanh/exp/atan2 differ by a few ulp between CUDA and NumPy)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agent_methods as oam
+from oracle import foraging as ofo
+from oracle import jax_random as jr
+
+pytestmark = pytest.mark.gpu
+
+G2 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "g2_foraging.json")))["ticks"]
+RTOL, ATOL = 1e-5, 2e-5
+
+
+def np_forager(a):
+    c = a.state.content
+    pc = a.policy.params.content
+    return {"state": {k: c[k].cpu().numpy() for k in ofo.FSTATE},
+            "policy": {**{k: pc[k].cpu().numpy() for k in ("J", "tau", "E", "B", "D")},
+                       "Z": a.policy.state.content["Z"].cpu().numpy()},
+            "unique_id": a.unique_id.cpu().numpy(), "agent_type": a.agent_type.cpu().numpy(),
+            "active_state": a.active_state.cpu().numpy(), "age": a.age.cpu().numpy()}
+
+
+def np_resource(a):
+    c = a.state.content
+    return {"state": {k: c[k].cpu().numpy() for k in ("X", "Y", "energy", "rad", "blossom", "key", "time_above_blossom")},
+            "params": {k: a.params.content[k].cpu().numpy() for k in ("growth_rate", "decay_rate")},
+            "unique_id": a.unique_id.cpu().numpy(), "agent_type": a.agent_type.cpu().numpy(),
+            "active_state": a.active_state.cpu().numpy(), "age": a.age.cpu().numpy()}
+
+
+def assert_tree(got, ref, exact=(), path="", rel=RTOL):
+    """Integer / bool / key leaves (and those named in `exact`) bit-exact; float leaves within
+    `rel` relative to the leaf's scale (the policy state Z reaches O(100), so an absolute floor
+    of rel * max|leaf| is the meaningful form of "1e-5 relative" for sums of 68 products)."""
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            assert_tree(got[k], v, exact, path + k + ".", rel)
+        elif v.dtype.kind in "iub" or (path + k) in exact:
+            np.testing.assert_array_equal(got[k], v, err_msg=path + k)
+        else:
+            scale = max(1.0, float(np.abs(v[np.isfinite(v)]).max()) if v.size else 1.0)
+            np.testing.assert_allclose(got[k], v, rtol=rel, atol=rel * scale, err_msg=path + k)
+
+
+def make_world(variant, cuda):
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples import foraging as fg
+    fg.use_variant(variant)
+    cfg = ofo.Config(variant)
+    w = fg.Foraging_world(fg.default_params(variant), fgx_random.PRNGKey(cfg.seed), 10)
+    return fg, w, cfg
+
+
+@pytest.mark.parametrize("variant", ["sim", "nb"])
+def test_create_matches_oracle(cuda, variant):
+    fg, w, cfg = make_world(variant, cuda)
+    ow = ofo.World(cfg)
+    exact = {"state." + k for k in ofo.FSTATE if k != "ang"} | {"policy." + k for k in ("J", "tau", "E", "B", "D", "Z")}
+    assert_tree(np_forager(w.foragers_set.agents), ow.fg, exact)
+    assert_tree(np_resource(w.resources_set.agents), ow.rs,
+                {"state.X", "state.Y", "state.energy", "state.rad", "state.time_above_blossom", "params.growth_rate",
+                 "params.decay_rate"})
+    np.testing.assert_array_equal(w.key.cpu().numpy(), ow.key)
+    fg.use_variant("sim")
+
+
+def test_tick_stages_match_oracle(cuda):
+    """interaction, sensor_model, forager step, resource step -- each stage against the oracle
+    on the oracle's own inputs (so that errors do not compound)."""
+    from foragax_b200.base.agent_classes import Params, Signal
+    fg, w, cfg = make_world("sim", cuda)
+    ow = ofo.World(cfg)
+    for _ in range(3):  # advance both worlds so that positions / Z are non-trivial
+        w.step()
+        ow.step()
+    F, Rs = w.foragers_set.agents, w.resources_set.agents
+    assert_tree(np_forager(F), ow.fg, rel=1e-4)  # three compounded ticks
+    # interaction
+    _, e_in, e_out = fg.jit_forager_resource_interaction(F, Rs)
+    r_in, r_out = ofo.interaction(np_forager(F), np_resource(Rs))
+    np.testing.assert_allclose(e_in.cpu().numpy(), r_in, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(e_out.cpu().numpy(), r_out, rtol=1e-6, atol=1e-6)
+    assert (r_in > 0).sum() > 5
+    # sensor model (device sincos within 2 ulp of the oracle's: distances to 1e-5, rare grazing flips)
+    obs = fg.jit_sensor_model(F, Rs, None, w.space.walls).cpu().numpy()
+    robs = ofo.sensor_model(cfg, np_forager(F), np_resource(Rs), cfg.walls)
+    same = np.isclose(obs, robs, rtol=RTOL, atol=ATOL * 60)
+    assert same.mean() > 0.9995, f"sensor mismatch fraction {1 - same.mean():.2e}"
+    assert (robs.reshape(len(robs), -1, 3)[:, :, 1] > 0).sum() > 50  # rays do hit agents
+    # forager step on the oracle's observations
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)  # noqa: E731
+    ref = ofo.forager_step(cfg, robs, r_in, np_forager(F))
+    sp = Params(content={'space': w.space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0,
+                         'energy_max': 15.0})
+    out = fg.Forager.step_agent(sp, Signal(content={'obs': d(robs), 'energy_in': d(r_in)}), F)
+    assert_tree(np_forager(out), ref)
+    # resource step
+    ref_r = ofo.resource_step(cfg, r_out, np_resource(Rs))
+    out_r = fg.Resource.step_agent(Params(content={'blossom_thresh': 3.0}), Signal(content={'energy_out': d(r_out)}), Rs)
+    got_r = np_resource(out_r)
+    assert_tree(got_r, ref_r, {"state.energy", "state.rad", "state.time_above_blossom"})
+
+
+def test_wilson_cowan_step_policy(cuda):
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.base.agent_classes import Params, Signal
+    from foragax_b200.policy.wilson_cowan import WilsonCowan
+    for nn, nobs, nact in ((40, 28, 2), (30, 28, 2), (17, 5, 3), (64, 97, 4)):
+        cfg = ofo.Config("sim", n_neurons=nn, n_obs=nobs, n_act=nact)
+        keys = jr.split(jr.PRNGKey(nn), 300)
+        dk = torch.from_numpy(keys).to(cuda)
+        pol = WilsonCowan.create_policy(Params(content={'num_neurons': nn, 'num_obs': nobs, 'num_actions': nact,
+                                                        'deterministic': True, 'dt': 0.1, 'action_scale': 1.0}), dk)
+        ref = ofo.wc_create(cfg, keys)
+        for k in ("J", "tau", "E", "B", "D"):
+            np.testing.assert_array_equal(pol.params.content[k].cpu().numpy(), ref[k], err_msg=k)
+        rng = np.random.default_rng(0)
+        for _ in range(3):
+            obs = rng.standard_normal((300, nobs)).astype(np.float32)
+            act, ref_Z = ofo.wc_step(cfg, ref, obs)
+            ref["Z"] = ref_Z
+            sig, pol = WilsonCowan.step_policy(Signal(content={'obs': torch.from_numpy(obs).to(cuda)}), pol)
+            scale = max(1.0, float(np.abs(ref_Z).max()))
+            np.testing.assert_allclose(pol.state.content['Z'].cpu().numpy(), ref_Z, rtol=RTOL, atol=RTOL * scale)
+            np.testing.assert_allclose(sig.content['actions'].cpu().numpy(), act, rtol=1e-4, atol=1e-4)
+            # keep the oracle on the device's state so that the per-step comparison does not compound
+            ref["Z"] = pol.state.content['Z'].cpu().numpy().copy()
+
+
+def test_world_ticks_match_oracle_sim_variant(cuda):
+    """Whole ticks (interaction -> sensor -> steps -> Neuroevolution) against the oracle world:
+    counts, masks, ids and keys exact; float state within tolerance."""
+    fg, w, cfg = make_world("sim", cuda)
+    ow = ofo.World(cfg)
+    for t in range(12):
+        nf, nr, le = w.step()
+        onf, onr, ole = ow.step()
+        assert (int(nf), int(nr)) == (onf, onr), f"tick {t}"
+        np.testing.assert_allclose(float(le), ole, rtol=1e-4)
+        gf, gr = np_forager(w.foragers_set.agents), np_resource(w.resources_set.agents)
+        np.testing.assert_array_equal(gf["active_state"], ow.fg["active_state"])
+        np.testing.assert_array_equal(gf["unique_id"], ow.fg["unique_id"])
+        np.testing.assert_array_equal(gr["active_state"], ow.rs["active_state"])
+        np.testing.assert_array_equal(gr["unique_id"], ow.rs["unique_id"])
+        np.testing.assert_array_equal(gr["state"]["key"], ow.rs["state"]["key"])
+        np.testing.assert_array_equal(w.key.cpu().numpy(), ow.key)
+    assert_tree(gf, ow.fg, rel=1e-3)  # twelve compounded ticks of an expanding RNN
+    assert_tree(gr, ow.rs, rel=1e-4)
+
+
+def test_g2_golden_on_the_cuda_path(cuda):
+    """The reference notebook's printed run (golden vector G2, PRNGKey(0)) reproduced by the CUDA
+    path: (num_active_foragers, num_active_resources, life_expectancy) for ticks 0..40."""
+    fg, w, cfg = make_world("nb", cuda)
+    try:
+        for t in range(41):
+            nf, nr, le = w.step()
+            assert (int(nf), int(nr)) == (G2[t][0], G2[t][1]), f"tick {t}: {(int(nf), int(nr))} != {G2[t][:2]}"
+            assert abs(float(le) - G2[t][2]) <= 1e-4 * max(1.0, abs(G2[t][2])), f"tick {t}"
+    finally:
+        fg.use_variant("sim")
