@@ -2,16 +2,23 @@
 """Benchmark of the per-tick agent hot path on the BASELINE.json headline configuration.
 
 Workload: 1,000,000 agents x 32 rays x 1,000 wall segments in a
-4096 x 4096 arena, synthetic (numpy PCG64, seeds 0/1).  A *step* is one tick of the hot
-path over all agents.  Metric: ray-wall tests/sec = agents x rays x walls x ticks / seconds
-(algorithmic pairs).  With N GPUs the agents are sharded by index (strong scaling: the
-1M agents are split), walls are replicated.
+4096 x 4096 arena, synthetic (numpy PCG64 seeds 0/1 for walls / positions, threefry PRNGKey(0)
+for the per-agent policy weights), 90 % of the slots active.  A *step* is one tick of the hot
+path over all agents:
+
+    K1  fgx_raycast_walls   ray_generator + ray_wall_sensor + min/argmin   (FP32-bound)
+    K2  fgx_forager_step    WilsonCowan policy (40 neurons, obs = 32 ray distances + own
+                            energy, 2 actions, per-agent weights) + physics   (HBM-bound)
+
+Metric: ray-wall tests/sec = agents x rays x walls x ticks / seconds (algorithmic pairs); the same
+line also carries agent-steps/sec.  With N GPUs the agents are sharded by index (strong scaling:
+the 1M agents are split), walls are replicated, no data-path collective is needed for this tick.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
-reference path (oracle/c, OpenMP on all host cores): the reference itself needs jax, which
-is not installed in this image.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path
+(oracle/c, OpenMP on all host cores): the reference itself needs jax, which is not installed in
+this image.
 """
 import argparse
 import json
@@ -32,9 +39,18 @@ N_WALLS = 1000
 ARENA = 4096.0
 RAY_SPAN = float(np.float32(np.pi / 4.0))
 RAY_LEN = 60.0
+N_NEURONS, N_OBS, N_ACT = 40, N_RAYS + 1, 2
+DT = 0.1
 FLOP_PER_TEST = 20  # 4 orientation determinants x 5 FP32 ops, no FMA credit
+# K2 algorithmic bytes per ACTIVE agent: weights J,E,D,tau,B + Z read, obs row + 6 state scalars read,
+# Z + 11 state scalars + age written (SURVEY.md 8(d) "Forager step"); 4 B (the flag) per inactive slot
+K2_BYTES_ACTIVE = 4 * (N_NEURONS * N_NEURONS + N_NEURONS * N_OBS + N_ACT * N_NEURONS + 3 * N_NEURONS  # weights + Z
+                       + N_RAYS + 8                                                                  # obs, state in
+                       + N_NEURONS + 12) + 4                                                         # Z, state out
 METRIC = "ray-wall tests/sec"
 UNIT = "tests/s"
+WORKLOAD = ("C4: 1M agents x 32 rays x 1000 walls, 4096^2 arena, WilsonCowan forager 40 neurons / 33 obs "
+            "(SURVEY.md 8d)")
 
 
 def make_workload(n_agents=N_AGENTS, n_walls=N_WALLS):
@@ -56,6 +72,11 @@ def make_workload(n_agents=N_AGENTS, n_walls=N_WALLS):
     active[: int(0.9 * n_agents)] = 1.0
     return {"x": x, "y": y, "ang": ang, "rad": rad, "active": active,
             "walls": [np.ascontiguousarray(w[:, i]) for i in range(4)]}
+
+
+def wall_array(work):
+    w = work["walls"]
+    return np.stack([np.stack([w[0], w[1]], 1), np.stack([w[2], w[3]], 1)], 1)  # [W, 2, 2]
 
 
 class ClockSampler:
@@ -116,58 +137,93 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def cpu_baseline(work, n_sample, repeats=1):
-    """The C restatement of the reference path (oracle/c), OpenMP on every host core, on the
-    first `n_sample` agents of the same workload."""
-    from oracle import c_oracle
-    w = work["walls"]
-    def sample(k):
-        return (work["x"][:k], work["y"][:k], work["ang"][:k], work["active"][:k], N_RAYS, RAY_SPAN, RAY_LEN, *w)
+class CpuTick:
+    """The same tick on the CPU: the C restatement of the reference path (oracle/c, OpenMP on every
+    host core) over the first `n_sample` agents of the workload."""
 
-    args = sample(n_sample)
-    c_oracle.raycast_walls(*sample(256))  # load the library, spin up the OpenMP pool
-    best = None
-    for _ in range(repeats):
+    def __init__(self, work, n_sample):
+        from oracle import agent_methods as oam
+        from oracle import c_oracle
+        from oracle import foraging as ofo
+        from oracle import jax_random as jr
+        self.c = c_oracle
+        self.n = n_sample
+        self.cfg = ofo.Config("sim", n_neurons=N_NEURONS, n_obs=N_OBS, n_act=N_ACT, x_max=ARENA, y_max=ARENA)
+        self.fg = oam.create_agents(lambda p, *a: ofo.forager_create(self.cfg, *a), None, n_sample, n_sample, 1,
+                                    jr.PRNGKey(0))
+        st = self.fg["state"]
+        st["X"], st["Y"], st["ang"] = (work[k][:n_sample].reshape(-1, 1).copy() for k in ("x", "y", "ang"))
+        self.fg["active_state"] = work["active"][:n_sample].copy()
+        self.walls = work["walls"]
+        self.zero = np.zeros(n_sample, np.float32)
+        self.tests = float(n_sample) * N_RAYS * len(self.walls[0])
+        c_oracle.raycast_walls(work["x"][:64], work["y"][:64], work["ang"][:64], None, N_RAYS, RAY_SPAN, RAY_LEN,
+                               *self.walls)  # load the library, spin up the OpenMP pool
+
+    def step(self):
+        st = self.fg["state"]
         t = time.perf_counter()
-        c_oracle.raycast_walls(*args)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    tests = float(n_sample) * N_RAYS * len(w[0])
-    return {"value": tests / best, "unit": UNIT, "cores": c_oracle.threads(), "kind": "port",
-            "sample": f"first {n_sample} agents x {N_RAYS} rays x {len(w[0])} walls of the same workload "
-                      f"({best:.2f} s), C restatement of the reference path with OpenMP (jax is not installed, "
-                      "so the reference itself cannot run)",
-            "seconds": best}
+        dist, _ = self.c.raycast_walls(st["X"], st["Y"], st["ang"], self.fg["active_state"], N_RAYS, RAY_SPAN,
+                                       RAY_LEN, *self.walls)
+        self.c.forager_step(self.cfg, dist, self.zero, self.fg)
+        return time.perf_counter() - t
+
+
+def cpu_baseline(work, n_sample):
+    tick = CpuTick(work, n_sample)
+    sec = tick.step()
+    return {"value": tick.tests / sec, "unit": UNIT, "cores": tick.c.threads(), "kind": "port",
+            "sample": f"one tick (ray cast + forager step) over the first {n_sample} agents x {N_RAYS} rays x "
+                      f"{N_WALLS} walls of the same workload ({sec:.2f} s); C restatement of the reference path "
+                      "with OpenMP (jax is not installed, so the reference itself cannot run)"}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     work = make_workload()
     n_sample = 20_000
+    tick = CpuTick(work, n_sample)
     times = []
     for i in range(args.warmup + args.steps):
-        b = cpu_baseline(work, n_sample)
+        dt = tick.step()
         if i >= args.warmup:
-            times.append(b["seconds"])
-    tests = float(n_sample) * N_RAYS * N_WALLS
+            times.append(dt)
     sec = float(np.mean(times))
-    val = tests / sec
-    from oracle import c_oracle
-    line = {
+    val = tick.tests / sec
+    sample = (f"each step = one tick (ray cast + forager step) over the first {n_sample} agents x {N_RAYS} rays x "
+              f"{N_WALLS} walls; C restatement of the reference path (oracle/c, OpenMP); the reference needs jax, "
+              "absent from this image")
+    print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4: 1M agents x 32 rays x 1000 walls, 4096^2 arena (SURVEY.md 8d)",
-                   "tick": ["ray_generator", "ray_wall_sensor min/argmin"],
-                   "step_sample": f"each step = first {n_sample} agents of the workload"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": c_oracle.threads(), "kind": "port",
-                         "sample": f"first {n_sample} agents x {N_RAYS} rays x {N_WALLS} walls per step; C restatement "
-                                   "of the reference path (oracle/c, OpenMP); the reference needs jax, absent here"},
+        "config": {"workload": WORKLOAD, "tick": ["raycast_walls", "forager_step"], "step_sample": sample},
+        "agent_steps_per_sec": n_sample / sec,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": tick.c.threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
+    }))
+
+
+def build_foragers(work, lo, hi, dev):
+    """The local shard [lo, hi) of the 1M-forager set: native create (threefry weights, PRNGKey(0)),
+    then positions / headings / active flags of the synthetic workload."""
+    import torch
+
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.base.agent_classes import Agent_Set, Params
+    from foragax_b200.base.agent_methods import create_agents
+    from foragax_b200.base.space_methods import create_space
+    from foragax_b200.examples.foraging import Forager
+    space = create_space(0.0, ARENA, 0.0, ARENA, False, wall_array(work))
+    fset = Agent_Set(agent=Forager, num_total_agents=N_AGENTS, num_active_agents=int(0.9 * N_AGENTS), agent_type=1)
+    cp = Params(content={'policy_params': {'num_neurons': N_NEURONS, 'num_obs': N_OBS, 'num_actions': N_ACT, 'dt': DT,
+                                           'action_scale': 1.0, 'deterministic': True}, 'dt': DT, 'space': space})
+    fset.agents = create_agents(cp, fset, fgx_random.PRNGKey(0), shard=(lo, hi - lo))
+    st = fset.agents.state.content
+    for k, src in (("X", "x"), ("Y", "y"), ("ang", "ang")):
+        st[k].copy_(torch.from_numpy(work[src][lo:hi]).to(dev).reshape(-1, 1))
+    return fset, space
 
 
 def run_ours(args):
@@ -185,31 +241,50 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import foragax_b200.base.space_methods as sm
-    from foragax_b200 import _lib as L
-    from foragax_b200.base.space_classes import Point, Wall
+    from foragax_b200.base.agent_classes import Params, Signal
+    from foragax_b200.base.agent_methods import step_agents
 
     work = make_workload()
     lo, hi = rank * N_AGENTS // world, (rank + 1) * N_AGENTS // world
     n_local = hi - lo
-    up = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
-    x, y, ang, act = (up(work[k][lo:hi]) for k in ("x", "y", "ang", "active"))
-    walls = Wall(Point(up(work["walls"][0]), up(work["walls"][1])), Point(up(work["walls"][2]), up(work["walls"][3])))
+    n_active_local = int(work["active"][lo:hi].sum())
+    fset, space = build_foragers(work, lo, hi, dev)
+    F = fset.agents
+    st = F.state.content
     dist_out = torch.empty((n_local, N_RAYS), dtype=torch.float32, device=dev)
     hit_out = torch.empty((n_local, N_RAYS), dtype=torch.int32, device=dev)
-    launches_per_step = 1
+    energy_in = torch.zeros(n_local, dtype=torch.float32, device=dev)
+    step_params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0,
+                                  'energy_max': 15.0})
+    step_input = Signal(content={'obs': dist_out, 'energy_in': energy_in})
+    launches_per_step = 2
+
+    def k1():
+        sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
+                         n_rays=N_RAYS, out=(dist_out, hit_out))
+
+    def k2():
+        fset.agents = step_agents(step_params, step_input, fset)
 
     def tick():
-        sm.raycast_walls((x, y, ang), RAY_SPAN, RAY_LEN, walls, active_state=act, n_rays=N_RAYS,
-                         out=(dist_out, hit_out))
+        k1()
+        k2()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     stream = torch.cuda.current_stream()
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         tick()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -218,40 +293,43 @@ def run_ours(args):
         tick()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     tests_per_step = float(N_AGENTS) * N_RAYS * N_WALLS
     value = tests_per_step / (ms_step * 1e-3)
 
-    # dominant kernel (raycast_walls_kernel): per-launch duration with CUDA events on the launching stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
+    # per-kernel durations, live, with CUDA events on the launching stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    k1_ms, k2_ms = [], []
     for _ in range(args.steps):
-        k0.record(stream)
-        tick()
-        k1.record(stream)
-        k1.synchronize()
-        kms.append(k0.elapsed_time(k1))
-    kernel_ms = float(np.mean(kms))
+        ev[0].record(stream)
+        k1()
+        ev[1].record(stream)
+        k2()
+        ev[2].record(stream)
+        ev[2].synchronize()
+        k1_ms.append(ev[0].elapsed_time(ev[1]))
+        k2_ms.append(ev[1].elapsed_time(ev[2]))
+    k1_ms, k2_ms = float(np.mean(k1_ms)), float(np.mean(k2_ms))
 
-    # end to end through the public API with HOST buffers: pinned H2D of the step's inputs, the tick,
-    # D2H of the step's result (distances + hit indices)
-    hx, hy, ha, hact = (torch.from_numpy(work[k][lo:hi].copy()).pin_memory() for k in ("x", "y", "ang", "active"))
+    # end to end through the public API with HOST buffers: every step copies the agents' pose and active
+    # flags from pinned host memory, runs the tick and reads back its result (ray distances, hit indices
+    # and the stepped positions)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    hx, hy, ha, hact = (pin(work[k][lo:hi]) for k in ("x", "y", "ang", "active"))
     h_dist = torch.empty((n_local, N_RAYS), dtype=torch.float32).pin_memory()
     h_hit = torch.empty((n_local, N_RAYS), dtype=torch.int32).pin_memory()
+    h_x, h_y = torch.empty((n_local, 1)).pin_memory(), torch.empty((n_local, 1)).pin_memory()
 
     def e2e_step():
-        x.copy_(hx, non_blocking=True)
-        y.copy_(hy, non_blocking=True)
-        ang.copy_(ha, non_blocking=True)
-        act.copy_(hact, non_blocking=True)
+        st["X"].copy_(hx.view(-1, 1), non_blocking=True)
+        st["Y"].copy_(hy.view(-1, 1), non_blocking=True)
+        st["ang"].copy_(ha.view(-1, 1), non_blocking=True)
+        F.active_state.copy_(hact, non_blocking=True)
         tick()
         h_dist.copy_(dist_out, non_blocking=True)
         h_hit.copy_(hit_out, non_blocking=True)
+        h_x.copy_(st["X"], non_blocking=True)
+        h_y.copy_(st["Y"], non_blocking=True)
 
     for _ in range(2):
         e2e_step()
@@ -261,12 +339,9 @@ def run_ours(args):
         e2e_step()
     e1.record(stream)
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(t.item()) / args.steps
-    h2d = 4 * 4 * n_local * world
-    d2h = 2 * 4 * N_RAYS * n_local * world
+    e2e_ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    h2d = 4 * 4 * N_AGENTS
+    d2h = (2 * 4 * N_RAYS + 2 * 4) * N_AGENTS
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -274,30 +349,39 @@ def run_ours(args):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_tflops = sms * 128 * sm_max * 1e6 / 1e12  # non-FMA FP32 lanes x clock
-        ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (kernel_ms * 1e-3) / 1e12
+        ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (k1_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": None, "kernel": "raycast_walls_kernel<8>", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "raycast_walls_kernel<8,2>", "kernel_ms": k1_ms,
+                "share_of_step": k1_ms / (k1_ms + k2_ms),
                 "peak_basis": f"{sms} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz, {peak_src} "
                               "MEASURED_PEAKS.json), non-FMA; 20 FLOP per ray-wall test (SURVEY.md 8d)"}
         if clocks and clocks.get("sm_mhz"):
             roof["frac_at_sampled_clock"] = ach / (sms * 128 * clocks["sm_mhz"] * 1e6 / 1e12)
+        k2_bytes = K2_BYTES_ACTIVE * n_active_local + 4 * (n_local - n_active_local)
+        k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        roof2 = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
+                 "traffic": None, "kernel": "forager_step_kernel", "kernel_ms": k2_ms,
+                 "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4: 1M agents x 32 rays x 1000 walls, 4096^2 arena (SURVEY.md 8d)",
-                       "agents": N_AGENTS, "rays": N_RAYS, "walls": N_WALLS, "sharding": f"agents by index / {world}",
-                       "tick": ["ray_generator", "ray_wall_sensor min/argmin (fgx_raycast_walls)"],
-                       "l2": "per-step working set 272 MB (16 MB in, 256 MB out) > 126 MB L2; kernel is FP32-bound"},
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "agents": N_AGENTS, "active_agents": int(0.9 * N_AGENTS), "rays": N_RAYS,
+                       "walls": N_WALLS, "sharding": f"agents by index / {world}, walls replicated",
+                       "tick": ["fgx_raycast_walls (ray_generator + ray_wall_sensor + min/argmin)",
+                                "fgx_forager_step (WilsonCowan policy + physics)"],
+                       "l2": "per-step working set 11.6 GB of per-agent weights + 272 MB ray I/O >> 126 MB L2"},
             "agent_steps_per_sec": N_AGENTS / (ms_step * 1e-3),
-            "roofline": roof,
+            "roofline": roof, "roofline_step_kernel": roof2,
             "e2e": {"value": tests_per_step / (e2e_ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step,
+                    "agent_steps_per_sec": N_AGENTS / (e2e_ms_step * 1e-3)},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(work, args.cpu_sample).items() if k != "seconds"}
+            line["cpu_baseline"] = cpu_baseline(work, args.cpu_sample)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

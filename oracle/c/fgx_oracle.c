@@ -161,3 +161,53 @@ int fgx_oracle_threads(void) {
   return 1;
 #endif
 }
+
+/* ---- vmapped Forager.step_agent with WilsonCowan.step_policy ----------------------------
+ * examples/.../EcoEvoJax/sim.py:74-136, foragax/policy/wilson_cowan.py:34-51 (sim.py variant:
+ * energy cost 0.3*dt*sum|a|, clip(energy_min, energy_max)).  state = 11 arrays float32[n] in the
+ * order X, X_vel, X_acc, Y, Y_vel, Y_acc, ang, energy, rad, time_above_rep, time_below_die.
+ * obs float32[n, n_obs-1]; in place.                                                      */
+void fgx_oracle_forager_step(int64_t n, int nn, int nobs, int nact, float dt, float action_scale, float x_min,
+                             float x_max, float y_min, float y_max, float repr_thresh, float die_thresh,
+                             float energy_min, float energy_max, const float* active, const float* obs,
+                             const float* energy_in, float** st, const float* J, const float* tau, const float* E,
+                             const float* B, const float* D, float* Z, float* age) {
+#pragma omp parallel for schedule(static)
+  for (int64_t a = 0; a < n; ++a) {
+    if (active[a] == 0.0f) continue;
+    float tz[256], nz[256], ob[512], act[8];
+    const float* Ja = J + a * nn * nn;
+    const float* Ea = E + a * nn * nobs;
+    const float* Da = D + a * nact * nn;
+    float* Za = Z + a * nn;
+    for (int k = 0; k < nobs - 1; ++k) ob[k] = obs[a * (nobs - 1) + k];
+    ob[nobs - 1] = st[7][a];
+    for (int j = 0; j < nn; ++j) tz[j] = tanhf(Za[j]);
+    for (int r = 0; r < nn; ++r) {
+      float sJ = 0.0f, sE = 0.0f;
+      for (int j = 0; j < nn; ++j) sJ += Ja[r * nn + j] * tz[j];
+      for (int k = 0; k < nobs; ++k) sE += Ea[r * nobs + k] * ob[k];
+      float dz = ((sJ + sE) + B[a * nn + r]) - Za[r];
+      dz = dz * (10.0f * (1.0f / (1.0f + expf(-tau[a * nn + r]))));
+      nz[r] = Za[r] + dt * dz;
+    }
+    for (int r = 0; r < nn; ++r) { Za[r] = nz[r]; nz[r] = tanhf(nz[r]); }
+    for (int k = 0; k < nact && k < 8; ++k) {
+      float s = 0.0f;
+      for (int j = 0; j < nn; ++j) s += Da[k * nn + j] * nz[j];
+      act[k] = action_scale * tanhf(s);
+    }
+    float X = st[0][a], Y = st[3][a], Xv = st[1][a], Yv = st[4][a];
+    float Xn = X + Xv * dt, Yn = Y + Yv * dt, Xvn = Xv + act[0] * dt, Yvn = Yv + act[1] * dt;
+    if (Xn > x_max || Xn < x_min) { Xn = X; Xvn = -Xv; }
+    if (Yn > y_max || Yn < y_min) { Yn = Y; Yvn = -Yv; }
+    float en = (st[7][a] + energy_in[a]) - (0.3f * dt) * (fabsf(act[0]) + fabsf(act[1]));
+    en = fminf(fmaxf(en, energy_min), energy_max);
+    st[0][a] = Xn; st[3][a] = Yn; st[1][a] = Xvn; st[4][a] = Yvn; st[2][a] = act[0]; st[5][a] = act[1];
+    st[6][a] = atan2f(Yvn, Xvn);
+    st[7][a] = en; st[8][a] = en;
+    st[9][a] = en > repr_thresh ? st[9][a] + dt : 0.0f;
+    st[10][a] = en < die_thresh ? st[10][a] + dt : 0.0f;
+    age[a] += dt;
+  }
+}

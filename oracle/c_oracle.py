@@ -53,3 +53,26 @@ def dice_step(sides, active, draw, key, age):
 
 def threads():
     return load().fgx_oracle_threads()
+
+
+def forager_step(cfg, obs, energy_in, fg):
+    """In place on the oracle's forager dict (oracle/foraging.py layout); sim.py variant only."""
+    lib = load()
+    st = [np.ascontiguousarray(fg["state"][k].reshape(-1)) for k in
+          ("X", "X_vel", "X_acc", "Y", "Y_vel", "Y_acc", "ang", "energy", "rad", "time_above_rep_thresh",
+           "time_below_die_thresh")]
+    arr = (C.c_void_p * 11)(*[_p(a) for a in st])
+    pol = fg["policy"]
+    n = len(fg["unique_id"])
+    f = C.c_float
+    obs = np.ascontiguousarray(obs, np.float32)
+    energy_in = np.ascontiguousarray(energy_in, np.float32)
+    lib.fgx_oracle_forager_step(C.c_int64(n), C.c_int(cfg.n_neurons), C.c_int(cfg.n_obs), C.c_int(cfg.n_act),
+                                f(cfg.dt), f(cfg.action_scale), f(cfg.x_min), f(cfg.x_max), f(cfg.y_min),
+                                f(cfg.y_max), f(cfg.repr_thresh), f(cfg.die_thresh), f(cfg.energy_min),
+                                f(cfg.energy_max), _p(fg["active_state"]), _p(obs), _p(energy_in), arr, _p(pol["J"]),
+                                _p(pol["tau"]), _p(pol["E"]), _p(pol["B"]), _p(pol["D"]), _p(pol["Z"]), _p(fg["age"]))
+    for k, a in zip(("X", "X_vel", "X_acc", "Y", "Y_vel", "Y_acc", "ang", "energy", "rad", "time_above_rep_thresh",
+                     "time_below_die_thresh"), st):
+        fg["state"][k] = a.reshape(-1, 1)
+    return fg
