@@ -9,6 +9,8 @@
 // read exactly once, fully coalesced), then lane r owns output row r and walks it with a
 // rotated column order so that the 32 lanes hit 32 different banks.  16 warps per SM keep
 // ~190 KB of weight rows in flight per SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "geometry.cuh"
 #include "threefry.cuh"
@@ -41,43 +43,120 @@ __host__ __device__ inline WcLayout wc_layout(int n, int nobs, int nact) {
   return l;
 }
 
+// Dot products of TWO weight rows (lane-rows r and r+32, the second optional) with the shared
+// vector `v`, all in shared memory.  The 32 lanes walk 32 different rows at once, so the column
+// order is chosen to keep them on different banks:
+//   len % 4 == 0 : 16-byte chunks (LDS.128), chunk order rotated by r  (pitch 16*k bytes)
+//   len odd      : plain order -- the odd pitch already spreads the banks, v[j] is a broadcast
+//   otherwise    : scalar walk rotated by r
+// Two rows per lane and four accumulators per row give the FMA chain enough independent work to
+// hide the LDS latency without relying on other warps.
+__device__ __forceinline__ void row_dot2(const float* rowA, const float* rowB, const float* v, int len, int r,
+                                         float& outA, float& outB) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  if ((len & 3) == 0) {
+    const int nch = len >> 2;
+    const float4* A4 = reinterpret_cast<const float4*>(rowA);
+    const float4* B4 = reinterpret_cast<const float4*>(rowB);
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    int c = r % nch;
+#pragma unroll 2
+    for (int t = 0; t < nch; ++t) {
+      const float4 x = v4[c], wa = A4[c], wb = B4[c];
+      a0 += wa.x * x.x; a1 += wa.y * x.y; a2 += wa.z * x.z; a3 += wa.w * x.w;
+      b0 += wb.x * x.x; b1 += wb.y * x.y; b2 += wb.z * x.z; b3 += wb.w * x.w;
+      c = c + 1 == nch ? 0 : c + 1;
+    }
+  } else if (len & 1) {
+    int j = 0;
+    for (; j + 4 <= len; j += 4) {
+      const float x0 = v[j], x1 = v[j + 1], x2 = v[j + 2], x3 = v[j + 3];
+      a0 += rowA[j] * x0; a1 += rowA[j + 1] * x1; a2 += rowA[j + 2] * x2; a3 += rowA[j + 3] * x3;
+      b0 += rowB[j] * x0; b1 += rowB[j + 1] * x1; b2 += rowB[j + 2] * x2; b3 += rowB[j + 3] * x3;
+    }
+    for (; j < len; ++j) {
+      a0 += rowA[j] * v[j];
+      b0 += rowB[j] * v[j];
+    }
+  } else {
+    int j = r % len;
+    for (int t = 0; t < len; ++t) {
+      a0 += rowA[j] * v[j];
+      b0 += rowB[j] * v[j];
+      j = j + 1 == len ? 0 : j + 1;
+    }
+  }
+  outA = (a0 + a1) + (a2 + a3);
+  outB = (b0 + b1) + (b2 + b3);
+}
+
 // one leaf row of one agent -> shared memory: TMA bulk copy when 16-byte clean, else lanes copy
 __device__ __forceinline__ uint32_t leaf_tma_bytes(const float* base, int row_floats) {
   return ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_floats & 3) == 0) ? (uint32_t)row_floats * 4u : 0u;
 }
 
+// Iterator over the ACTIVE agents of this warp's sequence a0, a0+GW, a0+2GW, ...: one coalesced
+// probe of 32 candidates (ballot) serves up to 32 agents, so inactive runs cost nothing per slot.
+struct ActiveScan {
+  int64_t base, probe_base;
+  unsigned mask;
+  __device__ __forceinline__ int64_t next(const float* __restrict__ active, int64_t GW, int64_t n_agents, int lane) {
+    while (mask == 0u) {
+      if (base >= n_agents) return n_agents;
+      const int64_t mine = base + lane * GW;
+      mask = __ballot_sync(0xffffffffu, mine < n_agents && active[mine] != 0.0f);
+      probe_base = base;
+      base += 32 * GW;
+    }
+    const int b = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    return probe_base + (int64_t)b * GW;
+  }
+};
+
 __global__ void __launch_bounds__(FS_WARPS * 32)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
                         const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
-                        float* __restrict__ actions_out) {
+                        float* __restrict__ actions_out, int slots) {
   // actions_out != nullptr: policy-only mode (WilsonCowan.step_policy on its own): obs has all n_obs
-  // columns, actions are written out and the Forager physics is skipped
+  // columns, actions are written out and the Forager physics is skipped.
+  // slots == 2: each warp owns two weight slots -- while it computes agent i from one, the TMA copies
+  // of its next active agent land in the other (mbarrier per slot).  slots == 1: one slot per warp and
+  // twice the warps per SM; the copies of the other warps overlap this warp's compute.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = p.n_neurons, nobs = p.n_obs, nact = p.n_act;
   const WcLayout L = wc_layout(n, nobs, nact);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
-  float* sm = reinterpret_cast<float*>(smem_raw + 16 * ((FS_WARPS * 8 + 15) / 16)) + (size_t)warp * L.total;
-  if (lane == 0) mbar_init(bar, 1);
+  const int nwarps = blockDim.x >> 5;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
+  float* slot0 = reinterpret_cast<float*>(smem_raw + 16 * FS_WARPS) + (size_t)warp * slots * L.total;
+  if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
   __syncwarp();
-  uint32_t parity = 0;
+  uint32_t parity[2] = {0u, 0u};
 
+  const int obs_cols = actions_out ? nobs : nobs - 1;
   const uint32_t bJ = leaf_tma_bytes(pol.J, n * n), bE = leaf_tma_bytes(pol.E, n * nobs),
                  bD = leaf_tma_bytes(pol.D, nact * n), bT = leaf_tma_bytes(pol.tau, n),
-                 bB = leaf_tma_bytes(pol.B, n), bZ = leaf_tma_bytes(pol.Z, n);
-  const uint32_t tx = bJ + bE + bD + bT + bB + bZ;
+                 bB = leaf_tma_bytes(pol.B, n), bZ = leaf_tma_bytes(pol.Z, n),
+                 bO = leaf_tma_bytes(obs_in, obs_cols);
+  const uint32_t tx = bJ + bE + bD + bT + bB + bZ + bO;
 
-  const int nwarps = blockDim.x >> 5;
-  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
-  for (int64_t a = gw; a < n_agents; a += GW) {
-    if (active[a] == 0.0f) continue;  // lax.cond(active_state): inactive slots pass through
+  // lane l < 11 owns state leaf l of an agent, lane 11 its age, lane 12 its energy_in: the scalars are
+  // fetched when the agent's copies are issued and shared by shuffles when it is computed
+  float* const* leaves = reinterpret_cast<float* const*>(&st);
+  const float* my_leaf = actions_out ? nullptr : (lane < 11 ? leaves[lane] : (lane == 11 ? age : (lane == 12 ? energy_in : nullptr)));
+
+  auto issue = [&](int64_t a, int s) -> float {
+    float* sm = slot0 + (size_t)s * L.total;
+    uint64_t* bar = bars + s;
     const float* gJ = pol.J + a * n * n;
     const float* gE = pol.E + a * n * nobs;
     const float* gD = pol.D + a * nact * n;
     const float* gT = pol.tau + a * n;
     const float* gB = pol.B + a * n;
-    float* gZ = pol.Z + a * n;
+    const float* gZ = pol.Z + a * n;
+    const float* gO = obs_in + a * obs_cols;
     if (lane == 0 && tx) {
       mbar_expect_tx(bar, tx);
       if (bJ) tma_bulk_g2s(sm + L.J, gJ, bJ, bar);
@@ -86,6 +165,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
       if (bT) tma_bulk_g2s(sm + L.tau, gT, bT, bar);
       if (bB) tma_bulk_g2s(sm + L.B, gB, bB, bar);
       if (bZ) tma_bulk_g2s(sm + L.Z, gZ, bZ, bar);
+      if (bO) tma_bulk_g2s(sm + L.obs, gO, bO, bar);
     }
     if (!bJ) for (int i = lane; i < n * n; i += 32) sm[L.J + i] = __ldg(gJ + i);
     if (!bE) for (int i = lane; i < n * nobs; i += 32) sm[L.E + i] = __ldg(gE + i);
@@ -93,76 +173,92 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     if (!bT) for (int i = lane; i < n; i += 32) sm[L.tau + i] = __ldg(gT + i);
     if (!bB) for (int i = lane; i < n; i += 32) sm[L.B + i] = __ldg(gB + i);
     if (!bZ) for (int i = lane; i < n; i += 32) sm[L.Z + i] = gZ[i];
-    // obs = concat(sensor obs, own energy) (sim.py:80-82)
-    const float energy = actions_out ? 0.0f : st.energy[a];
-    if (actions_out) {
-      for (int k = lane; k < nobs; k += 32) sm[L.obs + k] = __ldg(obs_in + a * nobs + k);
-    } else {
-      for (int k = lane; k < nobs - 1; k += 32) sm[L.obs + k] = __ldg(obs_in + a * (nobs - 1) + k);
-      if (lane == 0) sm[L.obs + nobs - 1] = energy;
-    }
+    if (!bO) for (int k = lane; k < obs_cols; k += 32) sm[L.obs + k] = __ldg(gO + k);
+    return my_leaf ? my_leaf[a] : 0.0f;
+  };
+
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
+  ActiveScan scan{gw, gw, 0u};
+  int64_t a = scan.next(active, GW, n_agents, lane);
+  int s = 0;
+  float sv = 0.0f;
+  if (a < n_agents) sv = issue(a, 0);
+  while (a < n_agents) {
+    const int64_t a_next = scan.next(active, GW, n_agents, lane);
+    float sv_next = 0.0f;
+    if (slots == 2 && a_next < n_agents) sv_next = issue(a_next, s ^ 1);  // slot s^1 was released by the last __syncwarp
+    float* sm = slot0 + (size_t)s * L.total;
+    float* gZ = pol.Z + a * n;
+    const float energy = __shfl_sync(0xffffffffu, sv, 7);
     __syncwarp();
     if (tx) {
-      mbar_wait(bar, parity);
-      parity ^= 1u;
+      mbar_wait(bars + s, parity[s]);
+      parity[s] ^= 1u;
     }
+    if (!actions_out && lane == 0) sm[L.obs + nobs - 1] = energy;  // obs = concat(sensor obs, own energy)
     // WilsonCowan.step_policy (wilson_cowan.py:34-51)
     for (int j = lane; j < n; j += 32) sm[L.tz + j] = tanhf(sm[L.Z + j]);
     __syncwarp();
-    const int rotJ = (n & 1) ? 0 : 1, rotE = (nobs & 1) ? 0 : 1;  // odd bank stride for the row walk
-    for (int r = lane; r < n; r += 32) {
-      float sJ = 0.0f, sE = 0.0f;
-      const float* rowJ = sm + L.J + r * n;
-      int j = rotJ ? r % n : 0;
-      for (int t = 0; t < n; ++t) {
-        sJ += rowJ[j] * sm[L.tz + j];
-        j = j + 1 == n ? 0 : j + 1;
+    for (int rA = lane; rA < n; rA += 64) {  // lane-rows rA and rA+32 together
+      const bool hasB = rA + 32 < n;
+      const int rB = hasB ? rA + 32 : rA;
+      float sJ[2], sE[2];
+      row_dot2(sm + L.J + rA * n, sm + L.J + rB * n, sm + L.tz, n, rA, sJ[0], sJ[1]);
+      row_dot2(sm + L.E + rA * nobs, sm + L.E + rB * nobs, sm + L.obs, nobs, rA, sE[0], sE[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !hasB) break;
+        const int r = h ? rB : rA;
+        const float z = sm[L.Z + r];
+        float dz = ((sJ[h] + sE[h]) + sm[L.B + r]) - z;
+        dz = dz * (10.0f * sigmoidf_(sm[L.tau + r]));
+        const float nz = z + p.policy_dt * dz;
+        gZ[r] = nz;
+        sm[L.tnz + r] = tanhf(nz);
       }
-      const float* rowE = sm + L.E + r * nobs;
-      int k = rotE ? r % nobs : 0;
-      for (int t = 0; t < nobs; ++t) {
-        sE += rowE[k] * sm[L.obs + k];
-        k = k + 1 == nobs ? 0 : k + 1;
-      }
-      const float z = sm[L.Z + r];
-      float dz = ((sJ + sE) + sm[L.B + r]) - z;
-      dz = dz * (10.0f * sigmoidf_(sm[L.tau + r]));
-      const float nz = z + p.policy_dt * dz;
-      gZ[r] = nz;
-      sm[L.tnz + r] = tanhf(nz);
     }
     __syncwarp();
     float act0 = 0.0f, act1 = 0.0f;  // the Forager uses actions[0], actions[1] (sim.py:86-87)
     for (int k = 0; k < nact; ++k) {
-      float s = 0.0f;
-      for (int j = lane; j < n; j += 32) s += sm[L.D + k * n + j] * sm[L.tnz + j];
+      float d = 0.0f;
+      for (int j = lane; j < n; j += 32) d += sm[L.D + k * n + j] * sm[L.tnz + j];
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      const float v = p.action_scale * tanhf(s);
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      const float v = p.action_scale * tanhf(d);
       if (k == 0) act0 = v;
       if (k == 1) act1 = v;
       if (actions_out && lane == 0) actions_out[a * nact + k] = v;
     }
+    const float X = __shfl_sync(0xffffffffu, sv, 0), Xv = __shfl_sync(0xffffffffu, sv, 1);
+    const float Y = __shfl_sync(0xffffffffu, sv, 3), Yv = __shfl_sync(0xffffffffu, sv, 4);
+    const float tar = __shfl_sync(0xffffffffu, sv, 9), tbd = __shfl_sync(0xffffffffu, sv, 10);
+    const float age0 = __shfl_sync(0xffffffffu, sv, 11), e_in = __shfl_sync(0xffffffffu, sv, 12);
     if (lane == 0 && !actions_out) {
       // Forager.step_agent physics (sim.py:89-128)
       const float dt = p.dt;
-      const float X = st.X[a], Y = st.Y[a], Xv = st.X_vel[a], Yv = st.Y_vel[a];
       float Xn = f_add(X, f_mul(Xv, dt)), Yn = f_add(Y, f_mul(Yv, dt));
       float Xvn = f_add(Xv, f_mul(act0, dt)), Yvn = f_add(Yv, f_mul(act1, dt));
       if (Xn > p.x_max || Xn < p.x_min) { Xn = X; Xvn = -Xv; }
       if (Yn > p.y_max || Yn < p.y_min) { Yn = Y; Yvn = -Yv; }
-      float en = f_sub(f_add(energy, energy_in[a]), f_mul(p.energy_cost_dt, f_add(fabsf(act0), fabsf(act1))));
+      float en = f_sub(f_add(energy, e_in), f_mul(p.energy_cost_dt, f_add(fabsf(act0), fabsf(act1))));
       en = fminf(en, p.energy_max);
       if (p.clip_min) en = fmaxf(en, p.energy_min);
       st.X[a] = Xn; st.Y[a] = Yn; st.X_vel[a] = Xvn; st.Y_vel[a] = Yvn;
       st.X_acc[a] = act0; st.Y_acc[a] = act1;
       st.ang[a] = atan2f(Yvn, Xvn);
       st.energy[a] = en; st.rad[a] = en;
-      st.time_above_rep_thresh[a] = en > p.repr_thresh ? f_add(st.time_above_rep_thresh[a], dt) : 0.0f;
-      st.time_below_die_thresh[a] = en < p.die_thresh ? f_add(st.time_below_die_thresh[a], dt) : 0.0f;
-      age[a] = f_add(age[a], dt);
+      st.time_above_rep_thresh[a] = en > p.repr_thresh ? f_add(tar, dt) : 0.0f;
+      st.time_below_die_thresh[a] = en < p.die_thresh ? f_add(tbd, dt) : 0.0f;
+      age[a] = f_add(age0, dt);
     }
-    __syncwarp();  // all lanes are done with the slots before the next agent's copies land
+    __syncwarp();  // all lanes are done with slot s before the copies of a later agent land in it
+    if (slots == 1) {
+      if (a_next < n_agents) sv_next = issue(a_next, 0);
+    } else {
+      s ^= 1;
+    }
+    a = a_next;
+    sv = sv_next;
   }
 }
 
@@ -315,9 +411,14 @@ static int launch_forager_step(const char* what, const fgx_forager_params_t& p, 
                                const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
   using namespace fgx;
   const WcLayout L = wc_layout(p.n_neurons, p.n_obs, p.n_act);
-  const size_t head = 16 * ((FS_WARPS * 8 + 15) / 16), per_warp = (size_t)L.total * sizeof(float);
+  // one weight slot per warp and two CTAs per SM when that fits (most memory-level parallelism);
+  // FGX_FS_SLOTS=2 selects the double-buffered variant (tuning hook, see profiles/)
+  int slots = 1;
+  if (const char* v = getenv("FGX_FS_SLOTS")) slots = atoi(v) == 2 ? 2 : 1;
+  const size_t head = 16 * FS_WARPS, per_warp = (size_t)slots * L.total * sizeof(float);
+  const size_t budget = slots == 2 ? 226 * 1024 : 113 * 1024;
   int warps = FS_WARPS;
-  while (warps > 1 && head + warps * per_warp > 113 * 1024) --warps;  // aim at 2 CTAs per SM
+  while (warps > 1 && head + warps * per_warp > budget) --warps;
   FGX_REQUIRE(head + warps * per_warp <= 227 * 1024,
               "%s: policy too large for shared memory (%zu bytes per agent)", what, per_warp);
   const size_t smem = head + warps * per_warp;
@@ -329,7 +430,7 @@ static int launch_forager_step(const char* what, const fgx_forager_params_t& p, 
   const int64_t need = ceil_div(n, warps);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   forager_step_kernel<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol,
-                                                                             age, actions);
+                                                                             age, actions, slots);
   return check_launch(what);
 }
 
