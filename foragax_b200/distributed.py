@@ -1,0 +1,99 @@
+"""Multi-GPU plumbing for the agent hot path: one process per GPU (``torch.distributed``, NCCL over
+NVLink on the GPU box; gloo in the CPU tests).
+
+The reference is single-process / single-device.  Sharding follows SURVEY.md
+8(e): agents are split by slot index into contiguous blocks, walls and broadcast params are
+replicated.  Ray-wall sensing and the fused step need no exchange; the two exchange steps are
+
+* :func:`all_gather_positions` -- ``float4 (x, y, rad, active)`` of every agent, needed only by
+  agent-agent sensing (16 B per agent);
+* :func:`global_partition_offsets` -- one int32 count per rank, all-gathered, whose exclusive
+  prefix sum places each rank's locally compacted (selected / unselected) slot lists inside the
+  global stable partition that ``select_agents`` returns on one GPU.
+
+Nothing here touches agent payload; the collectives move 16 B/agent and 4 B/rank.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def shard_bounds(n_total, world_size=None, rank=None):
+    """Contiguous block ``[lo, hi)`` of slot indices owned by ``rank``."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    return rank * n_total // world_size, (rank + 1) * n_total // world_size
+
+
+def all_gather_counts(local_count):
+    """int32/int64 scalar tensor per rank -> int64[world] (same device / backend as the input)."""
+    r, w = world()
+    c = local_count.reshape(1).to(torch.int64)
+    if w == 1:
+        return c
+    out = torch.empty(w, dtype=torch.int64, device=c.device)
+    dist.all_gather_into_tensor(out, c)
+    return out
+
+
+def global_partition_offsets(local_selected, n_local):
+    """Where this rank's locally compacted lists go in the GLOBAL stable partition
+    ("all selected slots ascending, then all unselected ascending", agent_methods.py:66-71).
+
+    Returns ``(sel_offset, unsel_offset, total_selected)`` as int64 0-d tensors: the rank's selected
+    slots occupy ``[sel_offset, sel_offset + local_selected)`` and its unselected ones
+    ``[unsel_offset, unsel_offset + n_local - local_selected)`` of the global permutation.
+    """
+    r, w = world()
+    sel = all_gather_counts(local_selected)
+    tot = all_gather_counts(torch.as_tensor(n_local, device=local_selected.device))
+    sel_before = sel[:r].sum()
+    unsel_before = (tot[:r] - sel[:r]).sum()
+    total_sel = sel.sum()
+    return sel_before, total_sel + unsel_before, total_sel
+
+
+def global_partition(local_perm, local_selected, lo, n_total):
+    """Assemble the global permutation from every rank's local stable partition.
+
+    ``local_perm`` int32[n_local] (local slot indices: selected ascending, then unselected),
+    ``local_selected`` its selected count, ``lo`` the rank's first global slot.  Returns
+    ``(total_selected, global_perm int32[n_total])`` -- identical on every rank and equal to the
+    single-GPU result.  (Used when the permutation itself must be materialised; the compaction
+    kernels only need :func:`global_partition_offsets`.)
+    """
+    r, w = world()
+    n_local = local_perm.shape[0]
+    so, uo, total = global_partition_offsets(local_selected, n_local)
+    k = int(local_selected)
+    gperm = torch.zeros(n_total, dtype=torch.int32, device=local_perm.device)
+    gids = local_perm + int(lo)
+    gperm[int(so):int(so) + k] = gids[:k]
+    gperm[int(uo):int(uo) + n_local - k] = gids[k:]
+    if w > 1:
+        dist.all_reduce(gperm, op=dist.ReduceOp.SUM)  # disjoint segments: the sum is a concatenation
+    return total.to(torch.int32), gperm
+
+
+def all_gather_positions(x, y, rad, active):
+    """``float4 (x, y, rad, active)`` of all agents, rank order = slot order: float32[n_total, 4]."""
+    r, w = world()
+    local = torch.stack([x.reshape(-1), y.reshape(-1), rad.reshape(-1), active.reshape(-1)], dim=1).contiguous()
+    if w == 1:
+        return local
+    counts = all_gather_counts(torch.as_tensor(local.shape[0], device=local.device))
+    if int(counts.min()) == int(counts.max()):
+        out = torch.empty((w * local.shape[0], 4), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+        return out
+    # ragged shards: pad to the largest one, gather, drop the padding
+    m = int(counts.max())
+    padded = torch.zeros((m, 4), dtype=torch.float32, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((w * m, 4), dtype=torch.float32, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[i * m: i * m + int(c)] for i, c in enumerate(counts)], dim=0)
