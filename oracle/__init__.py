@@ -14,13 +14,16 @@ semantics whose results that path exposes (jax is absent from
 
 Parity pinning status
 ---------------------
-* pinned: ``jax_random`` (threefry KATs, legacy counter layout) and the
-  select / remove / sort / add chain, by the reference's own printed notebook
-  output G1 (``examples/basic/hello_world/hello_world.ipynb:92-99``) and by G2
-  ticks 0-3 (``examples/many_agent_systems/foraging_agents/EcoEvoJax/sim.ipynb``).
-* parity unpinned: ``space_methods`` geometry (``ray_wall_sensor``,
-  ``ray_agent_sensor``, ``ray_generator``, ``check_collision``), the
-  WilsonCowan policy and ``normal`` -- the reference has no tests or golden
-  vectors for them and cannot be executed here (no jax); they are restated
-  from source and checked on hand-derived cases only.
+* pinned by the reference's own printed notebook outputs:
+  G1 (``examples/basic/hello_world/hello_world.ipynb:92-99``; ``tests/test_oracle_g1.py``) pins
+  ``jax_random`` (legacy counter layout) and the select / remove / stable sort / add chain
+  bit-exactly; G2 (``examples/many_agent_systems/foraging_agents/EcoEvoJax/sim.ipynb`` cell
+  output; ``tests/test_oracle_g2.py``) is reproduced for ticks 0-40 by the full restatement in
+  ``foraging.py`` and thereby pins -- through integer counts that depend on them -- ``uniform``
+  with bounds, ``bernoulli``, ``normal``, the serial key chain of ``add_agents``, the sensor
+  composition (``ray_generator``, ``ray_wall_sensor``, ``ray_agent_sensor``, first-argmin) and the
+  WilsonCowan policy.  Threefry is also pinned by the Random123 known-answer vectors.
+* parity unpinned (no reference golden data exists; restated from source, hand-derived cases
+  only): ``check_collision``, the collinear special cases of ``ray_wall_sensor`` that G2 does not
+  exercise, NaN / -0.0 / int-key sort edge cases.
 """
