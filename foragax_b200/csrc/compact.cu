@@ -20,19 +20,11 @@ constexpr int SEL_ITEMS = 8;
 constexpr int SEL_TILE = SEL_BLOCK * SEL_ITEMS;  // 2048 slots per tile
 constexpr int SEL_WARPS = SEL_BLOCK / 32;
 
-struct SelScratch {
-  unsigned int done;   // CTAs finished with pass A
-  int32_t total;       // selected count
-  int32_t pad[2];
-  // followed by int32 tile_offset[num_tiles]
-};
-
-__device__ __forceinline__ bool eval_term(const fgx_pred_term_t& t, int64_t i) {
-  const int64_t e = i * (int64_t)t.stride;
-  if (t.dtype == FGX_F32) {
-    const float v = __ldg(reinterpret_cast<const float*>(t.data) + e);
-    const float c = __uint_as_float(t.imm_bits);
-    switch (t.op) {
+// A comparison on a value already in a register (bits = raw 32-bit word, or the byte zero-extended)
+__device__ __forceinline__ bool compare_bits(uint32_t bits, int dtype, int op, uint32_t imm) {
+  if (dtype == FGX_F32) {
+    const float v = __uint_as_float(bits), c = __uint_as_float(imm);
+    switch (op) {
       case FGX_OP_EQ: return v == c;
       case FGX_OP_NE: return v != c;
       case FGX_OP_LT: return v < c;
@@ -41,39 +33,17 @@ __device__ __forceinline__ bool eval_term(const fgx_pred_term_t& t, int64_t i) {
       case FGX_OP_GE: return v >= c;
       default: return v != 0.0f;
     }
-  } else if (t.dtype == FGX_I32) {
-    const int32_t v = __ldg(reinterpret_cast<const int32_t*>(t.data) + e);
-    const int32_t c = (int32_t)t.imm_bits;
-    switch (t.op) {
-      case FGX_OP_EQ: return v == c;
-      case FGX_OP_NE: return v != c;
-      case FGX_OP_LT: return v < c;
-      case FGX_OP_LE: return v <= c;
-      case FGX_OP_GT: return v > c;
-      case FGX_OP_GE: return v >= c;
-      default: return v != 0;
-    }
-  } else {  // FGX_U8 (bool leaves)
-    const int32_t v = __ldg(reinterpret_cast<const uint8_t*>(t.data) + e);
-    const int32_t c = (int32_t)t.imm_bits;
-    switch (t.op) {
-      case FGX_OP_EQ: return v == c;
-      case FGX_OP_NE: return v != c;
-      case FGX_OP_LT: return v < c;
-      case FGX_OP_LE: return v <= c;
-      case FGX_OP_GT: return v > c;
-      case FGX_OP_GE: return v >= c;
-      default: return v != 0;
-    }
   }
-}
-
-__device__ __forceinline__ bool eval_pred(const fgx_predicate_t& p, int64_t i) {
-  unsigned idx = 0;
-#pragma unroll
-  for (int t = 0; t < 4; ++t)
-    if (t < p.n_terms) idx |= (eval_term(p.term[t], i) ? 1u : 0u) << t;
-  return (p.lut >> idx) & 1u;
+  const int32_t v = (int32_t)bits, c = (int32_t)imm;
+  switch (op) {
+    case FGX_OP_EQ: return v == c;
+    case FGX_OP_NE: return v != c;
+    case FGX_OP_LT: return v < c;
+    case FGX_OP_LE: return v <= c;
+    case FGX_OP_GT: return v > c;
+    case FGX_OP_GE: return v >= c;
+    default: return v != 0;
+  }
 }
 
 // element handled by (warp w, round r, lane l) of a tile: contiguous per warp
@@ -81,15 +51,46 @@ __device__ __forceinline__ int64_t tile_elem(int64_t tile, int w, int r, int l) 
   return tile * SEL_TILE + w * (32 * SEL_ITEMS) + r * 32 + l;
 }
 
-__device__ __forceinline__ int tile_count(const fgx_predicate_t& p, int64_t tile, int64_t n, int* warp_sums) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  int c = 0;
+// Truth values of ONE term for the thread's SEL_ITEMS slots, as a bit mask.  The loads are issued
+// back to back with no control flow between them (all in flight together); the comparison runs on
+// registers afterwards.
+template <typename T>
+__device__ __forceinline__ unsigned term_mask(const fgx_pred_term_t& t, int64_t tile, int64_t n, int w, int l) {
+  const T* __restrict__ base = reinterpret_cast<const T*>(t.data);
+  uint32_t raw[SEL_ITEMS];
 #pragma unroll
   for (int r = 0; r < SEL_ITEMS; ++r) {
-    const int64_t i = tile_elem(tile, w, r, l);
-    const bool s = i < n && eval_pred(p, i);
-    c += __popc(__ballot_sync(0xffffffffu, s));
+    const int64_t i = min(tile_elem(tile, w, r, l), n - 1);
+    raw[r] = (uint32_t)__ldg(base + i * t.stride);
   }
+  unsigned m = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_ITEMS; ++r) m |= (compare_bits(raw[r], t.dtype, t.op, t.imm_bits) ? 1u : 0u) << r;
+  return m;
+}
+
+// selected flags of the thread's SEL_ITEMS slots (bit r = slot of round r)
+__device__ __forceinline__ unsigned tile_flags(const fgx_predicate_t& p, int64_t tile, int64_t n, int w, int l) {
+  unsigned tm[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    if (t < p.n_terms)
+      tm[t] = p.term[t].dtype == FGX_U8 ? term_mask<uint8_t>(p.term[t], tile, n, w, l)
+                                        : term_mask<uint32_t>(p.term[t], tile, n, w, l);
+  unsigned f = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_ITEMS; ++r) {
+    const unsigned idx = ((tm[0] >> r) & 1u) | (((tm[1] >> r) & 1u) << 1) | (((tm[2] >> r) & 1u) << 2) |
+                         (((tm[3] >> r) & 1u) << 3);
+    const bool in = tile_elem(tile, w, r, l) < n;
+    f |= (in ? (p.lut >> idx) & 1u : 0u) << r;
+  }
+  return f;
+}
+
+__device__ __forceinline__ int tile_count(const fgx_predicate_t& p, int64_t tile, int64_t n, int* warp_sums) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int c = __reduce_add_sync(0xffffffffu, __popc(tile_flags(p, tile, n, w, l)));
   if (l == 0) warp_sums[w] = c;
   __syncthreads();
   int tot = 0;
@@ -99,24 +100,25 @@ __device__ __forceinline__ int tile_count(const fgx_predicate_t& p, int64_t tile
   return tot;
 }
 
-__device__ __forceinline__ void tile_scatter(const fgx_predicate_t& p, int64_t tile, int64_t n, int32_t tile_off,
-                                             int32_t total, int32_t* __restrict__ perm, int* warp_sums) {
+__device__ __forceinline__ int tile_scatter(const fgx_predicate_t& p, int64_t tile, int64_t n, int32_t tile_off,
+                                            int32_t total, int32_t* __restrict__ perm, int* warp_sums) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const unsigned flags = tile_flags(p, tile, n, w, l);
   unsigned ball[SEL_ITEMS];
   int c = 0;
 #pragma unroll
   for (int r = 0; r < SEL_ITEMS; ++r) {
-    const int64_t i = tile_elem(tile, w, r, l);
-    const bool s = i < n && eval_pred(p, i);
-    ball[r] = __ballot_sync(0xffffffffu, s);
+    ball[r] = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
     c += __popc(ball[r]);
   }
   if (l == 0) warp_sums[w] = c;
   __syncthreads();
-  int before = tile_off;
+  int before = tile_off, tile_total = 0;
 #pragma unroll
-  for (int k = 0; k < SEL_WARPS; ++k)
+  for (int k = 0; k < SEL_WARPS; ++k) {
     if (k < w) before += warp_sums[k];
+    tile_total += warp_sums[k];
+  }
   __syncthreads();
   const unsigned lt = lanemask_lt();
 #pragma unroll
@@ -130,66 +132,54 @@ __device__ __forceinline__ void tile_scatter(const fgx_predicate_t& p, int64_t t
     }
     before += __popc(ball[r]);
   }
+  return tile_total;
 }
 
-// pass A: per-tile counts; the last CTA to finish turns them into exclusive offsets
-__global__ void __launch_bounds__(SEL_BLOCK) select_count_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
-                                                                int64_t num_tiles, SelScratch* __restrict__ sc,
-                                                                int32_t* __restrict__ tile_off,
-                                                                int32_t* __restrict__ count_out) {
-  __shared__ int warp_sums[SEL_WARPS];
-  __shared__ bool is_last;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int c = tile_count(p, tile, n, warp_sums);
-    if (threadIdx.x == 0) tile_off[tile] = c;
-  }
-  __threadfence();
+// Both passes give CTA b the CONTIGUOUS tile range [b*T, (b+1)*T), so only per-CTA counts are
+// exchanged: pass B derives its starting rank (sum of the counts of the CTAs before it) and the
+// global total with two block reductions over <= SEL_MAX_GRID ints -- no serial scan, no atomics.
+constexpr int SEL_MAX_GRID = 4096;
+
+__device__ __forceinline__ int block_sum(int v, int* warp_sums) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&sc->done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // single-CTA exclusive scan of tile counts (num_tiles <= n/2048)
-  __shared__ int carry;
-  __shared__ int wsum[SEL_WARPS];
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int64_t base = 0; base < num_tiles; base += SEL_BLOCK) {
-    const int64_t t = base + threadIdx.x;
-    const int v = t < num_tiles ? __ldcg(tile_off + t) : 0;
-    int inc = v;
+  int t = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (l >= d) inc += o;
-    }
-    if (l == 31) wsum[w] = inc;
-    __syncthreads();
-    int wbase = carry;
-    for (int k = 0; k < w; ++k) wbase += wsum[k];
-    if (t < num_tiles) tile_off[t] = wbase + inc - v;
-    __syncthreads();
-    if (threadIdx.x == SEL_BLOCK - 1) carry = wbase + inc;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    sc->total = carry;
-    *count_out = carry;
-    sc->done = 0;  // re-arm for the next call on this scratch
-  }
+  for (int k = 0; k < SEL_WARPS; ++k) t += warp_sums[k];
+  __syncthreads();
+  return t;
+}
+
+// pass A: selected count of each CTA's tile range
+__global__ void __launch_bounds__(SEL_BLOCK) select_count_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
+                                                                int64_t num_tiles, int64_t tiles_per_cta,
+                                                                int32_t* __restrict__ cta_count) {
+  __shared__ int warp_sums[SEL_WARPS];
+  const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
+  int c = 0;
+  for (int64_t tile = t0; tile < t1; ++tile) c += tile_count(p, tile, n, warp_sums);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
 }
 
 // pass B: scatter
 __global__ void __launch_bounds__(SEL_BLOCK) select_scatter_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
-                                                                  int64_t num_tiles,
-                                                                  const SelScratch* __restrict__ sc,
-                                                                  const int32_t* __restrict__ tile_off,
-                                                                  int32_t* __restrict__ perm) {
+                                                                  int64_t num_tiles, int64_t tiles_per_cta,
+                                                                  const int32_t* __restrict__ cta_count,
+                                                                  int32_t* __restrict__ perm,
+                                                                  int32_t* __restrict__ count_out) {
   __shared__ int warp_sums[SEL_WARPS];
-  const int32_t total = sc->total;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-    tile_scatter(p, tile, n, tile_off[tile], total, perm, warp_sums);
+  int before = 0, all = 0;
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += SEL_BLOCK) {
+    const int v = cta_count[k];
+    all += v;
+    if (k < (int)blockIdx.x) before += v;
+  }
+  const int total = block_sum(all, warp_sums);
+  int off = block_sum(before, warp_sums);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = total;
+  const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
+  for (int64_t tile = t0; tile < t1; ++tile) off += tile_scatter(p, tile, n, off, total, perm, warp_sums);
 }
 
 // small sets (a few tiles): one CTA, one launch
@@ -216,9 +206,8 @@ constexpr int64_t SEL_SMALL_TILES = 8;  // <= 16384 slots: single-CTA path
 extern "C" {
 
 size_t fgx_select_scratch_bytes(int64_t n) {
-  if (n < 0) n = 0;
-  const int64_t tiles = fgx::ceil_div(n, fgx::SEL_TILE);
-  return sizeof(fgx::SelScratch) + (size_t)(tiles + 1) * sizeof(int32_t);
+  (void)n;
+  return (size_t)fgx::SEL_MAX_GRID * sizeof(int32_t);
 }
 
 int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32_t* count, void* scratch,
@@ -248,15 +237,14 @@ int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32
     return check_launch("fgx_select(small)");
   }
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_select_scratch_bytes(n), "fgx_select: scratch too small");
-  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "fgx_select: scratch must be 16-byte aligned");
-  SelScratch* sc = reinterpret_cast<SelScratch*>(scratch);
-  int32_t* tile_off = reinterpret_cast<int32_t*>(sc + 1);
-  // `done` must be zero on entry; the count kernel re-arms it, but the first use of a fresh scratch needs this
-  cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(SelScratch), s);
-  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_select: %s", cudaGetErrorString(e));
-  const int grid = (int)(tiles < (int64_t)sm_count() * 8 ? tiles : (int64_t)sm_count() * 8);
-  select_count_kernel<<<grid, SEL_BLOCK, 0, s>>>(*pred_host, n, tiles, sc, tile_off, count);
-  select_scatter_kernel<<<grid, SEL_BLOCK, 0, s>>>(*pred_host, n, tiles, sc, tile_off, perm);
+  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 3) == 0, "fgx_select: scratch must be 4-byte aligned");
+  int32_t* cta_count = reinterpret_cast<int32_t*>(scratch);
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > SEL_MAX_GRID) cap = SEL_MAX_GRID;
+  const int64_t per = ceil_div(tiles, tiles < cap ? tiles : cap);
+  const int grid = (int)ceil_div(tiles, per);
+  select_count_kernel<<<grid, SEL_BLOCK, 0, s>>>(*pred_host, n, tiles, per, cta_count);
+  select_scatter_kernel<<<grid, SEL_BLOCK, 0, s>>>(*pred_host, n, tiles, per, cta_count, perm, count);
   return check_launch("fgx_select");
 }
 }

@@ -17,30 +17,80 @@ struct LeafTable {
   int32_t vec[FGX_MAX_LEAVES];  // bytes per copy chunk: 16 / 8 / 4 / 2 / 1
 };
 
+// Narrow leaves (row <= 8 vector chunks of T): one thread per row, FOUR rows per thread with all index
+// loads, then all gathers, then all stores -- four independent gathers in flight per thread.
+// Wide leaves (per-agent weight matrices): one warp per row, lanes stride the 16-byte chunks
+// (coalesced 512 B per step).  grid.y = leaf in both kernels.
+__device__ __forceinline__ int64_t clamp_index(int64_t s, int64_t n) { return s < 0 ? 0 : (s >= n ? n - 1 : s); }
+
 template <typename T>
-__device__ __forceinline__ void gather_leaf(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n) {
+__device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n) {
   const int64_t chunks = lf.row_bytes / (int64_t)sizeof(T);
-  const int64_t total = n * chunks;
   const T* __restrict__ src = reinterpret_cast<const T*>(lf.src);
   T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / chunks;
-    const int64_t c = t - row * chunks;
-    int64_t s = __ldg(perm + row);
-    s = s < 0 ? 0 : (s >= n ? n - 1 : s);  // jnp.take clamps
-    dst[t] = __ldg(src + s * chunks + c);
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n; row += 4 * nthreads) {
+    int64_t s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = row + u * nthreads;
+      s[u] = r < n ? clamp_index(__ldg(perm + r), n) : 0;  // jnp.take clamps
+    }
+    if (chunks == 1) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + s[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = row + u * nthreads;
+        if (r < n) dst[r] = v[u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = row + u * nthreads;
+        if (r < n)
+          for (int64_t c = 0; c < chunks; ++c) dst[r * chunks + c] = __ldg(src + s[u] * chunks + c);
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ LeafTable tab,
-                                                          const int32_t* __restrict__ perm, int64_t n) {
+__global__ void __launch_bounds__(256) gather_narrow_kernel(const __grid_constant__ LeafTable tab,
+                                                            const int32_t* __restrict__ perm, int64_t n) {
   const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
   switch (tab.vec[blockIdx.y]) {
-    case 16: gather_leaf<uint4>(lf, perm, n); break;
-    case 8: gather_leaf<uint2>(lf, perm, n); break;
-    case 4: gather_leaf<uint32_t>(lf, perm, n); break;
-    case 2: gather_leaf<uint16_t>(lf, perm, n); break;
-    default: gather_leaf<uint8_t>(lf, perm, n); break;
+    case 16: gather_narrow<uint4>(lf, perm, n); break;
+    case 8: gather_narrow<uint2>(lf, perm, n); break;
+    case 4: gather_narrow<uint32_t>(lf, perm, n); break;
+    case 2: gather_narrow<uint16_t>(lf, perm, n); break;
+    default: gather_narrow<uint8_t>(lf, perm, n); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_wide_kernel(const __grid_constant__ LeafTable tab,
+                                                          const int32_t* __restrict__ perm, int64_t n) {
+  const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
+  const int v = tab.vec[blockIdx.y];
+  const int64_t chunks = lf.row_bytes / v;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const int64_t s = clamp_index(__ldg(perm + row), n);
+    if (v == 16) {
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(lf.src) + s * chunks;
+      uint4* __restrict__ dst = reinterpret_cast<uint4*>(lf.dst) + row * chunks;
+      for (int64_t c = lane; c < chunks; c += 32) dst[c] = __ldg(src + c);
+    } else {  // rows that are not 16-byte clean: byte-granular vector of v bytes
+      const char* __restrict__ src = reinterpret_cast<const char*>(lf.src) + s * lf.row_bytes;
+      char* __restrict__ dst = reinterpret_cast<char*>(lf.dst) + row * lf.row_bytes;
+      for (int64_t c = lane; c < chunks; c += 32) {
+        if (v == 8) reinterpret_cast<uint2*>(dst)[c] = __ldg(reinterpret_cast<const uint2*>(src) + c);
+        else if (v == 4) reinterpret_cast<uint32_t*>(dst)[c] = __ldg(reinterpret_cast<const uint32_t*>(src) + c);
+        else if (v == 2) reinterpret_cast<uint16_t*>(dst)[c] = __ldg(reinterpret_cast<const uint16_t*>(src) + c);
+        else dst[c] = __ldg(src + c);
+      }
+    }
   }
 }
 
@@ -88,23 +138,33 @@ int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32
               FGX_MAX_LEAVES);
   if (n == 0 || n_leaves == 0) return FGX_OK;
   FGX_REQUIRE(leaves_host && perm, "fgx_gather_rows: null pointer");
-  LeafTable tab;
-  int64_t max_chunks = 1;
+  LeafTable narrow, wide;
+  int nn = 0, nw = 0;
   for (int k = 0; k < n_leaves; ++k) {
     const fgx_leaf_t& lf = leaves_host[k];
     FGX_REQUIRE(lf.src && lf.dst && lf.row_bytes > 0, "fgx_gather_rows: leaf %d is malformed", k);
     FGX_REQUIRE(lf.src != lf.dst, "fgx_gather_rows: leaf %d aliases its destination", k);
-    tab.leaf[k] = lf;
     const uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | reinterpret_cast<uintptr_t>(lf.dst) |
                            (uintptr_t)lf.row_bytes;
     int v = 16;
     while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
-    tab.vec[k] = v;
-    const int64_t ch = lf.row_bytes / v;
-    if (ch > max_chunks) max_chunks = ch;
+    if (lf.row_bytes / v <= 8) {
+      narrow.leaf[nn] = lf;
+      narrow.vec[nn++] = v;
+    } else {
+      wide.leaf[nw] = lf;
+      wide.vec[nw++] = v;
+    }
   }
-  dim3 grid(grid_for(n * max_chunks, 256, 8), n_leaves);
-  gather_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(tab, perm, n);
+  cudaStream_t s = as_stream(stream);
+  if (nn) {
+    dim3 grid(grid_for(ceil_div(n, 4), 256, 8), nn);
+    gather_narrow_kernel<<<grid, 256, 0, s>>>(narrow, perm, n);
+  }
+  if (nw) {
+    dim3 grid(grid_for(n * 32, 256, 8), nw);
+    gather_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n);
+  }
   return check_launch("fgx_gather_rows");
 }
 

@@ -2,15 +2,16 @@
 //
 // Reference: agent_methods.py:74-76 -- argsort(q) or argsort(-q) (jnp.argsort =
 // stable lax.sort of (key, iota); float total order with -0.0 == +0.0 and NaN
-// last).  Here: keys are mapped to order-preserving uint32 images, then sorted
-// with a stable LSD radix sort (8-bit digits) of (image, slot index):
-//   prep     image + four global digit histograms + min/max image
-//   minmax   counts image==min / image==max: a two-valued key (the common
-//            sort on active_state or a 0/1 flag) needs ONE 1-bit pass
-//   plan     per pass: trivial? (one bin holds everything) + digit bases
-//   pass x4  tile histogram -> per-digit scan over tiles -> stable scatter with
-//            warp match/ballot ranking; skipped on device when trivial
-//   finish   copy to the caller's perm if the result landed in scratch
+// last).  Here: keys are mapped to order-preserving uint32 images, then
+//   1. minmax   image min / max over the keys
+//   2. two-valued fast path (the common sort on active_state or a 0/1 flag): count
+//      image==min per CTA; if every key is min or max the sort IS a stable 2-way
+//      partition -- one ballot/popc scatter pass writes the permutation and the
+//      general path below is skipped on device;
+//   3. general path: stable LSD radix sort of (image, slot index), 8-bit digits:
+//      prep (images + 4 digit histograms), plan (digit bases, trivial passes),
+//      per pass: tile histogram -> per-digit scan over tiles -> stable scatter with
+//      warp match/ballot ranking; finish copies to the caller's perm if needed.
 // Small inputs take a single-CTA bitonic sort of the 64-bit (image, index)
 // composite (unique, hence stable) in shared memory: one launch.
 #include "common.cuh"
@@ -22,108 +23,202 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_BLOCK / 32;
 constexpr int SORT_SMALL_N = 4096;  // bitonic path: 4096 * 8 B = 32 KB static smem
+constexpr int TV_ITEMS = 8;         // two-valued partition: 2048 slots per tile
+constexpr int TV_TILE = RS_BLOCK * TV_ITEMS;
+constexpr int TV_MAX_GRID = 4096;
 
 struct SortState {
   uint32_t hist[4][256];
   uint32_t base[4][256];
   uint32_t kmin, kmax;
   uint32_t cnt_min, cnt_max;
-  int32_t two_valued;
+  int32_t done;  // the two-valued fast path produced the result
   int32_t trivial[4];
   int32_t pad[3];
 };
 
-// The (image, idx) ping-pong side that holds the current order before `pass`
-// = parity of the non-trivial passes already executed; the idx buffer is
-// still the implicit iota until the first executed pass.
 __device__ __forceinline__ int passes_done(const SortState* st, int pass) {
   int c = 0;
   for (int q = 0; q < pass; ++q) c += st->trivial[q] ? 0 : 1;
   return c;
 }
 
-// warp-aggregated shared-memory histogram increment (keys are often two-valued:
-// un-aggregated atomics would serialise 32-way on one bank)
+// warp-aggregated shared-memory histogram increment
 __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid) {
   const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
   if (valid && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
 }
 
-__device__ __forceinline__ uint32_t key_image(const void* keys, int dtype, int descending, int64_t i) {
+// order-preserving uint32 image of a raw 32-bit key word (float32 or int32)
+__device__ __forceinline__ uint32_t image_of(uint32_t raw, int dtype, int descending) {
   if (dtype == FGX_F32) {
-    float v = reinterpret_cast<const float*>(keys)[i];
+    float v = __uint_as_float(raw);
     if (descending) v = -v;
     if (v != v) return 0xFFFFFFFFu;  // every NaN sorts last
     if (v == 0.0f) v = 0.0f;         // -0.0 -> +0.0
     const uint32_t b = __float_as_uint(v);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
   }
-  int32_t v = reinterpret_cast<const int32_t*>(keys)[i];
+  int32_t v = (int32_t)raw;
   if (descending) v = (int32_t)(0u - (uint32_t)v);
   return (uint32_t)v ^ 0x80000000u;
 }
+__device__ __forceinline__ uint32_t key_image(const void* keys, int dtype, int descending, int64_t i) {
+  return image_of(__ldg(reinterpret_cast<const uint32_t*>(keys) + i), dtype, descending);
+}
 
+// ---- 1. min / max image ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) sort_minmax_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                          int64_t n, SortState* __restrict__ st) {
+  uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = key_image(keys, dtype, descending, i);
+    lmin = min(lmin, v);
+    lmax = max(lmax, v);
+  }
+  lmin = __reduce_min_sync(0xffffffffu, lmin);
+  lmax = __reduce_max_sync(0xffffffffu, lmax);
+  __shared__ uint32_t smin[8], smax[8];
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lmin; smax[threadIdx.x >> 5] = lmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { lmin = min(lmin, smin[k]); lmax = max(lmax, smax[k]); }
+    atomicMin(&st->kmin, lmin);
+    atomicMax(&st->kmax, lmax);
+  }
+}
+
+// ---- 2. two-valued fast path: stable partition by (image == min) -------------------------
+__device__ __forceinline__ int64_t tv_elem(int64_t tile, int w, int r, int l) {
+  return tile * TV_TILE + w * (32 * TV_ITEMS) + r * 32 + l;
+}
+
+__global__ void __launch_bounds__(RS_BLOCK)
+    sort_two_count_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t num_tiles,
+                          int64_t tiles_per_cta, SortState* __restrict__ st, int32_t* __restrict__ cta_count) {
+  const uint32_t kmin = st->kmin, kmax = st->kmax;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
+  int cmin = 0, cmax = 0;
+  const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(keys);
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    uint32_t raw[TV_ITEMS];  // all loads first (no control flow between them), then the compares
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) raw[r] = __ldg(kw + min(tv_elem(tile, w, r, l), n - 1));
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      const bool in = tv_elem(tile, w, r, l) < n;
+      const uint32_t v = image_of(raw[r], dtype, descending);
+      cmin += in && v == kmin;
+      cmax += in && v == kmax;
+    }
+  }
+  cmin = __reduce_add_sync(0xffffffffu, cmin);
+  cmax = __reduce_add_sync(0xffffffffu, cmax);
+  __shared__ int smin[RS_WARPS], smax[RS_WARPS];
+  if (l == 0) { smin[w] = cmin; smax[w] = cmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int k = 0; k < RS_WARPS; ++k) { a += smin[k]; b += smax[k]; }
+    cta_count[blockIdx.x] = a;
+    if (a) atomicAdd(&st->cnt_min, (uint32_t)a);
+    if (b && kmax != kmin) atomicAdd(&st->cnt_max, (uint32_t)b);
+  }
+}
+
+__global__ void __launch_bounds__(RS_BLOCK)
+    sort_two_scatter_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t num_tiles,
+                            int64_t tiles_per_cta, SortState* __restrict__ st, const int32_t* __restrict__ cta_count,
+                            int32_t* __restrict__ perm) {
+  if ((uint64_t)st->cnt_min + st->cnt_max != (uint64_t)n) return;  // more than two values: general path
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->done = 1;
+  const uint32_t kmin = st->kmin;
+  const int total = (int)st->cnt_min;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __shared__ int ws[RS_WARPS];
+  int before = 0;
+  for (int k = threadIdx.x; k < (int)blockIdx.x; k += RS_BLOCK) before += cta_count[k];
+  before = __reduce_add_sync(0xffffffffu, before);
+  if (l == 0) ws[w] = before;
+  __syncthreads();
+  int off = 0;
+  for (int k = 0; k < RS_WARPS; ++k) off += ws[k];
+  __syncthreads();
+  const unsigned lt = lanemask_lt();
+  const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(keys);
+  const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    uint32_t raw[TV_ITEMS];  // all loads first, then the compares and ballots
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) raw[r] = __ldg(kw + min(tv_elem(tile, w, r, l), n - 1));
+    unsigned flags = 0;
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r)
+      flags |= (tv_elem(tile, w, r, l) < n && image_of(raw[r], dtype, descending) == kmin ? 1u : 0u) << r;
+    unsigned ball[TV_ITEMS];
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      ball[r] = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
+      c += __popc(ball[r]);
+    }
+    if (l == 0) ws[w] = c;
+    __syncthreads();
+    int rank0 = off, tile_total = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; ++k) {
+      if (k < w) rank0 += ws[k];
+      tile_total += ws[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      const int64_t i = tv_elem(tile, w, r, l);
+      if (i < n) {
+        const int rank = rank0 + __popc(ball[r] & lt);
+        const bool s = (ball[r] >> l) & 1u;
+        perm[s ? (int64_t)rank : (int64_t)total + (i - rank)] = (int32_t)i;
+      }
+      rank0 += __popc(ball[r]);
+    }
+    off += tile_total;
+  }
+}
+
+// ---- 3. general path --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sort_prep_kernel(const void* __restrict__ keys, int dtype, int descending,
                                                         int64_t n, uint32_t* __restrict__ img,
                                                         SortState* __restrict__ st) {
+  if (st->done) return;
   __shared__ uint32_t h[4][256];
-  __shared__ uint32_t smin, smax;
   for (int k = threadIdx.x; k < 1024; k += blockDim.x) (&h[0][0])[k] = 0;
-  if (threadIdx.x == 0) { smin = 0xFFFFFFFFu; smax = 0u; }
   __syncthreads();
-  uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < n; i0 += stride) {  // warp-uniform trip count
     const int64_t i = i0 + threadIdx.x;
     const bool valid = i < n;
     const uint32_t v = valid ? key_image(keys, dtype, descending, i) : 0u;
-    if (valid) {
-      img[i] = v;
-      lmin = min(lmin, v);
-      lmax = max(lmax, v);
-    }
+    if (valid) img[i] = v;
     hist_add(h[0], v & 255u, valid);
     hist_add(h[1], (v >> 8) & 255u, valid);
     hist_add(h[2], (v >> 16) & 255u, valid);
     hist_add(h[3], v >> 24, valid);
   }
-  lmin = __reduce_min_sync(0xffffffffu, lmin);
-  lmax = __reduce_max_sync(0xffffffffu, lmax);
-  if ((threadIdx.x & 31) == 0) { atomicMin(&smin, lmin); atomicMax(&smax, lmax); }
   __syncthreads();
   for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
     const uint32_t c = (&h[0][0])[k];
     if (c) atomicAdd(&st->hist[0][0] + k, c);
   }
-  if (threadIdx.x == 0) { atomicMin(&st->kmin, smin); atomicMax(&st->kmax, smax); }
-}
-
-__global__ void __launch_bounds__(256) sort_minmax_kernel(const uint32_t* __restrict__ img, int64_t n,
-                                                          SortState* __restrict__ st) {
-  const uint32_t kmin = st->kmin, kmax = st->kmax;
-  uint32_t a = 0, b = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = __ldg(img + i);
-    a += v == kmin;
-    b += v == kmax;
-  }
-  a = __reduce_add_sync(0xffffffffu, a);
-  b = __reduce_add_sync(0xffffffffu, b);
-  if ((threadIdx.x & 31) == 0) {
-    if (a) atomicAdd(&st->cnt_min, a);
-    if (b) atomicAdd(&st->cnt_max, b);
-  }
 }
 
 __global__ void __launch_bounds__(256) sort_plan_kernel(int64_t n, SortState* __restrict__ st) {
+  if (st->done) return;
   __shared__ uint32_t sh[256];
   __shared__ int triv;
   const int t = threadIdx.x;
-  const bool two = st->kmin != st->kmax && (uint64_t)st->cnt_min + st->cnt_max == (uint64_t)n;
-  const bool one = st->kmin == st->kmax;
   for (int p = 0; p < 4; ++p) {
-    uint32_t c = st->hist[p][t];
-    if (two && p == 0) c = t == 0 ? st->cnt_min : (t == 1 ? st->cnt_max : 0u);
+    const uint32_t c = st->hist[p][t];
     if (t == 0) triv = 0;
     __syncthreads();
     if ((uint64_t)c == (uint64_t)n) triv = 1;
@@ -135,15 +230,12 @@ __global__ void __launch_bounds__(256) sort_plan_kernel(int64_t n, SortState* __
     }
     __syncthreads();
     st->base[p][t] = sh[t];
-    if (t == 0) st->trivial[p] = (one || (two && p > 0)) ? 1 : triv;
+    if (t == 0) st->trivial[p] = triv;
     __syncthreads();
   }
-  if (t == 0) st->two_valued = two ? 1 : 0;
 }
 
-__device__ __forceinline__ uint32_t digit_of(uint32_t v, int pass, bool two, uint32_t kmax) {
-  return two ? (v == kmax ? 1u : 0u) : ((v >> (8 * pass)) & 255u);
-}
+__device__ __forceinline__ uint32_t digit_of(uint32_t v, int pass) { return (v >> (8 * pass)) & 255u; }
 
 // tile digit counts -> block_hist[digit][tile]
 __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __restrict__ img0,
@@ -151,10 +243,8 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __r
                                                              int64_t num_tiles, int pass,
                                                              const SortState* __restrict__ st,
                                                              uint32_t* __restrict__ block_hist) {
-  if (st->trivial[pass]) return;
+  if (st->done || st->trivial[pass]) return;
   const uint32_t* img = (passes_done(st, pass) & 1) ? img1 : img0;
-  const bool two = st->two_valued;
-  const uint32_t kmax = st->kmax;
   __shared__ uint32_t h[256];
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     h[threadIdx.x] = 0;
@@ -164,7 +254,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __r
     for (int r = 0; r < RS_ITEMS; ++r) {
       const int64_t i = base + r * RS_BLOCK + threadIdx.x;
       const bool valid = i < n;
-      hist_add(h, valid ? digit_of(__ldg(img + i), pass, two, kmax) : 0u, valid);
+      hist_add(h, valid ? digit_of(__ldg(img + i), pass) : 0u, valid);
     }
     __syncthreads();
     block_hist[(int64_t)threadIdx.x * num_tiles + tile] = h[threadIdx.x];
@@ -175,8 +265,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __r
 // one CTA per digit: exclusive scan of block_hist[digit][0..num_tiles) in place
 __global__ void __launch_bounds__(256) sort_scan_kernel(int64_t num_tiles, int pass, const SortState* __restrict__ st,
                                                         uint32_t* __restrict__ block_hist) {
-  if (st->trivial[pass]) return;
-  if (st->two_valued && blockIdx.x > 1) return;
+  if (st->done || st->trivial[pass]) return;
   uint32_t* row = block_hist + (int64_t)blockIdx.x * num_tiles;
   __shared__ uint32_t wsum[8];
   __shared__ uint32_t carry;
@@ -209,7 +298,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
                                                                 int64_t n, int64_t num_tiles, int pass,
                                                                 const SortState* __restrict__ st,
                                                                 const uint32_t* __restrict__ block_hist) {
-  if (st->trivial[pass]) return;
+  if (st->done || st->trivial[pass]) return;
   const int done = passes_done(st, pass);
   const int cur = done & 1;
   const uint32_t* kin = cur ? img1 : img0;
@@ -217,8 +306,6 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
   const int32_t* iin = cur ? idx1 : idx0;
   int32_t* iout = cur ? idx0 : idx1;
   const bool iota = done == 0;
-  const bool two = st->two_valued;
-  const uint32_t kmax = st->kmax;
   __shared__ uint32_t wcnt[RS_WARPS][256];
   __shared__ uint32_t gbase[256];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -236,7 +323,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
       const bool valid = i < n;
       key[r] = valid ? kin[i] : 0xFFFFFFFFu;
       // invalid lanes use a digit value outside 0..255 so they never match a real one
-      const uint32_t d = valid ? digit_of(key[r], pass, two, kmax) : 256u;
+      const uint32_t d = valid ? digit_of(key[r], pass) : 256u;
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
@@ -263,7 +350,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
     for (int r = 0; r < RS_ITEMS; ++r) {
       const int64_t i = wbase + r * 32 + l;
       if (i < n) {
-        const uint32_t d = digit_of(key[r], pass, two, kmax);
+        const uint32_t d = digit_of(key[r], pass);
         const uint32_t pos = gbase[d] + wcnt[w][d] + lpos[r];
         kout[pos] = key[r];
         iout[pos] = iota ? (int32_t)i : iin[i];
@@ -276,6 +363,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
 // result -> perm (idx0 aliases perm): copy only if the final order sits in idx1, or is still iota
 __global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* __restrict__ idx1, int32_t* __restrict__ perm,
                                                           int64_t n, const SortState* __restrict__ st) {
+  if (st->done) return;
   const int done = passes_done(st, 4);
   const bool iota = done == 0;
   if (!iota && (done & 1) == 0) return;
@@ -283,7 +371,7 @@ __global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* __restr
     perm[i] = iota ? (int32_t)i : idx1[i];
 }
 
-// ---- small path: single CTA, bitonic sort of (image << 32 | index) ----------
+// ---- small path: single CTA, bitonic sort of (image << 32 | index) ----------------------
 __global__ void __launch_bounds__(1024) sort_small_kernel(const void* __restrict__ keys, int dtype, int descending,
                                                           int n, int32_t* __restrict__ perm) {
   __shared__ unsigned long long s[SORT_SMALL_N];
@@ -320,6 +408,7 @@ size_t fgx_argsort_scratch_bytes(int64_t n) {
   if (n < 0) n = 0;
   const int64_t tiles = ceil_div(n, RS_TILE);
   size_t b = align_up(sizeof(SortState), 256);
+  b += align_up((size_t)TV_MAX_GRID * 4, 256);      // per-CTA counts of the two-valued path
   b += 2 * align_up((size_t)n * 4, 256);            // image ping-pong
   b += align_up((size_t)n * 4, 256);                // idx1 (idx0 is the caller's perm)
   b += align_up((size_t)tiles * 256 * 4 + 4, 256);  // block_hist[256][tiles]
@@ -334,8 +423,9 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   if (n == 0) return FGX_OK;
   FGX_REQUIRE(keys && perm, "fgx_argsort: null pointer");
   cudaStream_t s = as_stream(stream);
+  const int desc = descending ? 1 : 0;
   if (n <= SORT_SMALL_N) {
-    sort_small_kernel<<<1, 1024, 0, s>>>(keys, key_dtype, descending ? 1 : 0, (int)n, perm);
+    sort_small_kernel<<<1, 1024, 0, s>>>(keys, key_dtype, desc, (int)n, perm);
     return check_launch("fgx_argsort(small)");
   }
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_argsort_scratch_bytes(n), "fgx_argsort: scratch too small");
@@ -344,6 +434,8 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   char* p = reinterpret_cast<char*>(scratch);
   SortState* st = reinterpret_cast<SortState*>(p);
   p += align_up(sizeof(SortState), 256);
+  int32_t* cta_count = reinterpret_cast<int32_t*>(p);
+  p += align_up((size_t)TV_MAX_GRID * 4, 256);
   uint32_t* img0 = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n * 4, 256);
   uint32_t* img1 = reinterpret_cast<uint32_t*>(p);
@@ -355,12 +447,20 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
 
   cudaError_t e = cudaMemsetAsync(st, 0, sizeof(SortState), s);
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
-  // kmin starts at 0xFFFFFFFF
-  e = cudaMemsetAsync(&st->kmin, 0xFF, sizeof(uint32_t), s);
+  e = cudaMemsetAsync(&st->kmin, 0xFF, sizeof(uint32_t), s);  // kmin starts at 0xFFFFFFFF
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
   const int g = grid_for(n, 256, 8);
-  sort_prep_kernel<<<g, 256, 0, s>>>(keys, key_dtype, descending ? 1 : 0, n, img0, st);
-  sort_minmax_kernel<<<g, 256, 0, s>>>(img0, n, st);
+  sort_minmax_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, st);
+  // two-valued fast path (contiguous tile range per CTA)
+  const int64_t tv_tiles = ceil_div(n, TV_TILE);
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > TV_MAX_GRID) cap = TV_MAX_GRID;
+  const int64_t per = ceil_div(tv_tiles, tv_tiles < cap ? tv_tiles : cap);
+  const int tv_grid = (int)ceil_div(tv_tiles, per);
+  sort_two_count_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count);
+  sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count, perm);
+  // general path (every kernel returns at once when st->done)
+  sort_prep_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, img0, st);
   sort_plan_kernel<<<1, 256, 0, s>>>(n, st);
   const int gt = (int)(tiles < (int64_t)sm_count() * 4 ? tiles : (int64_t)sm_count() * 4);
   for (int pass = 0; pass < 4; ++pass) {
