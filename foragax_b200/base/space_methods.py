@@ -140,3 +140,45 @@ def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_r
     L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                     float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))
     return dist, hit
+
+
+def raycast_agents(agent_pos, ray_span, ray_length, targets, bounds, max_rad, active_state=None, n_rays=None,
+                   merge_walls=False, out=None):
+    """The fused agent-agent hot loop: ``ray_generator`` + ``ray_agent_sensor`` over sensing agents x rays x
+    target circles, reduced per ray to (min distance, first target index or -1) -- what the all-pairs
+    composition of ``EcoEvoJax/sim.py:418-457`` computes for agent entities, found through a uniform grid.
+
+    ``targets``: ``(x, y, rad, active)`` tensors of M targets, or one ``float32[M,4]`` tensor of interleaved
+    rows (the result of ``distributed.all_gather_positions``).  ``bounds = (x_min, x_max, y_min, y_max)``.
+    ``merge_walls=True``: ``out=(dist, hit)`` holds the result of :func:`raycast_walls` and receives the
+    merged result in entity order [targets, walls]."""
+    x, y, ang = (_f32(a) for a in agent_pos)
+    n = x.shape[0]
+    r = int(RESOLUTION if n_rays is None else n_rays)
+    act = None if active_state is None else _f32(active_state)
+    if isinstance(targets, torch.Tensor):
+        t = targets.to(torch.float32).contiguous()
+        m, stride = t.shape[0], 4
+        base, esz = t.data_ptr(), 4
+        tp = (base, base + esz, base + 2 * esz, base + 3 * esz) if m else (None,) * 4
+        keep = t
+    else:
+        keep = tuple(_f32(a) for a in targets)
+        m, stride = keep[0].shape[0], 1
+        tp = tuple(L.ptr(a) for a in keep) if m else (None,) * 4
+    if out is None:
+        if merge_walls:
+            raise L.FgxError("merge_walls needs out=(dist, hit) from raycast_walls")
+        dist = torch.empty((n, r), dtype=torch.float32, device=x.device)
+        hit = torch.empty((n, r), dtype=torch.int32, device=x.device)
+    else:
+        dist, hit = out
+    b = [float(v) for v in bounds]
+    nbytes = L.lib.fgx_raycast_agents_scratch_bytes(n, m, b[0], b[1], b[2], b[3], float(ray_length), float(max_rad))
+    scr = L.scratch(nbytes)
+    L.check(L.lib.fgx_raycast_agents(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
+                                     float(ray_length), tp[0], tp[1], tp[2], tp[3], stride, m, b[0], b[1], b[2], b[3],
+                                     float(max_rad), 1 if merge_walls else 0, L.ptr(dist), L.ptr(hit), L.ptr(scr),
+                                     nbytes, L.stream()))
+    del keep
+    return dist, hit

@@ -132,6 +132,22 @@ int fgx_raycast_walls(const float* x, const float* y, const float* ang, const fl
                       int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
                       const float* wx2, const float* wy2, int64_t n_walls, float* dist, int32_t* hit,
                       fgx_stream_t stream);
+/* The agents x rays x agent-targets loop: ray_generator + ray_agent_sensor (space_methods.py:71-94)
+ * for every ray of every sensing agent against every target circle (tx, ty, trad, tactive:
+ * float32, element i at [i*target_stride] -- stride 4 for the interleaved float4 rows of a position
+ * all-gather), reduced per ray to (min distance, FIRST target index attaining it, -1 if none), as
+ * the all-pairs reference does (EcoEvoJax/sim.py:444-447).  A uniform grid over [x_min,x_max] x
+ * [y_min,y_max] with cell >= ray_length + max_rad limits the search to 3x3 cells; the cull is exact
+ * provided no target radius exceeds max_rad.  merge_walls != 0: dist / hit hold the result of
+ * fgx_raycast_walls on entry and the merged result in entity order [targets, walls] on exit (wall w
+ * becomes index n_targets + w).  Inactive sensing agents: dist 0, hit -1.                     */
+size_t fgx_raycast_agents_scratch_bytes(int64_t n_agents, int64_t n_targets, float x_min, float x_max, float y_min,
+                                        float y_max, float ray_length, float max_rad);
+int fgx_raycast_agents(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
+                       int32_t n_rays, float ray_span, float ray_length, const float* tx, const float* ty,
+                       const float* trad, const float* tactive, int64_t target_stride, int64_t n_targets,
+                       float x_min, float x_max, float y_min, float y_max, float max_rad, int32_t merge_walls,
+                       float* dist, int32_t* hit, void* scratch, size_t scratch_bytes, fgx_stream_t stream);
 /* ray_generator (space_methods.py:56-69), directions only: dir_x, dir_y float32[n, n_rays]
  * = cos / sin of linspace(ang - span, ang + span, n_rays).                          */
 int fgx_ray_generator(const float* ang, int64_t n, int32_t n_rays, float ray_span, float* dir_x, float* dir_y,
