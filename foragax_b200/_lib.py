@@ -125,6 +125,27 @@ _decl("fgx_resource_add", C.c_int, i64, f32, f32, f32, f32, vp, vp, vp, vp, vp, 
 _decl("fgx_resource_set", C.c_int, i64, vp, vp, _P(ResourceState), vp)
 
 
+class AnimalState(C.Structure):
+    _fields_ = [(k, vp) for k in ("X_pos", "Y_pos", "energy", "reproduce", "key", "policy_key")]
+
+
+class AnimalParams(C.Structure):
+    _fields_ = [("x_min", i32), ("x_max", i32), ("y_min", i32), ("y_max", i32), ("torous", i32),
+                ("delta_energy", i32), ("reproduction_rate", f32)]
+
+
+_decl("fgx_animal_create", C.c_int, i64, i32, i32, i32, vp, vp, _P(AnimalState), vp, vp)
+_decl("fgx_animal_step", C.c_int, _P(AnimalParams), i64, vp, vp, _P(AnimalState), vp, vp)
+_decl("fgx_animal_remove", C.c_int, i64, vp, vp, _P(AnimalState), vp, vp, vp)
+_decl("fgx_animal_add", C.c_int, i64, vp, vp, vp, _P(AnimalState), vp, vp, vp)
+_decl("fgx_animal_set", C.c_int, i64, vp, vp, _P(AnimalState), vp)
+_decl("fgx_grass_create", C.c_int, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp)
+_decl("fgx_grass_step", C.c_int, i64, i32, vp, vp, vp, vp)
+_decl("fgx_wolf_sheep_interaction_scratch_bytes", sz, i32, i32)
+_decl("fgx_wolf_sheep_interaction", C.c_int, i32, i32, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp,
+      sz, vp)
+
+
 class FgxError(RuntimeError):
     pass
 

@@ -295,6 +295,47 @@ int fgx_resource_add(int64_t n, float x_min, float x_max, float y_min, float y_m
 int fgx_resource_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_resource_state_t* state,
                      fgx_stream_t stream);
 
+/* ---- K2: wolf-sheep-grass example (examples/basic/wolf_sheep_grass/sim.ipynb) --------------
+ * Animal state leaves ([n,1] leaves as int32[n]); policy_key = Random_Policy state (random_policy.py). */
+typedef struct {
+  int32_t *X_pos, *Y_pos, *energy, *reproduce;
+  uint32_t *key, *policy_key; /* uint32[n,2] */
+} fgx_animal_state_t;
+typedef struct {
+  int32_t x_min, x_max, y_min, y_max, torous, delta_energy; /* space + animal.params (sim.ipynb:44-45,73) */
+  float reproduction_rate;
+} fgx_animal_params_t;
+/* vmapped Animal.create_agent (sim.ipynb:40-70) */
+int fgx_animal_create(int64_t n, int32_t x_max, int32_t y_max, int32_t delta_energy, const uint32_t* create_keys,
+                      const float* active_state, const fgx_animal_state_t* state, float* age, fgx_stream_t stream);
+/* step_agents + vmapped Animal.step_agent (sim.ipynb:72-122) with Random_Policy.step_policy
+ * (random_policy.py:17-23); in place; energy_in int32[n] */
+int fgx_animal_step(const fgx_animal_params_t* p, int64_t n, const float* active_state, const int32_t* energy_in,
+                    const fgx_animal_state_t* state, float* age, fgx_stream_t stream);
+/* remove / add / set with Animal.remove_agent, add_agent, set_agent (sim.ipynb:124-170); k, n_active on device */
+int fgx_animal_remove(int64_t n, const int32_t* remove_ids, const int32_t* k, const fgx_animal_state_t* state,
+                      float* active_state, float* age, fgx_stream_t stream);
+int fgx_animal_add(int64_t n, const int32_t* copy_ids, const int32_t* n_active, const int32_t* k,
+                   const fgx_animal_state_t* state, float* active_state, float* age, fgx_stream_t stream);
+int fgx_animal_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_animal_state_t* state,
+                   fgx_stream_t stream);
+/* vmapped Grass.create_agent / step_agent (sim.ipynb:177-218); fully_grown bool[n], energy_out float32[n] */
+int fgx_grass_create(int64_t n, int32_t x_max, int32_t regrowth_time, const uint32_t* create_keys,
+                     const int32_t* unique_id, int32_t* X_pos, int32_t* Y_pos, uint8_t* fully_grown,
+                     int32_t* count_down, float* age, fgx_stream_t stream);
+int fgx_grass_step(int64_t n, int32_t regrowth_time, const float* energy_out, uint8_t* fully_grown,
+                   int32_t* count_down, fgx_stream_t stream);
+/* interaction (sim.ipynb:238-290): wolves_energy_in int32[W] = sheep on the wolf's cell,
+ * sheeps_energy_in int32[S] = fully grown grass on the sheep's cell, sheeps_eaten float32[S],
+ * grasses_eaten float32[G]; cell equality evaluated as a histogram join over the grid
+ * [-1, x_max] x [-1, y_max] (no active-state check, as in the reference)                     */
+size_t fgx_wolf_sheep_interaction_scratch_bytes(int32_t x_max, int32_t y_max);
+int fgx_wolf_sheep_interaction(int32_t x_max, int32_t y_max, int64_t n_wolves, const int32_t* wX, const int32_t* wY,
+                               int64_t n_sheeps, const int32_t* sX, const int32_t* sY, int64_t n_grasses,
+                               const int32_t* gX, const int32_t* gY, const uint8_t* g_fully_grown,
+                               int32_t* wolves_energy_in, int32_t* sheeps_energy_in, float* sheeps_eaten,
+                               float* grasses_eaten, void* scratch, size_t scratch_bytes, fgx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
