@@ -41,3 +41,23 @@ def test_product_code_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_reference_import_paths_resolve_to_the_native_mirror():
+    """User code written against the reference (`import foragax.base.agent_methods as fgx_methods`) imports as is."""
+    import foragax.base.agent_classes as fgx_classes
+    import foragax.base.agent_methods as fgx_methods
+    import foragax.base.space_methods as space_methods
+    from foragax.policy.wilson_cowan import WilsonCowan
+    import foragax_b200.base.agent_methods as native
+    assert fgx_methods is native
+    for name in ("create_agents", "step_agents", "jit_select_agents", "jit_remove_agents", "jit_add_agents",
+                 "jit_set_agents", "jit_sort_agents"):
+        assert callable(getattr(fgx_methods, name)), name
+    for name in ("Signal", "Params", "State", "Policy", "Agent", "Agent_Set"):
+        assert hasattr(fgx_classes, name), name
+    for name in ("check_collision", "wall_generator", "RESOLUTION", "ray_generator", "ray_agent_sensor",
+                 "ray_wall_sensor", "create_space", "jit_ray_generator", "jit_ray_wall_sensor", "jit_ray_agent_sensor",
+                 "jit_check_collision"):
+        assert hasattr(space_methods, name), name
+    assert hasattr(WilsonCowan, "step_policy")
