@@ -205,9 +205,11 @@ def run_reference(args):
     }))
 
 
-def build_foragers(work, lo, hi, dev):
-    """The local shard [lo, hi) of the 1M-forager set: native create (threefry weights, PRNGKey(0)),
-    then positions / headings / active flags of the synthetic workload."""
+def build_foragers(work, rank, world, dev):
+    """The local shard (slots rank, rank+world, ...: round-robin, so that active and inactive slots are
+    spread evenly over the ranks) of the 1M-forager set: native create (threefry weights, PRNGKey(0)),
+    then positions / headings of the synthetic workload.  Every rank builds exactly its rows of the
+    single-GPU set."""
     import torch
 
     from foragax_b200 import random as fgx_random
@@ -219,10 +221,11 @@ def build_foragers(work, lo, hi, dev):
     fset = Agent_Set(agent=Forager, num_total_agents=N_AGENTS, num_active_agents=int(0.9 * N_AGENTS), agent_type=1)
     cp = Params(content={'policy_params': {'num_neurons': N_NEURONS, 'num_obs': N_OBS, 'num_actions': N_ACT, 'dt': DT,
                                            'action_scale': 1.0, 'deterministic': True}, 'dt': DT, 'space': space})
-    fset.agents = create_agents(cp, fset, fgx_random.PRNGKey(0), shard=(lo, hi - lo))
+    n_local = len(range(rank, N_AGENTS, world))
+    fset.agents = create_agents(cp, fset, fgx_random.PRNGKey(0), shard=(rank, n_local, world))
     st = fset.agents.state.content
     for k, src in (("X", "x"), ("Y", "y"), ("ang", "ang")):
-        st[k].copy_(torch.from_numpy(work[src][lo:hi]).to(dev).reshape(-1, 1))
+        st[k].copy_(torch.from_numpy(np.ascontiguousarray(work[src][rank::world])).to(dev).reshape(-1, 1))
     return fset, space
 
 
@@ -245,10 +248,10 @@ def run_ours(args):
     from foragax_b200.base.agent_methods import step_agents
 
     work = make_workload()
-    lo, hi = rank * N_AGENTS // world, (rank + 1) * N_AGENTS // world
-    n_local = hi - lo
-    n_active_local = int(work["active"][lo:hi].sum())
-    fset, space = build_foragers(work, lo, hi, dev)
+    mine = slice(rank, None, world)  # round-robin sharding by slot index
+    n_local = len(range(rank, N_AGENTS, world))
+    n_active_local = int(work["active"][mine].sum())
+    fset, space = build_foragers(work, rank, world, dev)
     F = fset.agents
     st = F.state.content
     dist_out = torch.empty((n_local, N_RAYS), dtype=torch.float32, device=dev)
@@ -317,7 +320,7 @@ def run_ours(args):
     # into pinned memory while step i+1 computes (double-buffered distance / hit outputs); every byte is
     # still copied every step and the timed region ends only when the last read-back has landed.
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-    hx, hy, ha, hact = (pin(work[k][lo:hi]) for k in ("x", "y", "ang", "active"))
+    hx, hy, ha, hact = (pin(work[k][mine]) for k in ("x", "y", "ang", "active"))
     h_dist = torch.empty((n_local, N_RAYS), dtype=torch.float32).pin_memory()
     h_hit = torch.empty((n_local, N_RAYS), dtype=torch.int32).pin_memory()
     h_x, h_y = torch.empty((n_local, 1)).pin_memory(), torch.empty((n_local, 1)).pin_memory()
@@ -421,7 +424,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents": N_AGENTS, "active_agents": int(0.9 * N_AGENTS), "rays": N_RAYS,
-                       "walls": N_WALLS, "sharding": f"agents by index / {world}, walls replicated",
+                       "walls": N_WALLS, "sharding": f"agents by slot index, round-robin over {world} rank(s), walls replicated",
                        "tick": ["fgx_raycast_walls (ray_generator + ray_wall_sensor + min/argmin)",
                                 "fgx_forager_step (WilsonCowan policy + physics)"],
                        "l2": "per-step working set 11.6 GB of per-agent weights + 272 MB ray I/O >> 126 MB L2"},

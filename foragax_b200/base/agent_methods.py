@@ -48,11 +48,12 @@ def num_slots(agents):
 
 # agent_methods.py:9-17
 def create_agents(params, agent_set, key, shard=None):
-    """``shard=(first, n_local)`` creates only those slots of the set (multi-GPU: every rank builds
-    exactly its rows of the single-GPU result); default: the whole set."""
+    """``shard=(first, n_local[, stride])`` creates only the slots first, first+stride, ... of the set
+    (multi-GPU: every rank builds exactly its rows of the single-GPU result); default: the whole set."""
     n = int(agent_set.num_total_agents)
     n_active = int(agent_set.num_active_agents)
     first, n_local = (0, n) if shard is None else (int(shard[0]), int(shard[1]))
+    stride = 1 if shard is None or len(shard) < 3 else int(shard[2])
     dev = L.device()
     k0, k1 = fgx_random.key_to_host(key)
     key_host = (C.c_uint32 * 2)(k0, k1)
@@ -60,7 +61,7 @@ def create_agents(params, agent_set, key, shard=None):
     create_keys = torch.empty((n_local, 2), dtype=torch.uint32, device=dev)
     active_states = torch.empty(n_local, dtype=torch.float32, device=dev)
     agent_types = torch.empty(n_local, dtype=torch.int32, device=dev)
-    L.check(L.lib.fgx_create_base_shard(key_host, n, n_active, first, n_local, int(agent_set.agent_type),
+    L.check(L.lib.fgx_create_base_shard(key_host, n, n_active, first, stride, n_local, int(agent_set.agent_type),
                                         L.ptr(uniq_ids), L.ptr(create_keys), L.ptr(active_states),
                                         L.ptr(agent_types), L.stream()))
     return agent_set.create_agents(params, uniq_ids, active_states, agent_types, create_keys)

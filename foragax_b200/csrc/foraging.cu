@@ -51,8 +51,10 @@ __host__ __device__ inline WcLayout wc_layout(int n, int nobs, int nact) {
 //   otherwise    : scalar walk rotated by r
 // Two rows per lane and four accumulators per row give the FMA chain enough independent work to
 // hide the LDS latency without relying on other warps.
-__device__ __forceinline__ void row_dot2(const float* rowA, const float* rowB, const float* v, int len, int r,
+template <int LEN>
+__device__ __forceinline__ void row_dot2(const float* rowA, const float* rowB, const float* v, int len_rt, int r,
                                          float& outA, float& outB) {
+  const int len = LEN ? LEN : len_rt;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
   if ((len & 3) == 0) {
     const int nch = len >> 2;
@@ -60,7 +62,7 @@ __device__ __forceinline__ void row_dot2(const float* rowA, const float* rowB, c
     const float4* B4 = reinterpret_cast<const float4*>(rowB);
     const float4* v4 = reinterpret_cast<const float4*>(v);
     int c = r % nch;
-#pragma unroll 2
+#pragma unroll(LEN ? (LEN / 4 < 16 ? LEN / 4 : 4) : 2)
     for (int t = 0; t < nch; ++t) {
       const float4 x = v4[c], wa = A4[c], wb = B4[c];
       a0 += wa.x * x.x; a1 += wa.y * x.y; a2 += wa.z * x.z; a3 += wa.w * x.w;
@@ -114,6 +116,9 @@ struct ActiveScan {
   }
 };
 
+// NN / NOBS / NACT > 0 fix the policy shape at compile time (constant trip counts, immediate
+// shared-memory offsets, no shape branches); 0 = read it from the params (any shape).
+template <int NN, int NOBS, int NACT>
 __global__ void __launch_bounds__(FS_WARPS * 32)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   // of its next active agent land in the other (mbarrier per slot).  slots == 1: one slot per warp and
   // twice the warps per SM; the copies of the other warps overlap this warp's compute.
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = p.n_neurons, nobs = p.n_obs, nact = p.n_act;
+  const int n = NN ? NN : p.n_neurons, nobs = NOBS ? NOBS : p.n_obs, nact = NACT ? NACT : p.n_act;
   const WcLayout L = wc_layout(n, nobs, nact);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -203,8 +208,8 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
       const bool hasB = rA + 32 < n;
       const int rB = hasB ? rA + 32 : rA;
       float sJ[2], sE[2];
-      row_dot2(sm + L.J + rA * n, sm + L.J + rB * n, sm + L.tz, n, rA, sJ[0], sJ[1]);
-      row_dot2(sm + L.E + rA * nobs, sm + L.E + rB * nobs, sm + L.obs, nobs, rA, sE[0], sE[1]);
+      row_dot2<NN>(sm + L.J + rA * n, sm + L.J + rB * n, sm + L.tz, n, rA, sJ[0], sJ[1]);
+      row_dot2<NOBS>(sm + L.E + rA * nobs, sm + L.E + rB * nobs, sm + L.obs, nobs, rA, sE[0], sE[1]);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h == 1 && !hasB) break;
@@ -405,10 +410,13 @@ __global__ void __launch_bounds__(128) sensor_model_kernel(const SensorArgs a) {
 
 extern "C" {
 
+}  // extern "C" (templates below need C++ linkage)
+
 // shared launcher: as many warps per CTA (<= FS_WARPS) as the per-warp weight slots allow
-static int launch_forager_step(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
-                               const float* obs, const float* energy_in, const fgx_forager_state_t& st,
-                               const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
+template <int NN, int NOBS, int NACT>
+static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
+                                 const float* obs, const float* energy_in, const fgx_forager_state_t& st,
+                                 const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
   using namespace fgx;
   const WcLayout L = wc_layout(p.n_neurons, p.n_obs, p.n_act);
   // one weight slot per warp and two CTAs per SM when that fits (most memory-level parallelism);
@@ -422,17 +430,33 @@ static int launch_forager_step(const char* what, const fgx_forager_params_t& p, 
   FGX_REQUIRE(head + warps * per_warp <= 227 * 1024,
               "%s: policy too large for shared memory (%zu bytes per agent)", what, per_warp);
   const size_t smem = head + warps * per_warp;
-  cudaError_t e = cudaFuncSetAttribute(forager_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = forager_step_kernel<NN, NOBS, NACT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forager_step_kernel, warps * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div(n, warps);
   const int64_t cap = (int64_t)sm_count() * per_sm;
-  forager_step_kernel<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol,
-                                                                             age, actions, slots);
+  kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
+                                                              slots);
   return check_launch(what);
 }
+
+static int launch_forager_step(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
+                               const float* obs, const float* energy_in, const fgx_forager_state_t& st,
+                               const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
+#define FGX_FS_SHAPE(NN, NOBS, NACT)                                                              \
+  if (p.n_neurons == NN && p.n_obs == NOBS && p.n_act == NACT)                                    \
+    return launch_forager_step_t<NN, NOBS, NACT>(what, p, n, active, obs, energy_in, st, pol, age, actions, s);
+  FGX_FS_SHAPE(40, 28, 2)  // EcoEvoJax/sim.py:712
+  FGX_FS_SHAPE(30, 28, 2)  // EcoEvoJax/sim.ipynb
+  FGX_FS_SHAPE(40, 33, 2)  // bench C4: 32 ray distances + own energy
+#undef FGX_FS_SHAPE
+  return launch_forager_step_t<0, 0, 0>(what, p, n, active, obs, energy_in, st, pol, age, actions, s);
+}
+
+extern "C" {
 
 int fgx_forager_step(const fgx_forager_params_t* p, int64_t n, const float* active_state, const float* obs,
                      const float* energy_in, const fgx_forager_state_t* state, const fgx_wc_policy_t* policy,

@@ -113,11 +113,12 @@ __global__ void __launch_bounds__(256) count_active_kernel(const float* __restri
 // create_agents' argument construction (agent_methods.py:10-15) for the slots
 // [first, first + n_local) of a set of n_total slots (a shard computes exactly its rows)
 __global__ void __launch_bounds__(256) create_base_kernel(Key root, int64_t n_total, int64_t n_active, int64_t first,
-                                                          int64_t n_local, int32_t type, int32_t* __restrict__ uid,
+                                                          int64_t stride, int64_t n_local, int32_t type,
+                                                          int32_t* __restrict__ uid,
                                                           uint2* __restrict__ ckeys, float* __restrict__ active,
                                                           int32_t* __restrict__ atype) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_local; j += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = first + j;
+    const int64_t i = first + j * stride;
     const Key ck = split_child(root, (uint32_t)(n_total + 1), (uint32_t)(i + 1));
     uid[j] = (int32_t)i;
     ckeys[j] = make_uint2(ck.a, ck.b);
@@ -181,17 +182,18 @@ int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_str
 }
 
 int fgx_create_base_shard(const uint32_t key_host[2], int64_t n_total, int64_t n_active, int64_t first,
-                          int64_t n_local, int32_t agent_type, int32_t* unique_id, uint32_t* create_keys,
-                          float* active_state, int32_t* agent_types, fgx_stream_t stream) {
+                          int64_t stride, int64_t n_local, int32_t agent_type, int32_t* unique_id,
+                          uint32_t* create_keys, float* active_state, int32_t* agent_types, fgx_stream_t stream) {
   using namespace fgx;
   FGX_REQUIRE(key_host, "fgx_create_base: null key");
   FGX_REQUIRE(n_total >= 0 && n_active >= 0 && n_active <= n_total, "fgx_create_base: bad counts");
-  FGX_REQUIRE(first >= 0 && n_local >= 0 && first + n_local <= n_total, "fgx_create_base: bad shard range");
+  FGX_REQUIRE(first >= 0 && stride >= 1 && n_local >= 0 && (n_local == 0 || first + (n_local - 1) * stride < n_total),
+              "fgx_create_base: bad shard range");
   FGX_REQUIRE(n_total < (1ll << 30), "fgx_create_base: n_total too large for split(key, n+1)");
   if (n_local == 0) return FGX_OK;
   FGX_REQUIRE(unique_id && create_keys && active_state && agent_types, "fgx_create_base: null pointer");
   create_base_kernel<<<grid_for(n_local, 256, 8), 256, 0, as_stream(stream)>>>(
-      Key{key_host[0], key_host[1]}, n_total, n_active, first, n_local, agent_type, unique_id,
+      Key{key_host[0], key_host[1]}, n_total, n_active, first, stride, n_local, agent_type, unique_id,
       reinterpret_cast<uint2*>(create_keys), active_state, agent_types);
   return check_launch("fgx_create_base");
 }
@@ -199,7 +201,7 @@ int fgx_create_base_shard(const uint32_t key_host[2], int64_t n_total, int64_t n
 int fgx_create_base(const uint32_t key_host[2], int64_t n_total, int64_t n_active, int32_t agent_type,
                     int32_t* unique_id, uint32_t* create_keys, float* active_state, int32_t* agent_types,
                     fgx_stream_t stream) {
-  return fgx_create_base_shard(key_host, n_total, n_active, 0, n_total, agent_type, unique_id, create_keys,
+  return fgx_create_base_shard(key_host, n_total, n_active, 0, 1, n_total, agent_type, unique_id, create_keys,
                                active_state, agent_types, stream);
 }
 }

@@ -113,11 +113,12 @@ int fgx_create_base(const uint32_t key_host[2], int64_t n_total, int64_t n_activ
                     int32_t* unique_id, uint32_t* create_keys, float* active_state, int32_t* agent_types,
                     fgx_stream_t stream);
 
-/* the same for the slots [first, first+n_local) of the set only: a shard of a multi-GPU run
- * produces exactly its rows of the single-GPU result (arrays have n_local entries)           */
+/* the same for the slots first, first+stride, ... (n_local of them) of the set only: a shard of a
+ * multi-GPU run produces exactly its rows of the single-GPU result (arrays have n_local entries);
+ * stride 1 = a contiguous block, stride G with first = rank = round-robin sharding              */
 int fgx_create_base_shard(const uint32_t key_host[2], int64_t n_total, int64_t n_active, int64_t first,
-                          int64_t n_local, int32_t agent_type, int32_t* unique_id, uint32_t* create_keys,
-                          float* active_state, int32_t* agent_types, fgx_stream_t stream);
+                          int64_t stride, int64_t n_local, int32_t agent_type, int32_t* unique_id,
+                          uint32_t* create_keys, float* active_state, int32_t* agent_types, fgx_stream_t stream);
 
 /* ---- K1: ray casting (space_methods.py) ---------------------------------- */
 /* Walls are struct-of-arrays float32[n_walls]: (wx1,wy1) = Wall.p1, (wx2,wy2) = Wall.p2

@@ -201,3 +201,28 @@ def test_non_native_callbacks_are_rejected(cuda):
     import foragax_b200.base.agent_methods as fgx_methods
     with pytest.raises(TypeError, match="no CPU fallback"):
         fgx_methods.jit_remove_agents(lambda p, a, i: a, 1, None, None)
+
+
+@pytest.mark.parametrize("world,stride_mode", [(3, "round_robin"), (4, "blocks")])
+def test_sharded_create_equals_global_rows(cuda, world, stride_mode):
+    """Every rank of a multi-GPU run builds exactly its rows of the single-GPU set (fgx_create_base_shard)."""
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples.hello_world import Dice
+    n, n_active = 10007, 6001
+    s = fgx_classes.Agent_Set(agent=Dice, num_total_agents=n, num_active_agents=n_active, agent_type=2)
+    full = to_np(fgx_methods.create_agents(None, s, fgx_random.PRNGKey(9)))
+    for r in range(world):
+        if stride_mode == "round_robin":
+            rows = np.arange(r, n, world)
+            shard = (r, len(rows), world)
+        else:
+            lo, hi = r * n // world, (r + 1) * n // world
+            rows = np.arange(lo, hi)
+            shard = (lo, hi - lo)
+        part = to_np(fgx_methods.create_agents(None, s, fgx_random.PRNGKey(9), shard=shard))
+        for k in ("unique_id", "agent_type", "active_state", "age"):
+            np.testing.assert_array_equal(part[k], full[k][rows], err_msg=k)
+        np.testing.assert_array_equal(part["state"]["draw"], full["state"]["draw"][rows])
+        np.testing.assert_array_equal(part["state"]["key"], full["state"]["key"][rows])
