@@ -11,10 +11,12 @@
 //
 //   1. counting sort of the targets by cell (histogram with atomics, scan, scatter) and of the
 //      sensing agents by cell;
-//   2. one CTA task = 256 (agent, ray-group) threads of ONE cell: the targets of the 3x3
-//      neighbourhood are staged through shared memory in chunks and shared by all threads of the
-//      task; per (agent, target) the difference vector and c = |s|^2 - r^2 are hoisted out of the
-//      ray loop and far targets are skipped before any per-ray work;
+//   2. one CTA task = 8 agents of ONE cell, one warp per agent; the targets of the 3x3
+//      neighbourhood are staged through shared memory in chunks and shared by the 8 warps.
+//      Broad phase, lanes = targets: each lane takes one staged target, forms s = o - c and
+//      c = |s|^2 - r^2 and rejects it if it is inactive, farther than ray_length + r, or outside the
+//      ray fan by more than its radius.  Narrow phase, lanes = rays: the few survivors (ballot) are
+//      broadcast one by one with shuffles and every lane tests its own ray against them;
 //   3. optional merge with the wall result of fgx_raycast_walls in entity order [agents, walls].
 #include "common.cuh"
 #include "geometry.cuh"
@@ -22,7 +24,8 @@
 namespace fgx {
 
 constexpr int RA_BLOCK = 256;
-constexpr int RA_RPT = 8;      // rays per thread
+constexpr int RA_WARPS = RA_BLOCK / 32;  // agents per CTA task
+constexpr int RA_MAXRB = 4;              // rays per lane (n_rays <= 128)
 constexpr int RA_CHUNK = 512;  // targets staged per shared-memory chunk
 
 struct GridDesc {
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(int n_cells, int groups
     if (c < n_cells) {
       v[0] = tcount[c];
       v[1] = acount[c];
-      v[2] = (v[1] * (uint32_t)groups + RA_BLOCK - 1) / RA_BLOCK;
+      v[2] = (v[1] + RA_WARPS - 1) / RA_WARPS;  // CTA tasks of this cell (8 agents each)
     }
     uint32_t inc[3];
 #pragma unroll
@@ -145,41 +148,48 @@ struct RaycastAgentsArgs {
   int32_t* hit;
 };
 
+template <int RB>
 __global__ void __launch_bounds__(RA_BLOCK) raycast_agents_kernel(const RaycastAgentsArgs a) {
   __shared__ float4 st[RA_CHUNK];
   __shared__ int32_t si[RA_CHUNK];
   const int n_cells = a.g.gx * a.g.gy;
   const uint32_t total_tasks = a.bstart[n_cells];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float L = a.L;
+  // far-target bound: a hit needs |s| <= L + r, i.e. c = |s|^2 - r^2 <= L^2 + 2 L r
+  const float L2 = f_mul(L, L), twoL = f_mul(2.0f, L);
+  // fan cull (only for a convex fan): a circle farther than r from the cone of half-angle `span`
+  // around the heading cannot be hit by any ray of the fan
+  const bool fan_cull = a.span < 1.5f;
+  float cs_span = 1.0f, sn_span = 0.0f;
+  if (fan_cull) sincosf(a.span, &sn_span, &cs_span);
   for (uint32_t task = blockIdx.x; task < total_tasks; task += gridDim.x) {
-    // cell of this task: last c with bstart[c] <= task
-    int lo = 0, hi = n_cells;
+    int lo = 0, hi = n_cells;  // cell of this task: last c with bstart[c] <= task
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if (a.bstart[mid] <= task) lo = mid; else hi = mid;
     }
     const int cell = lo;
-    const uint32_t t_in_cell = (task - a.bstart[cell]) * RA_BLOCK + threadIdx.x;
-    const uint32_t slot = t_in_cell / a.groups;
-    const int ray0 = (int)(t_in_cell - slot * a.groups) * RA_RPT;
+    const uint32_t slot = (task - a.bstart[cell]) * RA_WARPS + warp;
     const uint32_t a0 = a.astart[cell], a1 = a.astart[cell + 1];
-    const bool valid = a0 + slot < a1;
+    const bool valid = a0 + slot < a1;                     // warp-uniform
     const int64_t agent = valid ? a.order[a0 + slot] : 0;
     const bool act = valid && (a.aactive == nullptr || a.aactive[agent] != 0.0f);
-    const float ox = valid ? a.ax[agent] : 0.0f, oy = valid ? a.ay[agent] : 0.0f, L = a.L;
-    float dx[RA_RPT], dy[RA_RPT], best[RA_RPT];
-    int bidx[RA_RPT];
+    const float ox = valid ? a.ax[agent] : 0.0f, oy = valid ? a.ay[agent] : 0.0f;
+    const float ang = valid ? a.aang[agent] : 0.0f;
+    float hu, hv;  // heading
+    sincosf(ang, &hv, &hu);
+    float dx[RB], dy[RB], best[RB];
+    int bidx[RB];
     {
-      const float ang = valid ? a.aang[agent] : 0.0f;
       const float lo_a = f_sub(ang, a.span), hi_a = f_add(ang, a.span);
 #pragma unroll
-      for (int j = 0; j < RA_RPT; ++j) {
-        sincosf(linspace_elem(lo_a, hi_a, a.n_rays, min(ray0 + j, a.n_rays - 1)), &dy[j], &dx[j]);
-        best[j] = L;
-        bidx[j] = -1;
+      for (int q = 0; q < RB; ++q) {
+        sincosf(linspace_elem(lo_a, hi_a, a.n_rays, min(lane + 32 * q, a.n_rays - 1)), &dy[q], &dx[q]);
+        best[q] = L;
+        bidx[q] = -1;
       }
     }
-    // far-target bound: a hit needs |s| <= L + r, i.e. c = |s|^2 - r^2 <= L^2 + 2 L r
-    const float L2 = f_mul(L, L), twoL = f_mul(2.0f, L);
     const int cx = cell % a.g.gx, cy = cell / a.g.gx;
     for (int ry = max(cy - 1, 0); ry <= min(cy + 1, a.g.gy - 1); ++ry) {
       const int c_lo = ry * a.g.gx + max(cx - 1, 0), c_hi = ry * a.g.gx + min(cx + 1, a.g.gx - 1);
@@ -193,22 +203,38 @@ __global__ void __launch_bounds__(RA_BLOCK) raycast_agents_kernel(const RaycastA
         }
         __syncthreads();
         if (!act) continue;
-        for (int k = 0; k < cnt; ++k) {
-          const float4 t = st[k];
-          if (t.w == 0.0f) continue;  // inactive target: ray_length (space_methods.py:92)
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+          // broad phase: lane <-> target
+          const int k = k0 + lane;
+          const float4 t = st[min(k, cnt - 1)];
           const float sx = f_sub(ox, t.x), sy = f_sub(oy, t.y);
           const float c = f_sub(f_add(f_mul(sx, sx), f_mul(sy, sy)), f_mul(t.z, t.z));
-          if (c > f_mul(f_add(L2, f_mul(twoL, t.z)), 1.0001f)) continue;
-          const int id = si[k];
+          bool pass = k < cnt && t.w != 0.0f && !(c > f_mul(f_add(L2, f_mul(twoL, t.z)), 1.0001f));
+          if (fan_cull) {
+            // v = c - o = -s in the heading frame: along = v.h, across = |v x h|
+            const float along = -(sx * hu + sy * hv), across = fabsf(sx * hv - sy * hu);
+            const float outside = across * cs_span - along * sn_span;  // distance to the fan's boundary line
+            pass = pass && !(outside > t.z * 1.0001f + 1e-4f * (fabsf(sx) + fabsf(sy)) + 1e-6f);
+          }
+          unsigned m = __ballot_sync(0xffffffffu, pass);
+          const int id = si[min(k, cnt - 1)];
+          // narrow phase: lane <-> ray, survivors broadcast one at a time
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1u;
+            const float bsx = __shfl_sync(0xffffffffu, sx, src), bsy = __shfl_sync(0xffffffffu, sy, src);
+            const float bc = __shfl_sync(0xffffffffu, c, src);
+            const int bid = __shfl_sync(0xffffffffu, id, src);
 #pragma unroll
-          for (int j = 0; j < RA_RPT; ++j) {
-            const float b = f_add(f_mul(sx, dx[j]), f_mul(sy, dy[j]));
-            const float h = f_sub(f_mul(b, b), c);
-            if (h >= 0.0f) {
-              const float tt = f_sub(-b, __fsqrt_rn(h));
-              if (tt >= 0.0f && (tt < best[j] || (tt == best[j] && id < bidx[j]))) {
-                best[j] = tt;
-                bidx[j] = id;
+            for (int q = 0; q < RB; ++q) {
+              const float b = f_add(f_mul(bsx, dx[q]), f_mul(bsy, dy[q]));
+              const float h = f_sub(f_mul(b, b), bc);
+              if (h >= 0.0f) {
+                const float tt = f_sub(-b, __fsqrt_rn(h));
+                if (tt >= 0.0f && (tt < best[q] || (tt == best[q] && bid < bidx[q]))) {
+                  best[q] = tt;
+                  bidx[q] = bid;
+                }
               }
             }
           }
@@ -217,17 +243,17 @@ __global__ void __launch_bounds__(RA_BLOCK) raycast_agents_kernel(const RaycastA
     }
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < RA_RPT; ++j) {
-        const int rj = ray0 + j;
+      for (int q = 0; q < RB; ++q) {
+        const int rj = lane + 32 * q;
         if (rj >= a.n_rays) continue;
         const int64_t o = agent * a.n_rays + rj;
-        float d = act ? best[j] : 0.0f;
-        int h = act ? bidx[j] : -1;
+        float d = act ? best[q] : 0.0f;
+        int h = act ? bidx[q] : -1;
         if (a.merge_walls && act) {
           // entity order [agents, walls]: an agent wins a tie; wall index w -> m + w
           const float wd = a.dist[o];
           const int wh = a.hit[o];
-          if (!(bidx[j] >= 0 && best[j] <= wd)) {
+          if (!(bidx[q] >= 0 && best[q] <= wd)) {
             d = wd;
             h = wh >= 0 ? (int)(a.m + wh) : -1;
           }
@@ -299,7 +325,8 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   using namespace fgx;
   FGX_REQUIRE(n_agents >= 0 && n_targets >= 0 && n_agents < (1ll << 31) && n_targets < (1ll << 31),
               "fgx_raycast_agents: size out of range");
-  FGX_REQUIRE(n_rays > 0 && target_stride >= 1, "fgx_raycast_agents: bad n_rays / stride");
+  FGX_REQUIRE(n_rays > 0 && n_rays <= 32 * RA_MAXRB && target_stride >= 1,
+              "fgx_raycast_agents: n_rays must be 1..%d, stride >= 1", 32 * RA_MAXRB);
   if (n_agents == 0) return FGX_OK;
   FGX_REQUIRE(x && y && ang && dist && hit, "fgx_raycast_agents: null pointer");
   FGX_REQUIRE(n_targets == 0 || (tx && ty && trad && tactive), "fgx_raycast_agents: null target array");
@@ -315,7 +342,7 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(s.tcount, 0, al256((size_t)n_cells * 4) * 2, st);  // tcount + acount
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_agents: %s", cudaGetErrorString(e));
-  const int groups = (n_rays + RA_RPT - 1) / RA_RPT;
+  const int groups = 1;  // one warp per agent
   if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, target_stride, n_targets, s.tcell, s.tcount);
   grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, 1, n_agents, s.acell, s.acount);
   grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, groups, s.tcount, s.acount, s.tstart, s.astart, s.bstart);
@@ -328,9 +355,15 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   RaycastAgentsArgs a{g, x, y, ang, active, n_agents, n_targets, n_rays, groups, ray_span, ray_length,
                       s.tstart, s.astart, s.bstart, s.order, s.sorted, s.tidx, merge_walls ? 1 : 0, dist, hit};
   // upper bound of CTA tasks: every cell rounds up by at most one
-  const int64_t max_tasks = ceil_div(n_agents * groups, RA_BLOCK) + n_cells;
+  const int64_t max_tasks = ceil_div(n_agents, RA_WARPS) + n_cells;
   const int64_t cap = (int64_t)sm_count() * 8;
-  raycast_agents_kernel<<<(int)(max_tasks < cap ? max_tasks : cap), RA_BLOCK, 0, st>>>(a);
+  const int grid = (int)(max_tasks < cap ? max_tasks : cap);
+  switch ((n_rays + 31) / 32) {
+    case 1: raycast_agents_kernel<1><<<grid, RA_BLOCK, 0, st>>>(a); break;
+    case 2: raycast_agents_kernel<2><<<grid, RA_BLOCK, 0, st>>>(a); break;
+    case 3: raycast_agents_kernel<3><<<grid, RA_BLOCK, 0, st>>>(a); break;
+    default: raycast_agents_kernel<4><<<grid, RA_BLOCK, 0, st>>>(a); break;
+  }
   return check_launch("fgx_raycast_agents");
 }
 }
