@@ -407,7 +407,7 @@ def run_ours(args):
         peak_tflops = sms * 128 * sm_max * 1e6 / 1e12  # non-FMA FP32 lanes x clock
         ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (k1_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": None, "kernel": "raycast_walls_kernel<8,2>", "kernel_ms": k1_ms,
+                "traffic": None, "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": k1_ms,
                 "share_of_step": k1_ms / (k1_ms + k2_ms),
                 "peak_basis": f"{sms} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz, {peak_src} "
                               "MEASURED_PEAKS.json), non-FMA; 20 FLOP per ray-wall test (SURVEY.md 8d)"}

@@ -9,7 +9,8 @@
 //  * wall segments are bulk-copied global -> shared with cp.async.bulk (TMA, completion on
 //    an mbarrier), then re-laid out once per CTA as float4 (p2x,p2y,q2x,q2y) + float2
 //    (q2-p2), so the inner loop issues one LDS.128 + one LDS.64 per wall (warp broadcast);
-//  * a thread owns RPT rays of one agent (q1 and q1-p1 in registers); per wall the
+//  * a thread owns RPT rays of one agent (16 when the ray count allows: 218 registers, one CTA per
+//    SM, 16-way instruction-level parallelism; q1 and q1-p1 in registers); per wall the
 //    agent-only determinant o3 is computed once and amortised over the RPT rays; o4
 //    reuses the two differences of o2 (fp negation is exact), so a test costs 13 rounded
 //    FP32 ops + 3 products + the sign/zero test;
@@ -365,9 +366,11 @@ int fgx_raycast_walls(const float* x, const float* y, const float* ang, const fl
       case 4: return launch_raycast<4, 5>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
       case 5: return launch_raycast<2, 6>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
       case 6: return launch_raycast<4, 2>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
+      case 7: return launch_raycast<8, 2>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
       default: break;
     }
   }
+  if (n_rays % 16 == 0) return launch_raycast<16, 1>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
   if (n_rays % 8 == 0) return launch_raycast<8>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
   if (n_rays % 4 == 0) return launch_raycast<4>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);
   if (n_rays % 3 == 0) return launch_raycast<3>(x, y, ang, active, n_agents, n_rays, ray_span, ray_length, w, n_walls, dist, hit, s);

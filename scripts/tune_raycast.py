@@ -19,8 +19,8 @@ w = work["walls"]
 walls = Wall(Point(up(w[0]), up(w[1])), Point(up(w[2]), up(w[3])))
 out = (torch.empty((bench.N_AGENTS, 32), dtype=torch.float32, device=dev),
        torch.empty((bench.N_AGENTS, 32), dtype=torch.int32, device=dev))
-names = {"": "default", "1": "RPT8/minb3", "2": "RPT4/minb3", "3": "RPT4/minb4", "4": "RPT4/minb5", "5": "RPT2/minb6",
-         "6": "RPT4/minb2"}
+names = {"": "default(RPT16/1)", "1": "RPT8/minb3", "2": "RPT4/minb3", "3": "RPT4/minb4", "4": "RPT4/minb5", "5": "RPT2/minb6",
+         "6": "RPT4/minb2", "7": "RPT8/minb2"}
 ref = None
 for v in (sys.argv[1:] or list(names)):
     if v:
