@@ -130,6 +130,16 @@ class ClockSampler:
         return out
 
 
+def measured_traffic(kernel, n_local):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json),
+    scaled to this rank's shard; None if there is no capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    return None if not t else t["dram_bytes_per_launch"] * n_local / t["agents"]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -407,7 +417,9 @@ def run_ours(args):
         peak_tflops = sms * 128 * sm_max * 1e6 / 1e12  # non-FMA FP32 lanes x clock
         ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (k1_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": None, "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": k1_ms,
+                "traffic": measured_traffic("raycast_walls_kernel", n_local),
+                "algorithmic_bytes": float(n_local) * (16 + 8 * N_RAYS),
+                "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": k1_ms,
                 "share_of_step": k1_ms / (k1_ms + k2_ms),
                 "peak_basis": f"{sms} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz, {peak_src} "
                               "MEASURED_PEAKS.json), non-FMA; 20 FLOP per ray-wall test (SURVEY.md 8d)"}
@@ -417,7 +429,8 @@ def run_ours(args):
         k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         roof2 = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
-                 "traffic": None, "kernel": "forager_step_kernel", "kernel_ms": k2_ms,
+                 "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
+                 "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
                  "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
