@@ -90,7 +90,7 @@ template <int RPT>
 __device__ __forceinline__ void flush_queue(RaySet<RPT>& r, const uint32_t* q, int qn, const float4* wall4,
                                             int64_t chunk_base) {
   for (int e = 0; e < qn; ++e) {
-    const int wl = (int)q[e * RC_BLOCK];
+    const int wl = (int)q[e * blockDim.x];
     const float4 w = wall4[wl];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -112,8 +112,8 @@ __device__ __forceinline__ bool sure_miss(float A, float B, float C) {
   return (fmaxf(A, B) > 0.0f) && (fabsf(C) > 0.0f);
 }
 
-template <int RPT, int MINB>
-__global__ void __launch_bounds__(RC_BLOCK, MINB)
+template <int RPT, int MINB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
     raycast_walls_kernel(const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ aang,
                          const float* __restrict__ aactive, int64_t n_agents, int n_rays, float span, float L,
                          WallsSoA walls, int64_t n_walls, int chunk, int tma_ok, float* __restrict__ dist,
@@ -131,12 +131,12 @@ __global__ void __launch_bounds__(RC_BLOCK, MINB)
 
   const int groups = (n_rays + RPT - 1) / RPT;  // ray groups per agent
   const int64_t total = n_agents * groups;
-  const int64_t num_tiles = (total + RC_BLOCK - 1) / RC_BLOCK;
+  const int64_t num_tiles = (total + BLOCK - 1) / BLOCK;
   const int n_chunks = (int)((n_walls + chunk - 1) / chunk);
   if (n_chunks == 1) stage_walls(walls, 0, (int)n_walls, chunk, tma_ok, stage, wall4, wdir, bar, parity);
 
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t task = tile * RC_BLOCK + threadIdx.x;
+    const int64_t task = tile * BLOCK + threadIdx.x;
     const bool valid = task < total;
     const int64_t agent = valid ? task / groups : 0;
     const int ray0 = valid ? (int)(task - agent * groups) * RPT : 0;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(RC_BLOCK, MINB)
             }
           }
           if (cand) {
-            queue[qn * RC_BLOCK] = (uint32_t)w;
+            queue[qn * BLOCK] = (uint32_t)w;
             ++qn;
           }
         }
@@ -249,33 +249,33 @@ __global__ void __launch_bounds__(RC_BLOCK, MINB)
   }
 }
 
-static size_t raycast_smem_bytes(int chunk) {
-  const size_t stage = (size_t)chunk * 16, queue = (size_t)RC_QCAP * RC_BLOCK * 4;
+static size_t raycast_smem_bytes(int chunk, int block) {
+  const size_t stage = (size_t)chunk * 16, queue = (size_t)RC_QCAP * block * 4;
   return 16 + (size_t)chunk * (16 + 8) + (stage > queue ? stage : queue);
 }
 
-template <int RPT, int MINB = 2>
+template <int RPT, int MINB = 2, int BLOCK = RC_BLOCK>
 static int launch_raycast(const float* x, const float* y, const float* ang, const float* active, int64_t n,
                           int n_rays, float span, float L, WallsSoA w, int64_t n_walls, float* dist, int32_t* hit,
                           cudaStream_t s) {
   int chunk = (int)(n_walls < RC_CHUNK ? n_walls : RC_CHUNK);
   chunk = chunk < 4 ? 4 : (chunk + 3) & ~3;  // stage rows stay 16-byte aligned
-  const size_t smem = raycast_smem_bytes(chunk);
-  auto kern = raycast_walls_kernel<RPT, MINB>;
+  const size_t smem = raycast_smem_bytes(chunk, BLOCK);
+  auto kern = raycast_walls_kernel<RPT, MINB, BLOCK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)raycast_smem_bytes(RC_CHUNK));
+                                       (int)raycast_smem_bytes(RC_CHUNK, BLOCK));
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls: %s", cudaGetErrorString(e));
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RC_BLOCK, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   const int groups = (n_rays + RPT - 1) / RPT;
-  const int64_t tiles = ceil_div(n * groups, RC_BLOCK);
+  const int64_t tiles = ceil_div(n * groups, BLOCK);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int grid = (int)(tiles < cap ? tiles : cap);
   const uintptr_t al = reinterpret_cast<uintptr_t>(w.x1) | reinterpret_cast<uintptr_t>(w.y1) |
                        reinterpret_cast<uintptr_t>(w.x2) | reinterpret_cast<uintptr_t>(w.y2);
   const int tma_ok = (al & 15) == 0;
-  kern<<<grid, RC_BLOCK, smem, s>>>(x, y, ang, active, n, n_rays, span, L, w, n_walls, chunk, tma_ok, dist, hit);
+  kern<<<grid, BLOCK, smem, s>>>(x, y, ang, active, n, n_rays, span, L, w, n_walls, chunk, tma_ok, dist, hit);
   return check_launch("fgx_raycast_walls");
 }
 
