@@ -307,9 +307,9 @@ def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space,
                                  foragers)
     age_after_death = foragers.age.sum(dtype=torch.float32)
     life_expectancy = (age_before_death - age_after_death) / (num_foragers_remove + 0.01)
-    life_expectancy = torch.where(life_expectancy == 0.0, torch.as_tensor(life_expectancy_old, dtype=torch.float32,
-                                                                         device=life_expectancy.device),
-                                  life_expectancy)
+    if not isinstance(life_expectancy_old, torch.Tensor):
+        life_expectancy_old = torch.as_tensor(life_expectancy_old, dtype=torch.float32, device=life_expectancy.device)
+    life_expectancy = torch.where(life_expectancy == 0.0, life_expectancy_old.reshape(()), life_expectancy)
 
     def select_depleted_resources(resources, select_params):
         return (P(resources.active_state) == 1.0) & (P(resources.state.content['energy'])
@@ -380,7 +380,7 @@ class Foraging_world:
         ks = fgx_random.split(self.key)
         self.key, subkey = ks[0].contiguous(), ks[1].contiguous()
         self.resources_set.agents = create_agents(resources_create_params, self.resources_set, subkey)
-        self.life_expectancy = 50.0
+        self.life_expectancy = torch.tensor(50.0, dtype=torch.float32, device=self.key.device)
 
     def step(self):
         dist_mat, energy_in, energy_out = jit_forager_resource_interaction(self.foragers_set.agents,
@@ -400,6 +400,28 @@ class Foraging_world:
                                                     self.resources_set.num_total_agents, self.space,
                                                     self.life_expectancy)
         return num_active_foragers, num_active_resources, self.life_expectancy
+
+    def capture(self, warmup=2):
+        """Capture one whole tick into a CUDA graph (``foragax_b200.graphs.GraphedTick``): ``warmup`` real
+        ticks are run first; afterwards every ``replay()`` is one tick and returns the static
+        ``(num_active_foragers, num_active_resources, life_expectancy)`` tensors."""
+        from ..graphs import GraphedTick
+        state = {'foragers': self.foragers_set.agents, 'resources': self.resources_set.agents, 'key': self.key,
+                 'life': self.life_expectancy}
+
+        def bind(st):
+            self.foragers_set.agents, self.resources_set.agents = st['foragers'], st['resources']
+            self.key, self.life_expectancy = st['key'], st['life']
+
+        def tick(st):
+            bind(st)
+            out = self.step()
+            return {'foragers': self.foragers_set.agents, 'resources': self.resources_set.agents, 'key': self.key,
+                    'life': self.life_expectancy}, out
+
+        g = GraphedTick(tick, state, warmup)
+        bind(state)
+        return g
 
     def run(self, print_freq=0):
         out = []

@@ -170,3 +170,24 @@ def test_g2_golden_on_the_cuda_path(cuda):
             assert abs(float(le) - G2[t][2]) <= 1e-4 * max(1.0, abs(G2[t][2])), f"tick {t}"
     finally:
         fg.use_variant("sim")
+
+
+def test_cuda_graph_replay_equals_eager_ticks(cuda):
+    """A whole tick captured into a CUDA graph and replayed (one launch per tick) walks the same
+    trajectory as the eager calls -- same kernels, same order -- and still reproduces G2."""
+    fg, w_eager, cfg = make_world("nb", cuda)
+    _, w_graph, _ = make_world("nb", cuda)
+    try:
+        g = w_graph.capture(warmup=2)          # ticks 0 and 1 run eagerly inside capture()
+        for t in range(2):
+            w_eager.step()
+        for t in range(2, 30):
+            nf, nr, le = g.replay()
+            enf, enr, ele = w_eager.step()
+            assert (int(nf), int(nr)) == (int(enf), int(enr)) == (G2[t][0], G2[t][1]), f"tick {t}"
+            assert float(le) == float(ele)
+        a, b = np_forager(w_graph.foragers_set.agents), np_forager(w_eager.foragers_set.agents)
+        assert_tree(a, b, exact={"state." + k for k in ofo.FSTATE} | {"policy." + k for k in ("J", "tau", "E", "B", "D", "Z")})
+        np.testing.assert_array_equal(w_graph.key.cpu().numpy(), w_eager.key.cpu().numpy())
+    finally:
+        fg.use_variant("sim")
