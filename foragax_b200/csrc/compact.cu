@@ -51,41 +51,46 @@ __device__ __forceinline__ int64_t tile_elem(int64_t tile, int w, int r, int l) 
   return tile * SEL_TILE + w * (32 * SEL_ITEMS) + r * 32 + l;
 }
 
-// Truth values of ONE term for the thread's SEL_ITEMS slots, as a bit mask.  The loads are issued
-// back to back with no control flow between them (all in flight together); the comparison runs on
-// registers afterwards.
-template <typename T>
-__device__ __forceinline__ unsigned term_mask(const fgx_pred_term_t& t, int64_t tile, int64_t n, int w, int l) {
+// Truth values of ONE term for a lane's ITEMS slots start + r*32 + l, as a bit mask.  The loads are
+// issued back to back with no control flow between them (all in flight together); the comparison
+// runs on registers afterwards.
+template <typename T, int ITEMS>
+__device__ __forceinline__ unsigned term_mask(const fgx_pred_term_t& t, int64_t start, int64_t n, int l) {
   const T* __restrict__ base = reinterpret_cast<const T*>(t.data);
-  uint32_t raw[SEL_ITEMS];
+  uint32_t raw[ITEMS];
 #pragma unroll
-  for (int r = 0; r < SEL_ITEMS; ++r) {
-    const int64_t i = min(tile_elem(tile, w, r, l), n - 1);
+  for (int r = 0; r < ITEMS; ++r) {
+    const int64_t i = min(start + r * 32 + l, n - 1);
     raw[r] = (uint32_t)__ldg(base + i * t.stride);
   }
   unsigned m = 0;
 #pragma unroll
-  for (int r = 0; r < SEL_ITEMS; ++r) m |= (compare_bits(raw[r], t.dtype, t.op, t.imm_bits) ? 1u : 0u) << r;
+  for (int r = 0; r < ITEMS; ++r) m |= (compare_bits(raw[r], t.dtype, t.op, t.imm_bits) ? 1u : 0u) << r;
   return m;
 }
 
-// selected flags of the thread's SEL_ITEMS slots (bit r = slot of round r)
-__device__ __forceinline__ unsigned tile_flags(const fgx_predicate_t& p, int64_t tile, int64_t n, int w, int l) {
+// selected flags of a lane's ITEMS slots (bit r = slot start + r*32 + l)
+template <int ITEMS>
+__device__ __forceinline__ unsigned flags_at(const fgx_predicate_t& p, int64_t start, int64_t n, int l) {
   unsigned tm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
   for (int t = 0; t < 4; ++t)
     if (t < p.n_terms)
-      tm[t] = p.term[t].dtype == FGX_U8 ? term_mask<uint8_t>(p.term[t], tile, n, w, l)
-                                        : term_mask<uint32_t>(p.term[t], tile, n, w, l);
+      tm[t] = p.term[t].dtype == FGX_U8 ? term_mask<uint8_t, ITEMS>(p.term[t], start, n, l)
+                                        : term_mask<uint32_t, ITEMS>(p.term[t], start, n, l);
   unsigned f = 0;
 #pragma unroll
-  for (int r = 0; r < SEL_ITEMS; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const unsigned idx = ((tm[0] >> r) & 1u) | (((tm[1] >> r) & 1u) << 1) | (((tm[2] >> r) & 1u) << 2) |
                          (((tm[3] >> r) & 1u) << 3);
-    const bool in = tile_elem(tile, w, r, l) < n;
+    const bool in = start + r * 32 + l < n;
     f |= (in ? (p.lut >> idx) & 1u : 0u) << r;
   }
   return f;
+}
+
+__device__ __forceinline__ unsigned tile_flags(const fgx_predicate_t& p, int64_t tile, int64_t n, int w, int l) {
+  return flags_at<SEL_ITEMS>(p, tile_elem(tile, w, 0, 0), n, l);
 }
 
 __device__ __forceinline__ int tile_count(const fgx_predicate_t& p, int64_t tile, int64_t n, int* warp_sums) {
@@ -182,24 +187,44 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_scatter_kernel(const __grid_
   for (int64_t tile = t0; tile < t1; ++tile) off += tile_scatter(p, tile, n, off, total, perm, warp_sums);
 }
 
-// small sets (a few tiles): one CTA, one launch
-__global__ void __launch_bounds__(SEL_BLOCK) select_small_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
-                                                                int64_t num_tiles, int32_t* __restrict__ perm,
-                                                                int32_t* __restrict__ count_out) {
-  __shared__ int warp_sums[SEL_WARPS];
-  __shared__ int offs[64];
-  int total = 0;
-  for (int64_t tile = 0; tile < num_tiles; ++tile) {
-    const int c = tile_count(p, tile, n, warp_sums);
-    if (threadIdx.x == 0) offs[tile] = total;
-    total += c;
+// small sets (<= 16384 slots): ONE CTA of 1024 threads holds every slot's flag in registers -- one round
+// of loads, one block scan, one scatter (config C2's select calls are latency-bound, not bandwidth-bound)
+constexpr int SEL_SMALL_BLOCK = 1024;
+constexpr int64_t SEL_SMALL_MAX = 16384;
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SEL_SMALL_BLOCK) select_small_kernel(const __grid_constant__ fgx_predicate_t p,
+                                                                      int64_t n, int32_t* __restrict__ perm,
+                                                                      int32_t* __restrict__ count_out) {
+  __shared__ int warp_sums[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int64_t start = (int64_t)w * (32 * ITEMS);
+  const unsigned flags = flags_at<ITEMS>(p, start, n, l);
+  unsigned ball[ITEMS];
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    ball[r] = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
+    c += __popc(ball[r]);
   }
+  if (l == 0) warp_sums[w] = c;
   __syncthreads();
-  for (int64_t tile = 0; tile < num_tiles; ++tile) tile_scatter(p, tile, n, offs[tile], total, perm, warp_sums);
+  const int mine = warp_sums[l];  // 32 warps: lane k holds warp k's count
+  const int total = __reduce_add_sync(0xffffffffu, mine);
+  int before = __reduce_add_sync(0xffffffffu, l < w ? mine : 0);
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int64_t i = start + r * 32 + l;
+    if (i < n) {
+      const int rank = before + __popc(ball[r] & lt);
+      const bool s = (ball[r] >> l) & 1u;
+      perm[s ? (int64_t)rank : (int64_t)total + (i - rank)] = (int32_t)i;
+    }
+    before += __popc(ball[r]);
+  }
   if (threadIdx.x == 0) *count_out = total;
 }
-
-constexpr int64_t SEL_SMALL_TILES = 8;  // <= 16384 slots: single-CTA path
 
 }  // namespace fgx
 
@@ -232,8 +257,13 @@ int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32
   }
   FGX_REQUIRE(perm, "fgx_select: null perm");
   const int64_t tiles = ceil_div(n, SEL_TILE);
-  if (tiles <= SEL_SMALL_TILES) {
-    select_small_kernel<<<1, SEL_BLOCK, 0, s>>>(*pred_host, n, tiles, perm, count);
+  if (n <= SEL_SMALL_MAX) {
+    const int64_t items = ceil_div(n, SEL_SMALL_BLOCK);
+    if (items <= 1) select_small_kernel<1><<<1, SEL_SMALL_BLOCK, 0, s>>>(*pred_host, n, perm, count);
+    else if (items <= 2) select_small_kernel<2><<<1, SEL_SMALL_BLOCK, 0, s>>>(*pred_host, n, perm, count);
+    else if (items <= 4) select_small_kernel<4><<<1, SEL_SMALL_BLOCK, 0, s>>>(*pred_host, n, perm, count);
+    else if (items <= 8) select_small_kernel<8><<<1, SEL_SMALL_BLOCK, 0, s>>>(*pred_host, n, perm, count);
+    else select_small_kernel<16><<<1, SEL_SMALL_BLOCK, 0, s>>>(*pred_host, n, perm, count);
     return check_launch("fgx_select(small)");
   }
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_select_scratch_bytes(n), "fgx_select: scratch too small");

@@ -295,40 +295,55 @@ __global__ void __launch_bounds__(256)
 }
 
 // forager_resource_interaction (sim.py:358-375): energy_in[f] = sum_r e(f,r), energy_out[r] = sum_f e(f,r),
-// e(f,r) = energy_r if |f - r| < rad_r + 0.1 else 0.  One thread per forager, resources tiled through
-// shared memory; energy_out is accumulated with atomics (all addends of one resource are equal, so
-// the sum does not depend on the order).
-__global__ void __launch_bounds__(256)
+// e(f,r) = energy_r if |f - r| < rad_r + 0.1 else 0.  One WARP per forager: lanes take 32 consecutive
+// resources (coalesced, IA_U independent groups in flight), hits are found by ballot and folded into the
+// forager's sum in ascending resource order (the order of a serial sum over r, kept so that the result
+// does not depend on the launch shape).  energy_out is accumulated with atomics: all addends of one
+// resource are equal, so that sum does not depend on the order either.
+constexpr int IA_WARPS = 8, IA_U = 4;
+
+__global__ void __launch_bounds__(IA_WARPS * 32)
     interaction_kernel(int64_t nf, const float* __restrict__ fx, const float* __restrict__ fy, int64_t nr,
                        const float* __restrict__ rx, const float* __restrict__ ry, const float* __restrict__ rrad,
                        const float* __restrict__ ren, float* __restrict__ energy_in, float* __restrict__ energy_out) {
-  __shared__ float4 tile[256];
-  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const float px = f < nf ? fx[f] : 0.0f, py = f < nf ? fy[f] : 0.0f;
+  const int lane = threadIdx.x & 31;
+  const int64_t f = blockIdx.x * (int64_t)IA_WARPS + (threadIdx.x >> 5);
+  if (f >= nf) return;
+  const float px = fx[f], py = fy[f];
   float acc = 0.0f;
-  for (int64_t base = 0; base < nr; base += 256) {
-    const int64_t r = base + threadIdx.x;
-    tile[threadIdx.x] = r < nr ? make_float4(rx[r], ry[r], f_add(rrad[r], 0.1f), ren[r]) : make_float4(0, 0, -1, 0);
-    __syncthreads();
-    const int cnt = (int)min((int64_t)256, nr - base);
-    if (f < nf) {
-      for (int k = 0; k < cnt; ++k) {
-        const float4 t = tile[k];
-        const float d = norm2(f_sub(t.x, px), f_sub(t.y, py));
-        if (d < t.z) {
-          acc = f_add(acc, t.w);
-          atomicAdd(energy_out + base + k, t.w);
-        }
-      }
+  for (int64_t base = 0; base < nr; base += 32 * IA_U) {
+    float x[IA_U], y[IA_U], z[IA_U], w[IA_U];
+#pragma unroll
+    for (int u = 0; u < IA_U; ++u) {
+      const int64_t r = base + u * 32 + lane;
+      const bool ok = r < nr;
+      x[u] = ok ? rx[r] : 0.0f;
+      y[u] = ok ? ry[r] : 0.0f;
+      z[u] = ok ? rrad[r] : -2.0f;
+      w[u] = ok ? ren[r] : 0.0f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < IA_U; ++u) {
+      const float d = norm2(f_sub(x[u], px), f_sub(y[u], py));
+      const bool hit = d < f_add(z[u], 0.1f);
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        acc = f_add(acc, __shfl_sync(0xffffffffu, w[u], src));
+      }
+      if (hit) atomicAdd(energy_out + base + u * 32 + lane, w[u]);
+    }
   }
-  if (f < nf) energy_in[f] = acc;
+  if (lane == 0) energy_in[f] = acc;
 }
 
-// sensor_model (sim.py:388-468): one thread per (forager, ray); entities = [foragers, resources, walls].
-// The reference prefilters agent entity e with column e of a distance matrix ordered
-// [resources, foragers] (sim.py:381,416,435) -- reproduced: `partner` is that other agent.
+// sensor_model (sim.py:388-468); entities = [foragers, resources, walls].  The reference prefilters
+// agent entity e with column e of a distance matrix ordered [resources, foragers] (sim.py:381,416,435)
+// -- reproduced: `partner` is that other agent.  One WARP per forager: the prefilter does not depend on
+// the ray, so the broad phase runs with lanes = entities (ballot of |partner - forager| < L + rad) and
+// only the survivors reach the narrow phase, lanes = rays, in ascending entity order (strict <: the
+// first minimum wins, as argmin does).
 struct SensorArgs {
   int64_t nf, nr, nw;
   const float *fx, *fy, *fang, *frad, *fen, *fact;
@@ -341,68 +356,77 @@ struct SensorArgs {
   float* obs;  // [nf, n_rays*3]
 };
 
-__global__ void __launch_bounds__(128) sensor_model_kernel(const SensorArgs a) {
-  __shared__ float4 ent[128];   // x, y, rad, active
-  __shared__ float2 part[128];  // partner x, y (the misaligned distance column)
-  const int64_t task = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t total = a.nf * a.n_rays;
-  const bool valid = task < total;
-  const int64_t f = valid ? task / a.n_rays : 0;
-  const int j = valid ? (int)(task - f * a.n_rays) : 0;
-  const bool act = valid && a.fact[f] != 0.0f;
-  const float ox = a.fx[f], oy = a.fy[f], L = a.L;
-  float s, c;
-  {
-    const float g = a.fang[f];
-    sincosf(linspace_elem(f_sub(g, a.span), f_add(g, a.span), a.n_rays, j), &s, &c);
-  }
-  float best = L;
-  int64_t bidx = -1;
+constexpr int SM_WARPS = 4, SM_U = 4;
+
+__global__ void __launch_bounds__(SM_WARPS * 32) sensor_model_kernel(const SensorArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = blockIdx.x * (int64_t)SM_WARPS + (threadIdx.x >> 5);
+  if (f >= a.nf) return;
+  const bool act = a.fact[f] != 0.0f;
+  const float ox = a.fx[f], oy = a.fy[f], L = a.L, g = a.fang[f];
   const int64_t ne = a.nf + a.nr;
-  for (int64_t base = 0; base < ne; base += 128) {
-    const int64_t e = base + threadIdx.x;
-    if (e < ne) {
-      const bool isf = e < a.nf;
-      const int64_t k = isf ? e : e - a.nf;
-      ent[threadIdx.x] = isf ? make_float4(a.fx[k], a.fy[k], a.frad[k], a.fact[k])
-                             : make_float4(a.rx[k], a.ry[k], a.rrad[k], a.ract[k]);
-      // column e of concat(forager-resource dists, forager-forager dists)
-      part[threadIdx.x] = e < a.nr ? make_float2(a.rx[e], a.ry[e]) : make_float2(a.fx[e - a.nr], a.fy[e - a.nr]);
-    }
-    __syncthreads();
+  for (int j0 = 0; j0 < a.n_rays; j0 += 32) {  // one pass for up to 32 rays
+    const int j = j0 + lane;
+    const bool ray = j < a.n_rays;
+    float best = L;
+    int64_t bidx = -1;
     if (act) {
-      const int cnt = (int)min((int64_t)128, ne - base);
-      for (int k = 0; k < cnt; ++k) {
-        const float4 t = ent[k];
-        const float2 q = part[k];
-        const float pd = norm2(f_sub(q.x, ox), f_sub(q.y, oy));
-        if (pd < f_add(L, t.z)) {
-          const float d = ray_agent_exact(ox, oy, c, s, L, t.x, t.y, t.z, t.w);
-          if (d < best) { best = d; bidx = base + k; }
+      float s, c;
+      sincosf(linspace_elem(f_sub(g, a.span), f_add(g, a.span), a.n_rays, ray ? j : 0), &s, &c);
+      for (int64_t base = 0; base < ne; base += 32 * SM_U) {
+        float ex[SM_U], ey[SM_U], er[SM_U], ea[SM_U], qx[SM_U], qy[SM_U];
+#pragma unroll
+        for (int u = 0; u < SM_U; ++u) {
+          const int64_t e = base + u * 32 + lane;
+          const bool ok = e < ne;
+          const bool isf = !ok || e < a.nf;  // padding lanes read forager 0 (always present)
+          const int64_t k = ok ? (isf ? e : e - a.nf) : 0;
+          ex[u] = (isf ? a.fx : a.rx)[k];
+          ey[u] = (isf ? a.fy : a.ry)[k];
+          er[u] = (isf ? a.frad : a.rrad)[k];
+          ea[u] = (isf ? a.fact : a.ract)[k];
+          // column e of concat(forager-resource dists, forager-forager dists)
+          const bool pr = e < a.nr;
+          const int64_t kp = ok ? (pr ? e : e - a.nr) : 0;
+          qx[u] = (pr ? a.rx : a.fx)[kp];
+          qy[u] = (pr ? a.ry : a.fy)[kp];
+        }
+#pragma unroll
+        for (int u = 0; u < SM_U; ++u) {
+          const float pd = norm2(f_sub(qx[u], ox), f_sub(qy[u], oy));
+          const bool near = (base + u * 32 + lane < ne) && pd < f_add(L, er[u]);
+          unsigned m = __ballot_sync(0xffffffffu, near);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float tx = __shfl_sync(0xffffffffu, ex[u], src), ty = __shfl_sync(0xffffffffu, ey[u], src);
+            const float tr = __shfl_sync(0xffffffffu, er[u], src), ta = __shfl_sync(0xffffffffu, ea[u], src);
+            const float d = ray_agent_exact(ox, oy, c, s, L, tx, ty, tr, ta);
+            if (d < best) { best = d; bidx = base + u * 32 + src; }
+          }
+        }
+      }
+      if (ray) {
+        const float ex1 = f_add(ox, f_mul(c, L)), ey1 = f_add(oy, f_mul(s, L));
+        for (int64_t w = 0; w < a.nw; ++w) {
+          const float d = ray_wall_exact(ox, oy, ex1, ey1, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w]);
+          if (d < best) { best = d; bidx = ne + w; }
         }
       }
     }
-    __syncthreads();
-  }
-  if (act) {
-    const float qx = f_add(ox, f_mul(c, L)), qy = f_add(oy, f_mul(s, L));
-    for (int64_t w = 0; w < a.nw; ++w) {
-      const float d = ray_wall_exact(ox, oy, qx, qy, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w]);
-      if (d < best) { best = d; bidx = ne + w; }
+    if (ray) {
+      float en = 0.0f, ty = 0.0f;
+      if (act && bidx >= 0 && bidx < ne) {
+        const bool isf = bidx < a.nf;
+        const int64_t k = isf ? bidx : bidx - a.nf;
+        en = isf ? a.fen[k] : a.ren[k];
+        ty = (float)(isf ? a.ftype[k] : a.rtype[k]);
+      }
+      float* o = a.obs + f * (a.n_rays * 3) + j * 3;
+      o[0] = act ? en : 0.0f;
+      o[1] = act ? ty : 0.0f;
+      o[2] = act ? best : 0.0f;
     }
-  }
-  if (valid) {
-    float en = 0.0f, ty = 0.0f;
-    if (act && bidx >= 0 && bidx < ne) {
-      const bool isf = bidx < a.nf;
-      const int64_t k = isf ? bidx : bidx - a.nf;
-      en = isf ? a.fen[k] : a.ren[k];
-      ty = (float)(isf ? a.ftype[k] : a.rtype[k]);
-    }
-    float* o = a.obs + f * (a.n_rays * 3) + j * 3;
-    o[0] = act ? en : 0.0f;
-    o[1] = act ? ty : 0.0f;
-    o[2] = act ? best : 0.0f;
   }
 }
 
@@ -513,7 +537,7 @@ int fgx_forager_resource_interaction(int64_t n_foragers, const float* fx, const 
   if (n_foragers == 0) return FGX_OK;
   FGX_REQUIRE(fx && fy && energy_in, "fgx_forager_resource_interaction: null pointer");
   FGX_REQUIRE(n_resources == 0 || (rx && ry && rrad && renergy), "fgx_forager_resource_interaction: null pointer");
-  interaction_kernel<<<(int)ceil_div(n_foragers, 256), 256, 0, s>>>(n_foragers, fx, fy, n_resources, rx, ry, rrad,
+  interaction_kernel<<<(int)ceil_div(n_foragers, IA_WARPS), IA_WARPS * 32, 0, s>>>(n_foragers, fx, fy, n_resources, rx, ry, rrad,
                                                                    renergy, energy_in, energy_out);
   return check_launch("fgx_forager_resource_interaction");
 }
@@ -533,7 +557,7 @@ int fgx_sensor_model(int64_t n_foragers, const float* fx, const float* fy, const
   FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_sensor_model: null wall array");
   SensorArgs a{n_foragers, n_resources, n_walls, fx, fy, fang, frad, fenergy, factive, ftype, rx, ry, rrad, renergy,
                ractive, rtype, wx1, wy1, wx2, wy2, n_rays, ray_span, ray_length, obs};
-  sensor_model_kernel<<<(int)ceil_div(n_foragers * n_rays, 128), 128, 0, as_stream(stream)>>>(a);
+  sensor_model_kernel<<<(int)ceil_div(n_foragers, SM_WARPS), SM_WARPS * 32, 0, as_stream(stream)>>>(a);
   return check_launch("fgx_sensor_model");
 }
 }

@@ -22,7 +22,7 @@ constexpr int RS_BLOCK = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int SORT_SMALL_N = 4096;  // bitonic path: 4096 * 8 B = 32 KB static smem
+constexpr int SORT_SMALL_N = 16384;  // bitonic path: up to 16384 * 8 B = 128 KB dynamic smem
 constexpr int TV_ITEMS = 8;         // two-valued partition: 2048 slots per tile
 constexpr int TV_TILE = RS_BLOCK * TV_ITEMS;
 constexpr int TV_MAX_GRID = 4096;
@@ -372,24 +372,26 @@ __global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* __restr
 }
 
 // ---- small path: single CTA, bitonic sort of (image << 32 | index) ----------------------
+// The 64-bit composites are unique, so the (unstable) network yields the stable order.  Every thread
+// owns compare-exchange PAIRS (i, i + j) -- no idle half -- and n <= 16384 keeps the whole array in
+// shared memory (config C2's sorts are latency-bound: one launch instead of the 15 of the radix path).
 __global__ void __launch_bounds__(1024) sort_small_kernel(const void* __restrict__ keys, int dtype, int descending,
                                                           int n, int32_t* __restrict__ perm) {
-  __shared__ unsigned long long s[SORT_SMALL_N];
+  extern __shared__ unsigned long long s[];
   int m = 1;
   while (m < n) m <<= 1;
   for (int i = threadIdx.x; i < m; i += blockDim.x)
     s[i] = i < n ? (((unsigned long long)key_image(keys, dtype, descending, i) << 32) | (unsigned)i)
                  : 0xFFFFFFFFFFFFFFFFull;
   __syncthreads();
+  const int half = m >> 1;
   for (int k = 2; k <= m; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = s[i], b = s[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { s[i] = b; s[ixj] = a; }
-        }
+      for (int t = threadIdx.x; t < half; t += blockDim.x) {
+        const int i = 2 * t - (t & (j - 1));  // bit j of i is clear
+        const unsigned long long a = s[i], b = s[i + j];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { s[i] = b; s[i + j] = a; }
       }
       __syncthreads();
     }
@@ -425,7 +427,15 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   cudaStream_t s = as_stream(stream);
   const int desc = descending ? 1 : 0;
   if (n <= SORT_SMALL_N) {
-    sort_small_kernel<<<1, 1024, 0, s>>>(keys, key_dtype, desc, (int)n, perm);
+    size_t m = 1;
+    while ((int64_t)m < n) m <<= 1;
+    const size_t smem = m * sizeof(unsigned long long);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           SORT_SMALL_N * (int)sizeof(unsigned long long));
+      if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
+    }
+    sort_small_kernel<<<1, 1024, smem, s>>>(keys, key_dtype, desc, (int)n, perm);
     return check_launch("fgx_argsort(small)");
   }
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_argsort_scratch_bytes(n), "fgx_argsort: scratch too small");

@@ -98,7 +98,8 @@ def test_churn_ticks_match_oracle(cuda, n, n_active, sides, ticks):
         assert_same(s.agents, ref)
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2047, 2048, 2049, 16384, 16385, 100003, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 1024, 1025, 2047, 2048, 2049, 6000, 8193, 16384, 16385, 100003,
+                               1 << 20])
 @pytest.mark.parametrize("frac", [0.0, 0.3, 1.0])
 def test_select_partition(cuda, n, frac):
     import foragax_b200.base.agent_methods as fgx_methods
@@ -139,7 +140,7 @@ def test_select_fused_predicates(cuda):
         np.testing.assert_array_equal(perm.cpu().numpy(), rp)
 
 
-@pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 50000, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 6000, 16384, 16385, 50000, 1 << 20])
 @pytest.mark.parametrize("kind", ["flag", "float", "float_special", "int", "int_small", "const"])
 @pytest.mark.parametrize("ascend", [True, False])
 def test_argsort(cuda, n, kind, ascend):
