@@ -295,27 +295,29 @@ __global__ void __launch_bounds__(256)
 }
 
 // forager_resource_interaction (sim.py:358-375): energy_in[f] = sum_r e(f,r), energy_out[r] = sum_f e(f,r),
-// e(f,r) = energy_r if |f - r| < rad_r + 0.1 else 0.  One WARP per forager: lanes take 32 consecutive
-// resources (coalesced, IA_U independent groups in flight), hits are found by ballot and folded into the
-// forager's sum in ascending resource order (the order of a serial sum over r, kept so that the result
-// does not depend on the launch shape).  energy_out is accumulated with atomics: all addends of one
-// resource are equal, so that sum does not depend on the order either.
-constexpr int IA_WARPS = 8, IA_U = 4;
+// e(f,r) = energy_r if |f - r| < rad_r + 0.1 else 0.  One CTA per forager: threads take consecutive
+// resources (coalesced, IA_U independent loads in flight); the few hits go to a shared list that
+// warp 0 puts back into ascending resource order before folding, so energy_in is the serial sum
+// over r whatever the launch shape (a list overflow falls back to an ordered rescan).  energy_out is
+// accumulated with atomics: all addends of one resource are equal, so that sum is order-free too.
+constexpr int IA_BLOCK = 256, IA_U = 4, IA_CAP = 128;
 
-__global__ void __launch_bounds__(IA_WARPS * 32)
+__global__ void __launch_bounds__(IA_BLOCK)
     interaction_kernel(int64_t nf, const float* __restrict__ fx, const float* __restrict__ fy, int64_t nr,
                        const float* __restrict__ rx, const float* __restrict__ ry, const float* __restrict__ rrad,
                        const float* __restrict__ ren, float* __restrict__ energy_in, float* __restrict__ energy_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t f = blockIdx.x * (int64_t)IA_WARPS + (threadIdx.x >> 5);
-  if (f >= nf) return;
+  __shared__ int hit_idx[IA_CAP];
+  __shared__ float hit_val[IA_CAP], ordered[IA_CAP];
+  __shared__ int n_hits;
+  const int64_t f = blockIdx.x;
   const float px = fx[f], py = fy[f];
-  float acc = 0.0f;
-  for (int64_t base = 0; base < nr; base += 32 * IA_U) {
+  if (threadIdx.x == 0) n_hits = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nr; base += IA_BLOCK * IA_U) {
     float x[IA_U], y[IA_U], z[IA_U], w[IA_U];
 #pragma unroll
     for (int u = 0; u < IA_U; ++u) {
-      const int64_t r = base + u * 32 + lane;
+      const int64_t r = base + u * IA_BLOCK + threadIdx.x;
       const bool ok = r < nr;
       x[u] = ok ? rx[r] : 0.0f;
       y[u] = ok ? ry[r] : 0.0f;
@@ -325,14 +327,39 @@ __global__ void __launch_bounds__(IA_WARPS * 32)
 #pragma unroll
     for (int u = 0; u < IA_U; ++u) {
       const float d = norm2(f_sub(x[u], px), f_sub(y[u], py));
-      const bool hit = d < f_add(z[u], 0.1f);
-      unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (d < f_add(z[u], 0.1f)) {
+        const int64_t r = base + u * IA_BLOCK + threadIdx.x;
+        const int pos = atomicAdd(&n_hits, 1);
+        if (pos < IA_CAP) { hit_idx[pos] = (int)r; hit_val[pos] = w[u]; }
+        atomicAdd(energy_out + r, w[u]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int h = n_hits, lane = threadIdx.x;
+  float acc = 0.0f;
+  if (h <= IA_CAP) {
+    for (int e = lane; e < h; e += 32) {
+      int rank = 0;
+      for (int k = 0; k < h; ++k) rank += hit_idx[k] < hit_idx[e] ? 1 : 0;
+      ordered[rank] = hit_val[e];
+    }
+    __syncwarp();
+    if (lane == 0)
+      for (int k = 0; k < h; ++k) acc = f_add(acc, ordered[k]);
+  } else {  // more overlaps than the list holds: ordered rescan by one warp
+    for (int64_t base = 0; base < nr; base += 32) {
+      const int64_t r = base + lane;
+      const bool ok = r < nr;
+      const float d = ok ? norm2(f_sub(rx[r], px), f_sub(ry[r], py)) : 0.0f;
+      const float w = ok ? ren[r] : 0.0f;
+      unsigned m = __ballot_sync(0xffffffffu, ok && d < f_add(rrad[ok ? r : 0], 0.1f));
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        acc = f_add(acc, __shfl_sync(0xffffffffu, w[u], src));
+        acc = f_add(acc, __shfl_sync(0xffffffffu, w, src));
       }
-      if (hit) atomicAdd(energy_out + base + u * 32 + lane, w[u]);
     }
   }
   if (lane == 0) energy_in[f] = acc;
@@ -340,10 +367,11 @@ __global__ void __launch_bounds__(IA_WARPS * 32)
 
 // sensor_model (sim.py:388-468); entities = [foragers, resources, walls].  The reference prefilters
 // agent entity e with column e of a distance matrix ordered [resources, foragers] (sim.py:381,416,435)
-// -- reproduced: `partner` is that other agent.  One WARP per forager: the prefilter does not depend on
-// the ray, so the broad phase runs with lanes = entities (ballot of |partner - forager| < L + rad) and
-// only the survivors reach the narrow phase, lanes = rays, in ascending entity order (strict <: the
-// first minimum wins, as argmin does).
+// -- reproduced: `partner` is that other agent.  One CTA per forager: the prefilter does not depend on
+// the ray, so the broad phase runs with lanes = entities (ballot of |partner - forager| < L + rad), the
+// CTA's warps interleaving blocks of entities, and only the survivors reach the narrow phase, lanes =
+// rays.  argmin keeps the first minimum: strict < inside a warp (ascending entities), then a merge of
+// the warps' (distance, entity) pairs that prefers the lower entity on ties.
 struct SensorArgs {
   int64_t nf, nr, nw;
   const float *fx, *fy, *fang, *frad, *fen, *fact;
@@ -356,24 +384,24 @@ struct SensorArgs {
   float* obs;  // [nf, n_rays*3]
 };
 
-constexpr int SM_WARPS = 4, SM_U = 4;
+constexpr int SM_WARPS = 8, SM_U = 4;
 
 __global__ void __launch_bounds__(SM_WARPS * 32) sensor_model_kernel(const SensorArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t f = blockIdx.x * (int64_t)SM_WARPS + (threadIdx.x >> 5);
-  if (f >= a.nf) return;
+  __shared__ float sbest[SM_WARPS][32];
+  __shared__ long long sidx[SM_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t f = blockIdx.x;  // one CTA per forager; its warps interleave blocks of 32*SM_U entities
   const bool act = a.fact[f] != 0.0f;
   const float ox = a.fx[f], oy = a.fy[f], L = a.L, g = a.fang[f];
   const int64_t ne = a.nf + a.nr;
   for (int j0 = 0; j0 < a.n_rays; j0 += 32) {  // one pass for up to 32 rays
     const int j = j0 + lane;
     const bool ray = j < a.n_rays;
-    float best = L;
+    float best = L, s = 0.0f, c = 1.0f;
     int64_t bidx = -1;
     if (act) {
-      float s, c;
       sincosf(linspace_elem(f_sub(g, a.span), f_add(g, a.span), a.n_rays, ray ? j : 0), &s, &c);
-      for (int64_t base = 0; base < ne; base += 32 * SM_U) {
+      for (int64_t base = (int64_t)warp * (32 * SM_U); base < ne; base += (int64_t)SM_WARPS * 32 * SM_U) {
         float ex[SM_U], ey[SM_U], er[SM_U], ea[SM_U], qx[SM_U], qy[SM_U];
 #pragma unroll
         for (int u = 0; u < SM_U; ++u) {
@@ -406,15 +434,24 @@ __global__ void __launch_bounds__(SM_WARPS * 32) sensor_model_kernel(const Senso
           }
         }
       }
-      if (ray) {
+    }
+    sbest[warp][lane] = best;
+    sidx[warp][lane] = bidx;
+    __syncthreads();
+    if (warp == 0 && ray) {
+      // the serial scan keeps the LOWEST entity among equal minima: merge on (distance, index)
+      for (int w = 1; w < SM_WARPS; ++w) {
+        const float d = sbest[w][lane];
+        const int64_t i = sidx[w][lane];
+        if (d < best || (d == best && i >= 0 && i < bidx)) { best = d; bidx = i; }
+      }
+      if (act) {
         const float ex1 = f_add(ox, f_mul(c, L)), ey1 = f_add(oy, f_mul(s, L));
         for (int64_t w = 0; w < a.nw; ++w) {
           const float d = ray_wall_exact(ox, oy, ex1, ey1, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w]);
           if (d < best) { best = d; bidx = ne + w; }
         }
       }
-    }
-    if (ray) {
       float en = 0.0f, ty = 0.0f;
       if (act && bidx >= 0 && bidx < ne) {
         const bool isf = bidx < a.nf;
@@ -427,6 +464,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) sensor_model_kernel(const Senso
       o[1] = act ? ty : 0.0f;
       o[2] = act ? best : 0.0f;
     }
+    __syncthreads();
   }
 }
 
@@ -527,7 +565,8 @@ int fgx_forager_resource_interaction(int64_t n_foragers, const float* fx, const 
                                      const float* rx, const float* ry, const float* rrad, const float* renergy,
                                      float* energy_in, float* energy_out, fgx_stream_t stream) {
   using namespace fgx;
-  FGX_REQUIRE(n_foragers >= 0 && n_resources >= 0, "fgx_forager_resource_interaction: bad sizes");
+  FGX_REQUIRE(n_foragers >= 0 && n_foragers < (1ll << 31) && n_resources >= 0 && n_resources < (1ll << 31),
+              "fgx_forager_resource_interaction: bad sizes");
   cudaStream_t s = as_stream(stream);
   if (n_resources > 0) {
     FGX_REQUIRE(energy_out, "fgx_forager_resource_interaction: null energy_out");
@@ -537,7 +576,7 @@ int fgx_forager_resource_interaction(int64_t n_foragers, const float* fx, const 
   if (n_foragers == 0) return FGX_OK;
   FGX_REQUIRE(fx && fy && energy_in, "fgx_forager_resource_interaction: null pointer");
   FGX_REQUIRE(n_resources == 0 || (rx && ry && rrad && renergy), "fgx_forager_resource_interaction: null pointer");
-  interaction_kernel<<<(int)ceil_div(n_foragers, IA_WARPS), IA_WARPS * 32, 0, s>>>(n_foragers, fx, fy, n_resources, rx, ry, rrad,
+  interaction_kernel<<<(unsigned)n_foragers, IA_BLOCK, 0, s>>>(n_foragers, fx, fy, n_resources, rx, ry, rrad,
                                                                    renergy, energy_in, energy_out);
   return check_launch("fgx_forager_resource_interaction");
 }
@@ -549,7 +588,8 @@ int fgx_sensor_model(int64_t n_foragers, const float* fx, const float* fy, const
                      const float* wy2, int32_t n_rays, float ray_span, float ray_length, float* obs,
                      fgx_stream_t stream) {
   using namespace fgx;
-  FGX_REQUIRE(n_foragers >= 0 && n_resources >= 0 && n_walls >= 0 && n_rays > 0, "fgx_sensor_model: bad sizes");
+  FGX_REQUIRE(n_foragers >= 0 && n_foragers < (1ll << 31) && n_resources >= 0 && n_walls >= 0 && n_rays > 0,
+              "fgx_sensor_model: bad sizes");
   if (n_foragers == 0) return FGX_OK;
   FGX_REQUIRE(fx && fy && fang && frad && fenergy && factive && ftype && obs, "fgx_sensor_model: null forager leaf");
   FGX_REQUIRE(n_resources == 0 || (rx && ry && rrad && renergy && ractive && rtype),
@@ -557,7 +597,7 @@ int fgx_sensor_model(int64_t n_foragers, const float* fx, const float* fy, const
   FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_sensor_model: null wall array");
   SensorArgs a{n_foragers, n_resources, n_walls, fx, fy, fang, frad, fenergy, factive, ftype, rx, ry, rrad, renergy,
                ractive, rtype, wx1, wy1, wx2, wy2, n_rays, ray_span, ray_length, obs};
-  sensor_model_kernel<<<(int)ceil_div(n_foragers, SM_WARPS), SM_WARPS * 32, 0, as_stream(stream)>>>(a);
+  sensor_model_kernel<<<(unsigned)n_foragers, SM_WARPS * 32, 0, as_stream(stream)>>>(a);
   return check_launch("fgx_sensor_model");
 }
 }

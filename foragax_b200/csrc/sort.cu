@@ -12,8 +12,8 @@
 //      prep (images + 4 digit histograms), plan (digit bases, trivial passes),
 //      per pass: tile histogram -> per-digit scan over tiles -> stable scatter with
 //      warp match/ballot ranking; finish copies to the caller's perm if needed.
-// Small inputs take a single-CTA bitonic sort of the 64-bit (image, index)
-// composite (unique, hence stable) in shared memory: one launch.
+// Small inputs order the unique 64-bit (image, index) composite (hence stable): n <= 256 by a
+// single-CTA bitonic network in shared memory, n <= 16384 by an all-pairs rank sort over every SM.
 #include "common.cuh"
 
 namespace fgx {
@@ -22,7 +22,7 @@ constexpr int RS_BLOCK = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int SORT_SMALL_N = 16384;  // bitonic path: up to 16384 * 8 B = 128 KB dynamic smem
+constexpr int SORT_SMALL_N = 256;  // bitonic path (needs no scratch): 256 * 8 B = 2 KB static smem
 constexpr int TV_ITEMS = 8;         // two-valued partition: 2048 slots per tile
 constexpr int TV_TILE = RS_BLOCK * TV_ITEMS;
 constexpr int TV_MAX_GRID = 4096;
@@ -371,13 +371,13 @@ __global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* __restr
     perm[i] = iota ? (int32_t)i : idx1[i];
 }
 
-// ---- small path: single CTA, bitonic sort of (image << 32 | index) ----------------------
-// The 64-bit composites are unique, so the (unstable) network yields the stable order.  Every thread
-// owns compare-exchange PAIRS (i, i + j) -- no idle half -- and n <= 16384 keeps the whole array in
-// shared memory (config C2's sorts are latency-bound: one launch instead of the 15 of the radix path).
-__global__ void __launch_bounds__(1024) sort_small_kernel(const void* __restrict__ keys, int dtype, int descending,
-                                                          int n, int32_t* __restrict__ perm) {
-  extern __shared__ unsigned long long s[];
+// ---- small paths (latency-bound sizes: one or two graph nodes instead of the 15 of the radix path) ----
+// n <= 256: single CTA, bitonic sort of the 64-bit composite (image << 32 | index) in shared memory.
+// The composites are unique, so the (unstable) network yields the stable order; every thread owns a
+// compare-exchange PAIR (i, i + j).
+__global__ void __launch_bounds__(128) sort_small_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                         int n, int32_t* __restrict__ perm) {
+  __shared__ unsigned long long s[SORT_SMALL_N];
   int m = 1;
   while (m < n) m <<= 1;
   for (int i = threadIdx.x; i < m; i += blockDim.x)
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(1024) sort_small_kernel(const void* __restrict
   const int half = m >> 1;
   for (int k = 2; k <= m; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < half; t += blockDim.x) {
+      const int t = threadIdx.x;
+      if (t < half) {
         const int i = 2 * t - (t & (j - 1));  // bit j of i is clear
         const unsigned long long a = s[i], b = s[i + j];
         const bool up = (i & k) == 0;
@@ -397,6 +398,60 @@ __global__ void __launch_bounds__(1024) sort_small_kernel(const void* __restrict
     }
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = (int32_t)(s[i] & 0xFFFFFFFFull);
+}
+
+// 256 < n <= 16384: all-pairs RANK sort over the whole GPU.  rank(i) = #{j : composite_j < composite_i}
+// is the final position of slot i (the composites are unique), so n^2 64-bit compares -- a few
+// microseconds of integer work spread over every SM -- replace log^2 n dependent shared-memory steps
+// on one SM.  grid = (i-tiles of 1024 slots) x (j-splits); partial ranks are added atomically and the
+// LAST CTA of an i-tile to arrive (ticket counter, no waiting) writes perm[rank[i]] = i.
+constexpr int RK_BLOCK = 256, RK_IPT = 4, RK_ITILE = RK_BLOCK * RK_IPT, RK_JMAX = 2048;
+constexpr int SORT_RANK_N = 16384;
+
+__global__ void __launch_bounds__(RK_BLOCK) sort_rank_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                             int n, int jchunk, int32_t* __restrict__ rank,
+                                                             int32_t* __restrict__ tickets,
+                                                             int32_t* __restrict__ perm) {
+  __shared__ __align__(16) unsigned long long sj[RK_JMAX];
+  __shared__ int last;
+  const int j0 = blockIdx.y * jchunk, cnt = min(n, j0 + jchunk) - j0, padded = (cnt + 7) & ~7;
+  for (int k = threadIdx.x; k < padded; k += RK_BLOCK)  // padding compares greater than every slot
+    sj[k] = k < cnt ? (((unsigned long long)key_image(keys, dtype, descending, j0 + k) << 32) | (unsigned)(j0 + k))
+                    : 0xFFFFFFFFFFFFFFFFull;
+  unsigned long long ci[RK_IPT];
+  int c[RK_IPT];
+#pragma unroll
+  for (int q = 0; q < RK_IPT; ++q) {
+    const int i = blockIdx.x * RK_ITILE + q * RK_BLOCK + threadIdx.x;
+    ci[q] = i < n ? (((unsigned long long)key_image(keys, dtype, descending, i) << 32) | (unsigned)i) : 0ull;
+    c[q] = 0;
+  }
+  __syncthreads();
+  for (int k = 0; k < padded; k += 8) {
+    ulonglong2 v[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) v[h] = *reinterpret_cast<const ulonglong2*>(&sj[k + 2 * h]);  // broadcast reads
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+      for (int q = 0; q < RK_IPT; ++q) c[q] += (v[h].x < ci[q] ? 1 : 0) + (v[h].y < ci[q] ? 1 : 0);
+  }
+#pragma unroll
+  for (int q = 0; q < RK_IPT; ++q) {
+    const int i = blockIdx.x * RK_ITILE + q * RK_BLOCK + threadIdx.x;
+    if (i < n && c[q]) atomicAdd(&rank[i], c[q]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&tickets[blockIdx.x], 1) == (int)gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < RK_IPT; ++q) {
+    const int i = blockIdx.x * RK_ITILE + q * RK_BLOCK + threadIdx.x;
+    if (i < n) perm[__ldcg(&rank[i])] = i;
+  }
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -427,19 +482,26 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   cudaStream_t s = as_stream(stream);
   const int desc = descending ? 1 : 0;
   if (n <= SORT_SMALL_N) {
-    size_t m = 1;
-    while ((int64_t)m < n) m <<= 1;
-    const size_t smem = m * sizeof(unsigned long long);
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           SORT_SMALL_N * (int)sizeof(unsigned long long));
-      if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
-    }
-    sort_small_kernel<<<1, 1024, smem, s>>>(keys, key_dtype, desc, (int)n, perm);
+    sort_small_kernel<<<1, 128, 0, s>>>(keys, key_dtype, desc, (int)n, perm);
     return check_launch("fgx_argsort(small)");
   }
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_argsort_scratch_bytes(n), "fgx_argsort: scratch too small");
   FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "fgx_argsort: scratch must be 256-byte aligned");
+  if (n <= SORT_RANK_N) {
+    const int itiles = (int)ceil_div(n, RK_ITILE);
+    int64_t js = ceil_div((int64_t)2 * sm_count(), itiles);
+    if (js > ceil_div(n, 64)) js = ceil_div(n, 64);
+    int jchunk = (int)ceil_div(n, js);
+    jchunk = (jchunk + 7) & ~7;
+    if (jchunk > RK_JMAX) jchunk = RK_JMAX;
+    js = ceil_div(n, jchunk);
+    int32_t* rank = reinterpret_cast<int32_t*>(scratch);  // rank[n] then one ticket per i-tile
+    cudaError_t e = cudaMemsetAsync(rank, 0, sizeof(int32_t) * (size_t)(n + itiles), s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
+    sort_rank_kernel<<<dim3(itiles, (unsigned)js), RK_BLOCK, 0, s>>>(keys, key_dtype, desc, (int)n, jchunk, rank,
+                                                                    rank + n, perm);
+    return check_launch("fgx_argsort(rank)");
+  }
   const int64_t tiles = ceil_div(n, RS_TILE);
   char* p = reinterpret_cast<char*>(scratch);
   SortState* st = reinterpret_cast<SortState*>(p);

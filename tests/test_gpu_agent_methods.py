@@ -140,7 +140,7 @@ def test_select_fused_predicates(cuda):
         np.testing.assert_array_equal(perm.cpu().numpy(), rp)
 
 
-@pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 6000, 16384, 16385, 50000, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 100, 256, 257, 1000, 1025, 4096, 6000, 16384, 16385, 50000, 1 << 20])
 @pytest.mark.parametrize("kind", ["flag", "float", "float_special", "int", "int_small", "const"])
 @pytest.mark.parametrize("ascend", [True, False])
 def test_argsort(cuda, n, kind, ascend):
