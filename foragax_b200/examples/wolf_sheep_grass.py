@@ -226,6 +226,27 @@ class Ecosystem:
                                                                                 self.wolves.num_total_agents, self.key)
         return num_active_sheeps, num_active_wolves
 
+    def capture(self, warmup=2):
+        """One whole tick as a CUDA graph (``foragax_b200.graphs.GraphedTick``): ``warmup`` real ticks run
+        first; every ``replay()`` is one tick and returns the static ``(num_active_sheeps, num_active_wolves)``."""
+        from ..graphs import GraphedTick
+        state = {'grass': self.grasses.agents, 'sheep': self.sheeps.agents, 'wolves': self.wolves.agents,
+                 'key': self.key}
+
+        def bind(st):
+            self.grasses.agents, self.sheeps.agents, self.wolves.agents = st['grass'], st['sheep'], st['wolves']
+            self.key = st['key']
+
+        def tick(st):
+            bind(st)
+            out = self.step()
+            return {'grass': self.grasses.agents, 'sheep': self.sheeps.agents, 'wolves': self.wolves.agents,
+                    'key': self.key}, out
+
+        g = GraphedTick(tick, state, warmup)
+        bind(state)
+        return g
+
     def run(self):
         num_sheep, num_wolf = [], []
         for _ in range(self.sim_steps):

@@ -83,3 +83,26 @@ def test_interaction_matches_equality_matrices(cuda):
     for a, b in zip(got, ref):
         np.testing.assert_array_equal(a.cpu().numpy(), b)
     assert ref[0].max() > 3 and ref[2].sum() > 100
+
+
+def test_cuda_graph_replay_equals_eager_ticks(cuda):
+    """The whole Ecosystem tick captured once and replayed (Ecosystem.capture) stays on the oracle's
+    trajectory: counts every tick, full state at the end."""
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples.wolf_sheep_grass import Ecosystem
+    cfg = dict(X_max=60, Y_max=45, max_animals=6000, init_sheeps=2500, init_wolves=800)
+    eco = Ecosystem(grass_regrowth_time=30, wolf_reproduction_rate=0.08, wolf_energy=30, init_wolves=cfg["init_wolves"],
+                    sheep_reproduction_rate=0.2, sheep_energy=5, init_sheeps=cfg["init_sheeps"], X_max=cfg["X_max"],
+                    Y_max=cfg["Y_max"], sim_steps=30, key=fgx_random.PRNGKey(0), max_animals=cfg["max_animals"])
+    ref = ows.Ecosystem(init_wolves=cfg["init_wolves"], init_sheeps=cfg["init_sheeps"], X_max=cfg["X_max"],
+                        Y_max=cfg["Y_max"], max_animals=cfg["max_animals"])
+    g = eco.capture(warmup=2)
+    for _ in range(2):
+        ref.step()
+    for t in range(2, 30):
+        ns, nw = g.replay()
+        rs, rw = ref.step()
+        assert (int(ns), int(nw)) == (rs, rw), f"tick {t}"
+    assert_equal_tree(np_animal(eco.sheeps.agents), ref.sheeps)
+    assert_equal_tree(np_animal(eco.wolves.agents), ref.wolves)
+    assert_equal_tree(np_grass(eco.grasses.agents), ref.grasses)
