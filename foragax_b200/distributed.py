@@ -11,7 +11,13 @@ replicated.  Ray-wall sensing and the fused step need no exchange; the two excha
   prefix sum places each rank's locally compacted (selected / unselected) slot lists inside the
   global stable partition that ``select_agents`` returns on one GPU.
 
-Nothing here touches agent payload; the collectives move 16 B/agent and 4 B/rank.
+Those two move 16 B/agent and 4 B/rank.  The third exchange moves agent rows:
+
+* :func:`global_pack_active` -- ``sort_agents(active_state, descending)`` over the WHOLE sharded set:
+  every rank packs its actives locally, the active counts are all-gathered, and one all-to-all per leaf
+  sends each row to the rank that owns its slot of the global stable order (all actives in slot order,
+  then all inactives), so that ``add_agents``' "actives are packed at the front" precondition
+  (agent_methods.py:26-38) holds globally.
 """
 import torch
 import torch.distributed as dist
@@ -97,3 +103,75 @@ def all_gather_positions(x, y, rad, active):
     out = torch.empty((w * m, 4), dtype=torch.float32, device=local.device)
     dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[i * m: i * m + int(c)] for i, c in enumerate(counts)], dim=0)
+
+
+def plan_pack_splits(active_counts, shard_sizes):
+    """Integer plan of :func:`global_pack_active` (pure host logic).
+
+    Rank s holds ``[a_s actives, n_s - a_s inactives]`` after its local stable partition.  In the global
+    stable order its actives occupy positions ``[A_s, A_s + a_s)`` (``A`` = exclusive prefix of the active
+    counts) and its inactives ``[A_tot + I_s, ...)``; rank d owns positions ``[B_d, B_{d+1})`` (``B`` = prefix
+    of the shard sizes).  Returns ``splits[s][d]`` = rows rank s sends to rank d.  The rows for one
+    destination are contiguous in the sender's packed buffer (only the LAST active piece and the FIRST
+    inactive piece can share a destination, and they are adjacent), so the packed leaves are the send
+    buffers as they are."""
+    w = len(shard_sizes)
+    a = [int(v) for v in active_counts]
+    n = [int(v) for v in shard_sizes]
+    bounds = [0]
+    for v in n:
+        bounds.append(bounds[-1] + v)
+    a_tot = sum(a)
+
+    def overlap(lo, hi, d):
+        return max(0, min(hi, bounds[d + 1]) - max(lo, bounds[d]))
+
+    splits = []
+    a_before = i_before = 0
+    for s_rank in range(w):
+        act = (a_before, a_before + a[s_rank])
+        ina = (a_tot + i_before, a_tot + i_before + n[s_rank] - a[s_rank])
+        splits.append([overlap(*act, d) + overlap(*ina, d) for d in range(w)])
+        a_before += a[s_rank]
+        i_before += n[s_rank] - a[s_rank]
+    return splits
+
+
+def global_pack_active(agents, sort_active, n_active_local=None):
+    """``sort_agents(quantity=active_state, ascend=False)`` of a set sharded in contiguous blocks: returns
+    this rank's block of the globally sorted set (bit-identical to slicing the single-GPU result).
+
+    ``sort_active(agents) -> agents`` is the LOCAL stable "actives first" partition (on the GPU path:
+    ``lambda a: jit_sort_agents(a.active_state, False, a)[0]``, i.e. the native two-valued argsort + row
+    gather).  Leaves whose leading dimension is the shard size are exchanged; everything else is
+    replicated state and left alone.  The split sizes have to be host integers for the collective, so
+    this is the one place the counts are read back (one int64 per rank)."""
+    from . import struct
+    r, w = world()
+    n_local = agents.active_state.shape[0]
+    agents = sort_active(agents)
+    if w == 1:
+        return agents
+    if n_active_local is None:
+        n_active_local = (agents.active_state != 0).sum()
+    a = all_gather_counts(torch.as_tensor(n_active_local, device=agents.active_state.device)).tolist()
+    n = all_gather_counts(torch.as_tensor(n_local, device=agents.active_state.device)).tolist()
+    splits = plan_pack_splits(a, n)
+    send = splits[r]
+    recv = [splits[s_rank][r] for s_rank in range(w)]
+    assert sum(recv) == n_local and sum(send) == n_local
+
+    def exchange(leaf):
+        if not isinstance(leaf, torch.Tensor) or leaf.dim() == 0 or leaf.shape[0] != n_local:
+            return leaf
+        src = leaf.contiguous()
+        row = 1
+        for d in src.shape[1:]:
+            row *= int(d)
+        # rows as raw bytes: one code path for every dtype (gloo / nccl lack bool and the unsigned types)
+        flat = src.reshape(n_local, row).view(torch.uint8)
+        out = torch.empty_like(flat)
+        dist.all_to_all_single(out, flat, recv, send)
+        return out.view(src.dtype).reshape(src.shape)
+
+    return sort_active(struct.tree_map(exchange, agents))

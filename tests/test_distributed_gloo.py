@@ -79,3 +79,80 @@ def test_shard_bounds_cover_range():
             b = [shard_bounds(n, w, r) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+# ---- global_pack_active: sort(active_state, descending) over a sharded set -----------------------------
+def _torch_sort_active(agents):
+    """Test stand-in for the native local sort: stable 'actives first' partition + row gather."""
+    from foragax_b200 import struct
+    ids = torch.from_numpy(np.argsort(-agents.active_state.numpy(), kind="stable"))
+    n = agents.active_state.shape[0]
+    return struct.tree_map(lambda x: x[ids] if x.dim() and x.shape[0] == n else x, agents)
+
+
+def _make_set(n, seed):
+    from foragax_b200.base.agent_classes import Agent, State
+    rng = np.random.default_rng(seed)
+    active = (rng.random(n) < 0.55).astype(np.float32)
+    return Agent(params=None, unique_id=torch.arange(n, dtype=torch.int32), agent_type=torch.zeros(n, dtype=torch.int32),
+                 active_state=torch.from_numpy(active), age=torch.from_numpy(rng.random(n).astype(np.float32)),
+                 state=State(content={'w': torch.from_numpy(rng.random((n, 3)).astype(np.float32)),
+                                      'flag': torch.from_numpy(rng.random(n) < 0.5),
+                                      'key': torch.from_numpy(rng.integers(0, 2**32, (n, 2), dtype=np.uint32))}),
+                 policy=None)
+
+
+def _pack_worker(rank, world, port, n, seed, sizes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import struct
+    full = _make_set(n, seed)
+    lo, hi = sum(sizes[:rank]), sum(sizes[:rank + 1])
+    mine = struct.tree_map(lambda x: x[lo:hi].clone(), full)
+    out = fd.global_pack_active(mine, _torch_sort_active)
+    q.put((rank, [x.numpy() for x in struct.tree_leaves(out)]))
+    dist.destroy_process_group()
+
+
+def _run_pack(world, n, seed, sizes):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pack_worker, args=(r, world, port, n, seed, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(out, key=lambda t: t[0])
+
+
+def test_global_pack_active_equals_single_process_sort():
+    """2 ranks (even shards) and 3 ranks (ragged shards, one of them with no active row to keep): every rank
+    ends up with exactly its block of the single-process sort_agents(active_state, descending)."""
+    from foragax_b200 import struct
+    for world, n, sizes in ((2, 1000, [500, 500]), (3, 611, [300, 11, 300])):
+        seed = 7 + world
+        ref = _torch_sort_active(_make_set(n, seed))
+        ref_leaves = [x.numpy() for x in struct.tree_leaves(ref)]
+        res = _run_pack(world, n, seed, sizes)
+        for rank, leaves in res:
+            lo, hi = sum(sizes[:rank]), sum(sizes[:rank + 1])
+            assert len(leaves) == len(ref_leaves)
+            for got, want in zip(leaves, ref_leaves):
+                np.testing.assert_array_equal(got, want[lo:hi])
+
+
+def test_plan_pack_splits_is_a_bijection():
+    from foragax_b200.distributed import plan_pack_splits
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        w = int(rng.integers(1, 9))
+        n = [int(v) for v in rng.integers(0, 50, w)]
+        a = [int(rng.integers(0, v + 1)) for v in n]
+        sp = plan_pack_splits(a, n)
+        assert [sum(row) for row in sp] == n                          # every rank sends all its rows
+        assert [sum(sp[s][d] for s in range(w)) for d in range(w)] == n  # and receives a full shard
