@@ -24,13 +24,18 @@
 namespace fgx {
 
 constexpr int RA_BLOCK = 256;
-constexpr int RA_WARPS = RA_BLOCK / 32;  // agents per CTA task
+constexpr int RA_WARPS = RA_BLOCK / 32;  // agents per CTA (one warp each)
+constexpr int RA_G = 4;                  // ray groups per warp
+constexpr int RA_GW = 32 / RA_G;         // lanes per group
 constexpr int RA_MAXRB = 4;              // rays per lane (n_rays <= 128)
-constexpr int RA_CHUNK = 512;  // targets staged per shared-memory chunk
+constexpr int RA_CAP = 64;               // survivor list entries per (warp, group)
+constexpr int RA_MINB = 4;                // CTAs per SM the register budget is held to
+constexpr int RA_SUB = 3;                // cells per (ray_length + max_rad): search radius K = RA_SUB cells
 
 struct GridDesc {
   float x0, y0, inv_cs;
   int gx, gy;
+  int K;  // neighbourhood radius in cells: K * cell >= ray_length + max_rad
 };
 
 __device__ __forceinline__ int cell_coord(float v, float v0, float inv_cs, int g) {
@@ -137,10 +142,10 @@ struct RaycastAgentsArgs {
   GridDesc g;
   const float *ax, *ay, *aang, *aactive;  // sensing agents [n]
   int64_t n, m;
-  int n_rays, groups;
-  float span, L;
-  const uint32_t *tstart, *astart, *bstart;
-  const int32_t* order;
+  int n_rays;
+  float span, L, max_rad;
+  const uint32_t* tstart;
+  const int32_t *order, *acell;
   const float4* targets;
   const int32_t* tidx;
   int merge_walls;
@@ -148,119 +153,210 @@ struct RaycastAgentsArgs {
   int32_t* hit;
 };
 
-template <int RB>
-__global__ void __launch_bounds__(RA_BLOCK) raycast_agents_kernel(const RaycastAgentsArgs a) {
-  __shared__ float4 st[RA_CHUNK];
-  __shared__ int32_t si[RA_CHUNK];
-  const int n_cells = a.g.gx * a.g.gy;
-  const uint32_t total_tasks = a.bstart[n_cells];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// rays <-> lanes: the warp's lanes form RA_G groups of RA_GW lanes; group g owns the contiguous rays
+// [g*RG, (g+1)*RG), RG = ceil(n_rays / RA_G), lane w of the group the rays g*RG + w + RA_GW*q
+__device__ __forceinline__ int ray_of(int g, int w, int q, int RG) { return g * RG + q * RA_GW + w; }
+
+// max over the rectangle [x0,x1] x [y0,y1] of the linear form cx*x + cy*y
+__device__ __forceinline__ float rect_max(float cx, float cy, float x0, float x1, float y0, float y1) {
+  return cx * (cx > 0.0f ? x1 : x0) + cy * (cy > 0.0f ? y1 : y0);
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const RaycastAgentsArgs a) {
+  // per warp and ray group: survivors of the broad phase as (sx, sy, c, target index); the odd row
+  // stride keeps the four groups' concurrent 16-byte reads on different banks
+  __shared__ float4 lists[RA_WARPS][RA_G][RA_CAP + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / RA_GW, w = lane % RA_GW;
+  const unsigned lt = lanemask_lt();
+  float4(*mine)[RA_CAP + 3] = lists[warp];
+  const int RG = (a.n_rays + RA_G - 1) / RA_G;
   const float L = a.L;
   // far-target bound: a hit needs |s| <= L + r, i.e. c = |s|^2 - r^2 <= L^2 + 2 L r
   const float L2 = f_mul(L, L), twoL = f_mul(2.0f, L);
-  // fan cull (only for a convex fan): a circle farther than r from the cone of half-angle `span`
-  // around the heading cannot be hit by any ray of the fan
-  const bool fan_cull = a.span < 1.5f;
-  float cs_span = 1.0f, sn_span = 0.0f;
-  if (fan_cull) sincosf(a.span, &sn_span, &cs_span);
-  for (uint32_t task = blockIdx.x; task < total_tasks; task += gridDim.x) {
-    int lo = 0, hi = n_cells;  // cell of this task: last c with bstart[c] <= task
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (a.bstart[mid] <= task) lo = mid; else hi = mid;
+  const float reach = (L + a.max_rad) * 1.0001f, reach2 = reach * reach;
+  const bool fan_convex = a.span < 1.5f;  // the whole fan is a convex cone: cells can be culled against it
+  const float cs = 1.0f / a.g.inv_cs, cell_margin = 1e-3f * cs + 1e-3f;
+  const int K = a.g.K;
+  const int64_t n_warps = (int64_t)gridDim.x * RA_WARPS;
+  for (int64_t i = blockIdx.x * (int64_t)RA_WARPS + warp; i < a.n; i += n_warps) {
+    const int64_t agent = a.order[i];
+    if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {  // inactive sensor: zeros, as the reference's cond
+      for (int r = lane; r < a.n_rays; r += 32) {
+        a.dist[agent * a.n_rays + r] = 0.0f;
+        a.hit[agent * a.n_rays + r] = -1;
+      }
+      continue;
     }
-    const int cell = lo;
-    const uint32_t slot = (task - a.bstart[cell]) * RA_WARPS + warp;
-    const uint32_t a0 = a.astart[cell], a1 = a.astart[cell + 1];
-    const bool valid = a0 + slot < a1;                     // warp-uniform
-    const int64_t agent = valid ? a.order[a0 + slot] : 0;
-    const bool act = valid && (a.aactive == nullptr || a.aactive[agent] != 0.0f);
-    const float ox = valid ? a.ax[agent] : 0.0f, oy = valid ? a.ay[agent] : 0.0f;
-    const float ang = valid ? a.aang[agent] : 0.0f;
-    float hu, hv;  // heading
-    sincosf(ang, &hv, &hu);
-    float dx[RB], dy[RB], best[RB];
-    int bidx[RB];
+    const int cell = a.acell[agent];
+    const float ox = a.ax[agent], oy = a.ay[agent], ang = a.aang[agent];
+    float dx[RPL], dy[RPL], best[RPL], kb[RPL];
+    int bidx[RPL];
     {
       const float lo_a = f_sub(ang, a.span), hi_a = f_add(ang, a.span);
 #pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        sincosf(linspace_elem(lo_a, hi_a, a.n_rays, min(lane + 32 * q, a.n_rays - 1)), &dy[q], &dx[q]);
+      for (int q = 0; q < RPL; ++q) {
+        const int r = ray_of(g, w, q, RG);
+        const bool ok = q * RA_GW + w < RG && r < a.n_rays;
+        sincosf(linspace_elem(lo_a, hi_a, a.n_rays, ok ? r : 0), &dy[q], &dx[q]);
         best[q] = L;
+        kb[q] = L * 1.00001f;
         bidx[q] = -1;
       }
     }
-    const int cx = cell % a.g.gx, cy = cell / a.g.gx;
-    for (int ry = max(cy - 1, 0); ry <= min(cy + 1, a.g.gy - 1); ++ry) {
-      const int c_lo = ry * a.g.gx + max(cx - 1, 0), c_hi = ry * a.g.gx + min(cx + 1, a.g.gx - 1);
-      const uint32_t r0 = a.tstart[c_lo], r1 = a.tstart[c_hi + 1];  // the row's cells are contiguous
-      for (uint32_t base = r0; base < r1; base += RA_CHUNK) {
-        const int cnt = (int)min((uint32_t)RA_CHUNK, r1 - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < cnt; k += RA_BLOCK) {
-          st[k] = a.targets[base + k];
-          si[k] = a.tidx[base + k];
-        }
-        __syncthreads();
-        if (!act) continue;
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-          // broad phase: lane <-> target
-          const int k = k0 + lane;
-          const float4 t = st[min(k, cnt - 1)];
-          const float sx = f_sub(ox, t.x), sy = f_sub(oy, t.y);
-          const float c = f_sub(f_add(f_mul(sx, sx), f_mul(sy, sy)), f_mul(t.z, t.z));
-          bool pass = k < cnt && t.w != 0.0f && !(c > f_mul(f_add(L2, f_mul(twoL, t.z)), 1.0001f));
-          if (fan_cull) {
-            // v = c - o = -s in the heading frame: along = v.h, across = |v x h|
-            const float along = -(sx * hu + sy * hv), across = fabsf(sx * hv - sy * hu);
-            const float outside = across * cs_span - along * sn_span;  // distance to the fan's boundary line
-            pass = pass && !(outside > t.z * 1.0001f + 1e-4f * (fabsf(sx) + fabsf(sy)) + 1e-6f);
-          }
-          unsigned m = __ballot_sync(0xffffffffu, pass);
-          const int id = si[min(k, cnt - 1)];
-          // narrow phase: lane <-> ray, survivors broadcast one at a time
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1u;
-            const float bsx = __shfl_sync(0xffffffffu, sx, src), bsy = __shfl_sync(0xffffffffu, sy, src);
-            const float bc = __shfl_sync(0xffffffffu, c, src);
-            const int bid = __shfl_sync(0xffffffffu, id, src);
+    // group cones: group k's rays lie between bd[k] (its first ray) and bd[k+1] (the next group's first ray,
+    // or the fan's last ray); the directions come from the lanes that own those rays
+    float bdx[RA_G + 1], bdy[RA_G + 1];
+    bool gok[RA_G];
+    {
+      const int g_last = (a.n_rays - 1) / RG, li = a.n_rays - 1 - g_last * RG, qb = li / RA_GW;
+      float ex = dx[0], ey = dy[0];
 #pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              const float b = f_add(f_mul(bsx, dx[q]), f_mul(bsy, dy[q]));
-              const float h = f_sub(f_mul(b, b), bc);
-              if (h >= 0.0f) {
-                const float tt = f_sub(-b, __fsqrt_rn(h));
-                if (tt >= 0.0f && (tt < best[q] || (tt == best[q] && bid < bidx[q]))) {
-                  best[q] = tt;
-                  bidx[q] = bid;
-                }
-              }
-            }
-          }
-        }
+      for (int q = 1; q < RPL; ++q)
+        if (q == qb) { ex = dx[q]; ey = dy[q]; }
+      bdx[RA_G] = __shfl_sync(0xffffffffu, ex, g_last * RA_GW + li % RA_GW);
+      bdy[RA_G] = __shfl_sync(0xffffffffu, ey, g_last * RA_GW + li % RA_GW);
+#pragma unroll
+      for (int k = 0; k < RA_G; ++k) {
+        gok[k] = k * RG < a.n_rays;
+        const float fx = __shfl_sync(0xffffffffu, dx[0], k * RA_GW), fy = __shfl_sync(0xffffffffu, dy[0], k * RA_GW);
+        bdx[k] = gok[k] ? fx : bdx[RA_G];
+        bdy[k] = gok[k] ? fy : bdy[RA_G];
       }
     }
-    if (valid) {
+    const float fax = bdx[0], fay = bdy[0], fbx = bdx[RA_G], fby = bdy[RA_G], fmx = fax + fbx, fmy = fay + fby;
+
+    int cnt[RA_G];
 #pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        const int rj = lane + 32 * q;
-        if (rj >= a.n_rays) continue;
-        const int64_t o = agent * a.n_rays + rj;
-        float d = act ? best[q] : 0.0f;
-        int h = act ? bidx[q] : -1;
-        if (a.merge_walls && act) {
-          // entity order [agents, walls]: an agent wins a tie; wall index w -> m + w
-          const float wd = a.dist[o];
-          const int wh = a.hit[o];
-          if (!(bidx[q] >= 0 && best[q] <= wd)) {
-            d = wd;
-            h = wh >= 0 ? (int)(a.m + wh) : -1;
+    for (int k = 0; k < RA_G; ++k) cnt[k] = 0;
+
+    // narrow phase, lanes = rays: every group walks its own survivor list, two entries per trip
+    auto drain = [&]() {
+      __syncwarp();
+      int n_mine = cnt[0], n_max = cnt[0];
+#pragma unroll
+      for (int k = 1; k < RA_G; ++k) {
+        if (g == k) n_mine = cnt[k];
+        n_max = max(n_max, cnt[k]);
+      }
+      for (int e = 0; e < n_max; e += 2) {
+        const float4 t0 = mine[g][e], t1 = mine[g][e + 1];  // stale slots are masked by in0 / in1
+        const bool in0 = e < n_mine, in1 = e + 1 < n_mine;
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          const float b0 = f_add(f_mul(t0.x, dx[q]), f_mul(t0.y, dy[q]));
+          const float b1 = f_add(f_mul(t1.x, dx[q]), f_mul(t1.y, dy[q]));
+          const float h0 = f_sub(f_mul(b0, b0), t0.z), h1 = f_sub(f_mul(b1, b1), t1.z);
+          // cheap necessary condition for "tt >= 0 and tt <= best": b <= 0 and sqrt(h) >= -b - best, with a
+          // 1e-5 relative slack that dwarfs the rounding of the exact evaluation below (kb = best * 1.00001)
+          const float v0 = fmaf(b0, -0.99999f, -kb[q]), v1 = fmaf(b1, -0.99999f, -kb[q]);
+          const bool c0 = in0 & (h0 >= 0.0f) & (b0 <= 0.0f) & ((v0 <= 0.0f) | (h0 >= v0 * v0 * 0.99999f));
+          const bool c1 = in1 & (h1 >= 0.0f) & (b1 <= 0.0f) & ((v1 <= 0.0f) | (h1 >= v1 * v1 * 0.99999f));
+          if (c0 | c1) {
+            if (c0) {
+              const float tt = f_sub(-b0, __fsqrt_rn(h0));
+              const int bid = __float_as_int(t0.w);
+              if (tt >= 0.0f && (tt < best[q] || (tt == best[q] && bid < bidx[q]))) {
+                best[q] = tt;
+                bidx[q] = bid;
+              }
+            }
+            if (c1) {
+              const float tt = f_sub(-b1, __fsqrt_rn(h1));
+              const int bid = __float_as_int(t1.w);
+              if (tt >= 0.0f && (tt < best[q] || (tt == best[q] && bid < bidx[q]))) {
+                best[q] = tt;
+                bidx[q] = bid;
+              }
+            }
+            kb[q] = best[q] * 1.00001f;
           }
         }
-        a.dist[o] = d;
-        a.hit[o] = h;
       }
+#pragma unroll
+      for (int k = 0; k < RA_G; ++k) cnt[k] = 0;
+      __syncwarp();
+    };
+
+    const int cx = cell % a.g.gx, cy = cell / a.g.gx;
+    for (int step = 0; step <= 2 * K; ++step) {
+      // rows nearest first (cy, cy+1, cy-1, cy+2, ...): the minima settle early and the cheap rejection in
+      // drain() then skips the exact evaluation for most of the farther survivors
+      const int ry = cy + ((step & 1) ? (step + 1) / 2 : -(step / 2));
+      if (ry < 0 || ry >= a.g.gy) continue;
+      // cells of this row that can hold a target in reach and (convex fan) inside the widened fan; lane <-> cell
+      const int ccx = cx - K + lane;
+      bool keep = lane <= 2 * K && ccx >= 0 && ccx < a.g.gx;
+      if (keep) {
+        // rectangle of target centres in the cell, relative to the sensor; border cells are unbounded outwards
+        const float x0 = ccx == 0 ? -1e30f : (a.g.x0 + ccx * cs - cell_margin) - ox;
+        const float x1 = ccx == a.g.gx - 1 ? 1e30f : (a.g.x0 + (ccx + 1) * cs + cell_margin) - ox;
+        const float y0 = ry == 0 ? -1e30f : (a.g.y0 + ry * cs - cell_margin) - oy;
+        const float y1 = ry == a.g.gy - 1 ? 1e30f : (a.g.y0 + (ry + 1) * cs + cell_margin) - oy;
+        const float ddx = fmaxf(fmaxf(x0, -x1), 0.0f), ddy = fmaxf(fmaxf(y0, -y1), 0.0f);
+        keep = ddx * ddx + ddy * ddy <= reach2;
+        if (fan_convex) {
+          const float R = a.max_rad * 1.0001f + 1e-3f;
+          keep = keep && rect_max(-fay, fax, x0, x1, y0, y1) >= -R    // cross(d_first, p) >= -R
+                      && rect_max(fby, -fbx, x0, x1, y0, y1) >= -R    // cross(p, d_last) >= -R
+                      && rect_max(fmx, fmy, x0, x1, y0, y1) >= -2.0f * R;  // not behind the sensor
+        }
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (km == 0u) continue;
+      const int c_lo = ry * a.g.gx + cx - K + (__ffs(km) - 1), c_hi = ry * a.g.gx + cx - K + (31 - __clz(km));
+      const uint32_t r0 = a.tstart[c_lo], r1 = a.tstart[c_hi + 1];  // the row's cells are contiguous
+      for (uint32_t base = r0; base < r1; base += 32) {
+        // broad phase: lane <-> target
+        const uint32_t k = base + lane;
+        const bool in = k < r1;
+        const float4 t = a.targets[in ? k : r1 - 1];
+        const int id = a.tidx[in ? k : r1 - 1];
+        const float sx = f_sub(ox, t.x), sy = f_sub(oy, t.y);
+        const float c = f_sub(f_add(f_mul(sx, sx), f_mul(sy, sy)), f_mul(t.z, t.z));
+        const bool pass = in && t.w != 0.0f && !(c > f_mul(f_add(L2, f_mul(twoL, t.z)), 1.0001f));
+        // a circle farther than r from the cone spanned by a group's rays cannot be hit by any of them.
+        // v = target - sensor = -s:  cross(bd, v) = bdy*sx - bdx*sy,  cross(v, bd) = -cross(bd, v)
+        const float tol = t.z * 1.0001f + 1e-4f * (fabsf(sx) + fabsf(sy)) + 1e-6f;
+        float cr[RA_G + 1];
+#pragma unroll
+        for (int k = 0; k <= RA_G; ++k) cr[k] = bdy[k] * sx - bdx[k] * sy;
+        const bool front_fan = -(fmx * sx + fmy * sy) >= -2.0f * tol;  // not behind the sensor (convex fan)
+        const float4 entry = make_float4(sx, sy, c, __int_as_float(id));
+        bool full = false;
+#pragma unroll
+        for (int gg = 0; gg < RA_G; ++gg) {
+          bool pg = pass && gok[gg] && cr[gg] >= -tol && cr[gg + 1] <= tol;
+          if (fan_convex) pg = pg && front_fan;
+          else pg = pg && -((bdx[gg] + bdx[gg + 1]) * sx + (bdy[gg] + bdy[gg + 1]) * sy) >= -2.0f * tol;
+          const unsigned m = __ballot_sync(0xffffffffu, pg);
+          if (pg) mine[gg][cnt[gg] + __popc(m & lt)] = entry;
+          cnt[gg] += __popc(m);
+          full = full || cnt[gg] > RA_CAP - 32;
+        }
+        if (full) drain();
+      }
+    }
+    drain();
+
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = ray_of(g, w, q, RG);
+      if (!(q * RA_GW + w < RG && r < a.n_rays)) continue;
+      const int64_t o = agent * a.n_rays + r;
+      float d = best[q];
+      int h = bidx[q];
+      if (a.merge_walls) {
+        // entity order [agents, walls]: an agent wins a tie; wall index w -> m + w
+        const float wd = a.dist[o];
+        const int wh = a.hit[o];
+        if (!(bidx[q] >= 0 && best[q] <= wd)) {
+          d = wd;
+          h = wh >= 0 ? (int)(a.m + wh) : -1;
+        }
+      }
+      a.dist[o] = d;
+      a.hit[o] = h;
     }
   }
 }
@@ -291,19 +387,20 @@ static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s)
 
 static int grid_dims(float x_min, float x_max, float y_min, float y_max, float ray_length, float max_rad,
                      GridDesc* g) {
-  const float cs = (ray_length + max_rad) * 1.0001f;
-  if (!(cs > 0.0f) || !(x_max > x_min) || !(y_max > y_min)) return -1;
-  int gx = (int)ceilf((x_max - x_min) / cs), gy = (int)ceilf((y_max - y_min) / cs);
-  gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
-  gy = gy < 1 ? 1 : (gy > 1024 ? 1024 : gy);
-  // if the clamp made cells LARGER than cs that is still conservative (cell >= cs is all that matters)
-  const float csx = (x_max - x_min) / gx, csy = (y_max - y_min) / gy;
-  const float c = fmaxf(cs, fmaxf(csx, csy));
+  const float reach = (ray_length + max_rad) * 1.0001f;  // a target farther than this (per axis) cannot be hit
+  if (!(reach > 0.0f) || !(x_max > x_min) || !(y_max > y_min)) return -1;
+  // RA_SUB cells per reach: the fan and range culls then skip most of the (2K+1)^2 neighbourhood
+  float c = reach / RA_SUB;
+  const float ext = fmaxf(x_max - x_min, y_max - y_min);
+  if (ext / c > 2048.0f) c = ext / 2048.0f;  // at most 2048 cells per axis
   g->x0 = x_min; g->y0 = y_min; g->inv_cs = 1.0f / c;
   g->gx = (int)ceilf((x_max - x_min) / c); g->gy = (int)ceilf((y_max - y_min) / c);
   if (g->gx < 1) g->gx = 1;
   if (g->gy < 1) g->gy = 1;
-  return 0;
+  // |cell(a) - cell(b)| <= K whenever |a - b| <= reach (monotone clamp included; reach carries the margin)
+  g->K = (int)ceilf(reach / c * 0.99999f);
+  if (g->K < 1) g->K = 1;
+  return g->K <= 15 ? 0 : -1;  // one lane per cell of a neighbourhood row
 }
 
 }  // namespace fgx
@@ -342,23 +439,23 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(s.tcount, 0, al256((size_t)n_cells * 4) * 2, st);  // tcount + acount
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_agents: %s", cudaGetErrorString(e));
-  const int groups = 1;  // one warp per agent
   if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, target_stride, n_targets, s.tcell, s.tcount);
   grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, 1, n_agents, s.acell, s.acount);
-  grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, groups, s.tcount, s.acount, s.tstart, s.astart, s.bstart);
+  grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, 1, s.tcount, s.acount, s.tstart, s.astart, s.bstart);
   if (n_targets)
     grid_scatter_targets_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(tx, ty, trad, tactive, target_stride,
                                                                              n_targets, s.tcell, s.tstart, s.tcount,
                                                                              s.sorted, s.tidx);
   grid_scatter_agents_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(n_agents, s.acell, s.astart, s.acount,
                                                                         s.order);
-  RaycastAgentsArgs a{g, x, y, ang, active, n_agents, n_targets, n_rays, groups, ray_span, ray_length,
-                      s.tstart, s.astart, s.bstart, s.order, s.sorted, s.tidx, merge_walls ? 1 : 0, dist, hit};
-  // upper bound of CTA tasks: every cell rounds up by at most one
-  const int64_t max_tasks = ceil_div(n_agents, RA_WARPS) + n_cells;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  const int grid = (int)(max_tasks < cap ? max_tasks : cap);
-  switch ((n_rays + 31) / 32) {
+  RaycastAgentsArgs a{g, x, y, ang, active, n_agents, n_targets, n_rays, ray_span, ray_length, max_rad,
+                      s.tstart, s.order, s.acell, s.sorted, s.tidx, merge_walls ? 1 : 0, dist, hit};
+  // one warp per agent, walking the cell-sorted agent list (neighbouring warps share their targets in L1/L2)
+  const int64_t ctas = ceil_div(n_agents, RA_WARPS);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(ctas < cap ? ctas : cap);
+  const int rg = (n_rays + RA_G - 1) / RA_G;
+  switch ((rg + RA_GW - 1) / RA_GW) {
     case 1: raycast_agents_kernel<1><<<grid, RA_BLOCK, 0, st>>>(a); break;
     case 2: raycast_agents_kernel<2><<<grid, RA_BLOCK, 0, st>>>(a); break;
     case 3: raycast_agents_kernel<3><<<grid, RA_BLOCK, 0, st>>>(a); break;

@@ -18,10 +18,10 @@ def dev(a, cuda):
     return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
 
 
-def device_dirs(x, y, ang, n_rays, cuda):
+def device_dirs(x, y, ang, n_rays, cuda, span=SPAN):
     import foragax_b200.base.space_methods as sm
     sm.RESOLUTION = n_rays
-    rays = sm.ray_generator((dev(x, cuda), dev(y, cuda), dev(ang, cuda)), SPAN, LEN)
+    rays = sm.ray_generator((dev(x, cuda), dev(y, cuda), dev(ang, cuda)), span, LEN)
     return rays.ray_direction.x.cpu().numpy(), rays.ray_direction.y.cpu().numpy()
 
 
@@ -63,6 +63,32 @@ def test_raycast_agents_self_sensing_bit_exact(cuda, n, n_rays, size, rmax):
     np.testing.assert_array_equal(got_h.cpu().numpy(), ref_h)
     if n >= 800:
         assert (ref_h >= 0).mean() > 0.05
+
+
+@pytest.mark.parametrize("n,n_rays,size,rmax,span", [
+    (900, 40, 500.0, 10.0, np.pi / 4),    # two rays per lane
+    (600, 100, 400.0, 8.0, np.pi / 3),    # four rays per lane
+    (1200, 1, 400.0, 10.0, 0.3),          # a single ray: degenerate cones
+    (1500, 32, 500.0, 10.0, 2.5),         # non-convex fan (no cell cull against the fan, per-group front test)
+    (1000, 7, 300.0, 6.0, np.pi),         # full circle, fewer rays than lanes of a group
+    (6000, 32, 330.0, 6.0, np.pi / 4),    # dense: survivor lists overflow and drain several times per agent
+])
+def test_raycast_agents_ray_layouts_and_fans(cuda, n, n_rays, size, rmax, span):
+    import foragax_b200.base.space_methods as sm
+    span = np.float32(span)
+    rng = np.random.default_rng(7 * n + n_rays)
+    x, y = rng.uniform(0, size, n).astype(np.float32), rng.uniform(0, size, n).astype(np.float32)
+    ang = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    rad = rng.uniform(rmax / 3, rmax, n).astype(np.float32)
+    act = (rng.random(n) < 0.9).astype(np.float32)
+    dx, dy = device_dirs(x, y, ang, n_rays, cuda, span)
+    ref_d, ref_h = oracle_agents(x, y, dx, dy, x, y, rad, act, act)
+    got_d, got_h = sm.raycast_agents((dev(x, cuda), dev(y, cuda), dev(ang, cuda)), span, LEN,
+                                     (dev(x, cuda), dev(y, cuda), dev(rad, cuda), dev(act, cuda)),
+                                     (0.0, size, 0.0, size), rmax, active_state=dev(act, cuda), n_rays=n_rays)
+    np.testing.assert_array_equal(got_d.cpu().numpy(), ref_d)
+    np.testing.assert_array_equal(got_h.cpu().numpy(), ref_h)
+    assert (ref_h >= 0).mean() > 0.05
 
 
 def test_raycast_agents_interleaved_targets_out_of_bounds_and_wall_merge(cuda):
