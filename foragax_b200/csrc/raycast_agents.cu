@@ -2,21 +2,25 @@
 //
 // Reference: ray_agent_sensor (space_methods.py:71-94) evaluated for every (ray, target) and
 // reduced per ray with min / first-argmin (EcoEvoJax/sim.py:444-447).  The reference is all-pairs
-// (O(N^2 R)); here a uniform grid with cell >= ray_length + max_rad bounds the search to the 3x3
-// neighbourhood of the sensing agent's cell.  The cull is exact, not approximate: a target farther
-// than ray_length + rad from the ray origin cannot produce t < ray_length (the rounding error of
-// t = -b - sqrt(b*b - c) is ~1e-6 relative, the cell carries a 1e-4 relative margin), so the result
-// equals the all-pairs evaluation bit for bit; ties are resolved by the lexicographic (distance,
-// target index) minimum, i.e. argmin's first-index rule, independent of the grid order.
+// (O(N^2 R)); here a uniform grid with cell = (ray_length + max_rad) / 3 bounds the search to the cells of
+// the 7x7 neighbourhood that can hold a target in reach and inside the (widened) ray fan.  Every cull is
+// conservative, not approximate: a target farther than ray_length + rad from the ray origin, or farther
+// than rad from the cone spanned by a group of rays, cannot produce t < ray_length (the rounding error
+// of t = -b - sqrt(b*b - c) is ~1e-6 relative, the culls carry 1e-4 relative margins), so the result
+// equals the all-pairs evaluation bit for bit; ties are resolved by the lexicographic (distance, target
+// index) minimum, i.e. argmin's first-index rule, independent of the grid order.
 //
 //   1. counting sort of the targets by cell (histogram with atomics, scan, scatter) and of the
 //      sensing agents by cell;
-//   2. one CTA task = 8 agents of ONE cell, one warp per agent; the targets of the 3x3
-//      neighbourhood are staged through shared memory in chunks and shared by the 8 warps.
-//      Broad phase, lanes = targets: each lane takes one staged target, forms s = o - c and
-//      c = |s|^2 - r^2 and rejects it if it is inactive, farther than ray_length + r, or outside the
-//      ray fan by more than its radius.  Narrow phase, lanes = rays: the few survivors (ballot) are
-//      broadcast one by one with shuffles and every lane tests its own ray against them;
+//   2. one warp per sensing agent, walking the cell-sorted agent list (the warps of a CTA sense
+//      neighbouring agents and share their targets through L1/L2; no shared staging, no barrier).
+//      Per neighbourhood row, lanes = cells: keep the cells within reach and inside the fan; their
+//      targets are contiguous.  Broad phase, lanes = targets: s = o - c, c = |s|^2 - r^2, reject
+//      inactive / out-of-reach targets, then test the circle against the cone of each of the 4 ray
+//      groups (lanes 8g..8g+7 own the rays of group g) and append it to the shared-memory list of every
+//      group it can touch (ballot + popc compaction).  Narrow phase, lanes = rays: each group walks its
+//      own list, two entries per trip; a cheap necessary condition (b <= 0, h >= (-b - best - slack)^2)
+//      guards the exactly rounded sqrt, and rows are visited nearest first so the minima settle early;
 //   3. optional merge with the wall result of fgx_raycast_walls in entity order [agents, walls].
 #include "common.cuh"
 #include "geometry.cuh"
@@ -30,7 +34,7 @@ constexpr int RA_GW = 32 / RA_G;         // lanes per group
 constexpr int RA_MAXRB = 4;              // rays per lane (n_rays <= 128)
 constexpr int RA_CAP = 64;               // survivor list entries per (warp, group)
 constexpr int RA_MINB = 4;                // CTAs per SM the register budget is held to
-constexpr int RA_SUB = 3;                // cells per (ray_length + max_rad): search radius K = RA_SUB cells
+constexpr int RA_SUB = 3;                // at most this many cells per (ray_length + max_rad); search radius K cells
 
 struct GridDesc {
   float x0, y0, inv_cs;
@@ -58,27 +62,32 @@ __global__ void __launch_bounds__(256) grid_count_kernel(GridDesc g, const float
   }
 }
 
-// single CTA: exclusive scans of the target counts, the agent counts and the per-cell CTA-task counts
-__global__ void __launch_bounds__(1024) grid_scan_kernel(int n_cells, int groups, uint32_t* __restrict__ tcount,
+// single CTA: exclusive scans of the target counts and the agent counts over the cells (8 consecutive
+// cells per thread, so a 300 x 300 grid takes 11 trips); resets the counts, which double as scatter cursors
+constexpr int GS_ITEMS = 8;
+
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int n_cells, uint32_t* __restrict__ tcount,
                                                          uint32_t* __restrict__ acount, uint32_t* __restrict__ tstart,
-                                                         uint32_t* __restrict__ astart, uint32_t* __restrict__ bstart) {
-  __shared__ uint32_t carry[3];
-  __shared__ uint32_t wsum[3][32];
-  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+                                                         uint32_t* __restrict__ astart) {
+  __shared__ uint32_t carry[2];
+  __shared__ uint32_t wsum[2][32];
+  if (threadIdx.x < 2) carry[threadIdx.x] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int base = 0; base < n_cells; base += 1024) {
-    const int c = base + threadIdx.x;
-    uint32_t v[3] = {0u, 0u, 0u};
-    if (c < n_cells) {
-      v[0] = tcount[c];
-      v[1] = acount[c];
-      v[2] = (v[1] + RA_WARPS - 1) / RA_WARPS;  // CTA tasks of this cell (8 agents each)
-    }
-    uint32_t inc[3];
+  uint32_t* const counts[2] = {tcount, acount};
+  uint32_t* const starts[2] = {tstart, astart};
+  for (int base = 0; base < n_cells; base += 1024 * GS_ITEMS) {
+    const int c0 = base + threadIdx.x * GS_ITEMS;
+    uint32_t v[2][GS_ITEMS], tot[2], inc[2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      inc[k] = v[k];
+    for (int k = 0; k < 2; ++k) {
+      tot[k] = 0;
+#pragma unroll
+      for (int j = 0; j < GS_ITEMS; ++j) {
+        v[k][j] = c0 + j < n_cells ? counts[k][c0 + j] : 0u;
+        tot[k] += v[k][j];
+      }
+      inc[k] = tot[k];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, inc[k], d);
@@ -87,30 +96,30 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(int n_cells, int groups
       if (l == 31) wsum[k][w] = inc[k];
     }
     __syncthreads();
-    uint32_t* outs[3] = {tstart, astart, bstart};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      uint32_t wb = carry[k];
-      for (int q = 0; q < w; ++q) wb += wsum[k][q];
-      if (c < n_cells) outs[k][c] = wb + inc[k] - v[k];
-      inc[k] += wb;
+    for (int k = 0; k < 2; ++k) {
+      uint32_t run = carry[k] + inc[k] - tot[k];
+      for (int q = 0; q < w; ++q) run += wsum[k][q];
+#pragma unroll
+      for (int j = 0; j < GS_ITEMS; ++j) {
+        if (c0 + j < n_cells) {
+          starts[k][c0 + j] = run;
+          counts[k][c0 + j] = 0;
+        }
+        run += v[k][j];
+      }
+      inc[k] = run;  // inclusive total up to and including this thread
     }
     __syncthreads();
     if (threadIdx.x == 1023) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) carry[k] = inc[k];
+      carry[0] = inc[0];
+      carry[1] = inc[1];
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     tstart[n_cells] = carry[0];
     astart[n_cells] = carry[1];
-    bstart[n_cells] = carry[2];
-  }
-  // the counts double as scatter cursors: reset them
-  for (int c = threadIdx.x; c < n_cells; c += 1024) {
-    tcount[c] = 0;
-    acount[c] = 0;
   }
 }
 
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct RaScratch {
-  uint32_t *tcount, *acount, *tstart, *astart, *bstart;
+  uint32_t *tcount, *acount, *tstart, *astart;
   int32_t *tcell, *acell, *order, *tidx;
   float4* sorted;
 };
@@ -376,7 +385,6 @@ static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s)
   p = take((size_t)n_cells * 4); if (s) s->acount = (uint32_t*)p;
   p = take((size_t)(n_cells + 1) * 4); if (s) s->tstart = (uint32_t*)p;
   p = take((size_t)(n_cells + 1) * 4); if (s) s->astart = (uint32_t*)p;
-  p = take((size_t)(n_cells + 1) * 4); if (s) s->bstart = (uint32_t*)p;
   p = take((size_t)m * 4); if (s) s->tcell = (int32_t*)p;
   p = take((size_t)n * 4); if (s) s->acell = (int32_t*)p;
   p = take((size_t)n * 4); if (s) s->order = (int32_t*)p;
@@ -386,11 +394,15 @@ static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s)
 }
 
 static int grid_dims(float x_min, float x_max, float y_min, float y_max, float ray_length, float max_rad,
-                     GridDesc* g) {
+                     int64_t n_targets, GridDesc* g) {
   const float reach = (ray_length + max_rad) * 1.0001f;  // a target farther than this (per axis) cannot be hit
   if (!(reach > 0.0f) || !(x_max > x_min) || !(y_max > y_min)) return -1;
-  // RA_SUB cells per reach: the fan and range culls then skip most of the (2K+1)^2 neighbourhood
-  float c = reach / RA_SUB;
+  // up to RA_SUB cells per reach: the fan and range culls then skip most of the (2K+1)^2 neighbourhood -- as
+  // long as a cell still holds ~16 targets (a row of cells is one 32-lane trip of the broad phase)
+  const float per_reach_cell = (float)n_targets / ((x_max - x_min) * (y_max - y_min)) * reach * reach;
+  int sub = (int)sqrtf(per_reach_cell / 16.0f);
+  sub = sub < 1 ? 1 : (sub > RA_SUB ? RA_SUB : sub);
+  float c = reach / sub;
   const float ext = fmaxf(x_max - x_min, y_max - y_min);
   if (ext / c > 2048.0f) c = ext / 2048.0f;  // at most 2048 cells per axis
   g->x0 = x_min; g->y0 = y_min; g->inv_cs = 1.0f / c;
@@ -410,7 +422,7 @@ extern "C" {
 size_t fgx_raycast_agents_scratch_bytes(int64_t n_agents, int64_t n_targets, float x_min, float x_max, float y_min,
                                         float y_max, float ray_length, float max_rad) {
   fgx::GridDesc g;
-  if (fgx::grid_dims(x_min, x_max, y_min, y_max, ray_length, max_rad, &g)) return 0;
+  if (fgx::grid_dims(x_min, x_max, y_min, y_max, ray_length, max_rad, n_targets, &g)) return 0;
   return fgx::carve(nullptr, n_agents < 0 ? 0 : n_agents, n_targets < 0 ? 0 : n_targets, g.gx * g.gy, nullptr);
 }
 
@@ -428,7 +440,7 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   FGX_REQUIRE(x && y && ang && dist && hit, "fgx_raycast_agents: null pointer");
   FGX_REQUIRE(n_targets == 0 || (tx && ty && trad && tactive), "fgx_raycast_agents: null target array");
   GridDesc g;
-  FGX_REQUIRE(grid_dims(x_min, x_max, y_min, y_max, ray_length, max_rad, &g) == 0,
+  FGX_REQUIRE(grid_dims(x_min, x_max, y_min, y_max, ray_length, max_rad, n_targets, &g) == 0,
               "fgx_raycast_agents: bad arena bounds / ray_length / max_rad");
   const int n_cells = g.gx * g.gy;
   const size_t need = carve(nullptr, n_agents, n_targets, n_cells, nullptr);
@@ -441,7 +453,7 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_agents: %s", cudaGetErrorString(e));
   if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, target_stride, n_targets, s.tcell, s.tcount);
   grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, 1, n_agents, s.acell, s.acount);
-  grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, 1, s.tcount, s.acount, s.tstart, s.astart, s.bstart);
+  grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, s.tcount, s.acount, s.tstart, s.astart);
   if (n_targets)
     grid_scatter_targets_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(tx, ty, trad, tactive, target_stride,
                                                                              n_targets, s.tcell, s.tstart, s.tcount,
