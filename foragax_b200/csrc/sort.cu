@@ -14,7 +14,11 @@
 //      warp match/ballot ranking; finish copies to the caller's perm if needed.
 // Small inputs order the unique 64-bit (image, index) composite (hence stable): n <= 256 by a
 // single-CTA bitonic network in shared memory, n <= 16384 by an all-pairs rank sort over every SM.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace fgx {
 
@@ -37,9 +41,11 @@ struct SortState {
   int32_t pad[3];
 };
 
+// SortState fields written by an earlier phase are read with ld.cg: in the fused kernel the writer is
+// another CTA of the SAME launch (L1 is not coherent; every phase boundary is a grid-wide sync)
 __device__ __forceinline__ int passes_done(const SortState* st, int pass) {
   int c = 0;
-  for (int q = 0; q < pass; ++q) c += st->trivial[q] ? 0 : 1;
+  for (int q = 0; q < pass; ++q) c += __ldcg(&st->trivial[q]) ? 0 : 1;
   return c;
 }
 
@@ -187,10 +193,8 @@ __global__ void __launch_bounds__(RS_BLOCK)
 }
 
 // ---- 3. general path --------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sort_prep_kernel(const void* __restrict__ keys, int dtype, int descending,
-                                                        int64_t n, uint32_t* __restrict__ img,
-                                                        SortState* __restrict__ st) {
-  if (st->done) return;
+__device__ __forceinline__ void sort_prep_body(const void* __restrict__ keys, int dtype, int descending, int64_t n,
+                                               uint32_t* __restrict__ img, SortState* __restrict__ st) {
   __shared__ uint32_t h[4][256];
   for (int k = threadIdx.x; k < 1024; k += blockDim.x) (&h[0][0])[k] = 0;
   __syncthreads();
@@ -212,13 +216,12 @@ __global__ void __launch_bounds__(256) sort_prep_kernel(const void* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) sort_plan_kernel(int64_t n, SortState* __restrict__ st) {
-  if (st->done) return;
+__device__ __forceinline__ void sort_plan_body(int64_t n, SortState* __restrict__ st) {
   __shared__ uint32_t sh[256];
   __shared__ int triv;
   const int t = threadIdx.x;
   for (int p = 0; p < 4; ++p) {
-    const uint32_t c = st->hist[p][t];
+    const uint32_t c = __ldcg(&st->hist[p][t]);
     if (t == 0) triv = 0;
     __syncthreads();
     if ((uint64_t)c == (uint64_t)n) triv = 1;
@@ -238,12 +241,9 @@ __global__ void __launch_bounds__(256) sort_plan_kernel(int64_t n, SortState* __
 __device__ __forceinline__ uint32_t digit_of(uint32_t v, int pass) { return (v >> (8 * pass)) & 255u; }
 
 // tile digit counts -> block_hist[digit][tile]
-__global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __restrict__ img0,
-                                                             const uint32_t* __restrict__ img1, int64_t n,
-                                                             int64_t num_tiles, int pass,
-                                                             const SortState* __restrict__ st,
-                                                             uint32_t* __restrict__ block_hist) {
-  if (st->done || st->trivial[pass]) return;
+__device__ __forceinline__ void sort_hist_body(const uint32_t* img0, const uint32_t* img1, int64_t n,
+                                               int64_t num_tiles, int pass, const SortState* st,
+                                               uint32_t* block_hist) {
   const uint32_t* img = (passes_done(st, pass) & 1) ? img1 : img0;
   __shared__ uint32_t h[256];
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __r
     for (int r = 0; r < RS_ITEMS; ++r) {
       const int64_t i = base + r * RS_BLOCK + threadIdx.x;
       const bool valid = i < n;
-      hist_add(h, valid ? digit_of(__ldg(img + i), pass) : 0u, valid);
+      hist_add(h, valid ? digit_of(__ldcg(img + i), pass) : 0u, valid);
     }
     __syncthreads();
     block_hist[(int64_t)threadIdx.x * num_tiles + tile] = h[threadIdx.x];
@@ -263,42 +263,39 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* __r
 }
 
 // one CTA per digit: exclusive scan of block_hist[digit][0..num_tiles) in place
-__global__ void __launch_bounds__(256) sort_scan_kernel(int64_t num_tiles, int pass, const SortState* __restrict__ st,
-                                                        uint32_t* __restrict__ block_hist) {
-  if (st->done || st->trivial[pass]) return;
-  uint32_t* row = block_hist + (int64_t)blockIdx.x * num_tiles;
+__device__ __forceinline__ void sort_scan_body(int64_t num_tiles, uint32_t* block_hist) {
   __shared__ uint32_t wsum[8];
   __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int64_t b = 0; b < num_tiles; b += 256) {
-    const int64_t t = b + threadIdx.x;
-    const uint32_t v = t < num_tiles ? row[t] : 0u;
-    uint32_t inc = v;
+  for (int digit = blockIdx.x; digit < 256; digit += gridDim.x) {
+    uint32_t* row = block_hist + (int64_t)digit * num_tiles;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < num_tiles; b += 256) {
+      const int64_t t = b + threadIdx.x;
+      const uint32_t v = t < num_tiles ? __ldcg(row + t) : 0u;
+      uint32_t inc = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (l >= d) inc += o;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (l >= d) inc += o;
+      }
+      if (l == 31) wsum[w] = inc;
+      __syncthreads();
+      uint32_t wb = carry;
+      for (int k = 0; k < w; ++k) wb += wsum[k];
+      if (t < num_tiles) row[t] = wb + inc - v;
+      __syncthreads();
+      if (threadIdx.x == 255) carry = wb + inc;
+      __syncthreads();
     }
-    if (l == 31) wsum[w] = inc;
-    __syncthreads();
-    uint32_t wb = carry;
-    for (int k = 0; k < w; ++k) wb += wsum[k];
-    if (t < num_tiles) row[t] = wb + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry = wb + inc;
-    __syncthreads();
   }
 }
 
 // stable scatter of one pass
-__global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __restrict__ img0, uint32_t* __restrict__ img1,
-                                                                int32_t* __restrict__ idx0, int32_t* __restrict__ idx1,
-                                                                int64_t n, int64_t num_tiles, int pass,
-                                                                const SortState* __restrict__ st,
-                                                                const uint32_t* __restrict__ block_hist) {
-  if (st->done || st->trivial[pass]) return;
+__device__ __forceinline__ void sort_scatter_body(uint32_t* img0, uint32_t* img1, int32_t* idx0, int32_t* idx1,
+                                                  int64_t n, int64_t num_tiles, int pass, const SortState* st,
+                                                  const uint32_t* block_hist) {
   const int done = passes_done(st, pass);
   const int cur = done & 1;
   const uint32_t* kin = cur ? img1 : img0;
@@ -312,7 +309,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
   const unsigned lt = lanemask_lt();
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_BLOCK) (&wcnt[0][0])[k] = 0;
-    gbase[threadIdx.x] = st->base[pass][threadIdx.x] + block_hist[(int64_t)threadIdx.x * num_tiles + tile];
+    gbase[threadIdx.x] = __ldcg(&st->base[pass][threadIdx.x]) + __ldcg(&block_hist[(int64_t)threadIdx.x * num_tiles + tile]);
     __syncthreads();
     const int64_t wbase = tile * RS_TILE + (int64_t)w * (32 * RS_ITEMS);
     uint32_t key[RS_ITEMS];
@@ -321,7 +318,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
     for (int r = 0; r < RS_ITEMS; ++r) {
       const int64_t i = wbase + r * 32 + l;
       const bool valid = i < n;
-      key[r] = valid ? kin[i] : 0xFFFFFFFFu;
+      key[r] = valid ? __ldcg(kin + i) : 0xFFFFFFFFu;
       // invalid lanes use a digit value outside 0..255 so they never match a real one
       const uint32_t d = valid ? digit_of(key[r], pass) : 256u;
       const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -353,7 +350,7 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
         const uint32_t d = digit_of(key[r], pass);
         const uint32_t pos = gbase[d] + wcnt[w][d] + lpos[r];
         kout[pos] = key[r];
-        iout[pos] = iota ? (int32_t)i : iin[i];
+        iout[pos] = iota ? (int32_t)i : __ldcg(iin + i);
       }
     }
     __syncthreads();
@@ -361,14 +358,70 @@ __global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* __rest
 }
 
 // result -> perm (idx0 aliases perm): copy only if the final order sits in idx1, or is still iota
-__global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* __restrict__ idx1, int32_t* __restrict__ perm,
-                                                          int64_t n, const SortState* __restrict__ st) {
-  if (st->done) return;
+__device__ __forceinline__ void sort_finish_body(const int32_t* idx1, int32_t* perm, int64_t n, const SortState* st) {
   const int done = passes_done(st, 4);
   const bool iota = done == 0;
   if (!iota && (done & 1) == 0) return;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    perm[i] = iota ? (int32_t)i : idx1[i];
+    perm[i] = iota ? (int32_t)i : __ldcg(idx1 + i);
+}
+
+// The general path as kernels.  Default: ONE cooperative launch with grid-wide syncs between the phases,
+// so that a sort the two-valued path already finished costs one empty launch instead of fifteen (a tick
+// replayed as a CUDA graph pays ~2 us per empty node).  FGX_SORT_MULTI=1 selects one launch per phase.
+__global__ void __launch_bounds__(RS_BLOCK, 2) sort_general_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                                int64_t n, int64_t num_tiles, uint32_t* img0,
+                                                                uint32_t* img1, int32_t* idx0, int32_t* idx1,
+                                                                uint32_t* block_hist, SortState* st) {
+  if (__ldcg(&st->done)) return;  // uniform over the grid: written by an earlier launch
+  cg::grid_group grid = cg::this_grid();
+  sort_prep_body(keys, dtype, descending, n, img0, st);
+  grid.sync();
+  if (blockIdx.x == 0) sort_plan_body(n, st);
+  grid.sync();
+  for (int pass = 0; pass < 4; ++pass) {
+    if (__ldcg(&st->trivial[pass])) continue;
+    sort_hist_body(img0, img1, n, num_tiles, pass, st, block_hist);
+    grid.sync();
+    sort_scan_body(num_tiles, block_hist);
+    grid.sync();
+    sort_scatter_body(img0, img1, idx0, idx1, n, num_tiles, pass, st, block_hist);
+    grid.sync();
+  }
+  sort_finish_body(idx1, idx0, n, st);
+}
+
+__global__ void __launch_bounds__(256) sort_prep_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                        int64_t n, uint32_t* __restrict__ img,
+                                                        SortState* __restrict__ st) {
+  if (st->done) return;
+  sort_prep_body(keys, dtype, descending, n, img, st);
+}
+__global__ void __launch_bounds__(256) sort_plan_kernel(int64_t n, SortState* __restrict__ st) {
+  if (st->done) return;
+  sort_plan_body(n, st);
+}
+__global__ void __launch_bounds__(RS_BLOCK) sort_hist_kernel(const uint32_t* img0, const uint32_t* img1, int64_t n,
+                                                             int64_t num_tiles, int pass, const SortState* st,
+                                                             uint32_t* block_hist) {
+  if (st->done || st->trivial[pass]) return;
+  sort_hist_body(img0, img1, n, num_tiles, pass, st, block_hist);
+}
+__global__ void __launch_bounds__(256) sort_scan_kernel(int64_t num_tiles, int pass, const SortState* st,
+                                                        uint32_t* block_hist) {
+  if (st->done || st->trivial[pass]) return;
+  sort_scan_body(num_tiles, block_hist);
+}
+__global__ void __launch_bounds__(RS_BLOCK) sort_scatter_kernel(uint32_t* img0, uint32_t* img1, int32_t* idx0,
+                                                                int32_t* idx1, int64_t n, int64_t num_tiles, int pass,
+                                                                const SortState* st, const uint32_t* block_hist) {
+  if (st->done || st->trivial[pass]) return;
+  sort_scatter_body(img0, img1, idx0, idx1, n, num_tiles, pass, st, block_hist);
+}
+__global__ void __launch_bounds__(256) sort_finish_kernel(const int32_t* idx1, int32_t* perm, int64_t n,
+                                                          const SortState* st) {
+  if (st->done) return;
+  sort_finish_body(idx1, perm, n, st);
 }
 
 // ---- small paths (latency-bound sizes: one or two graph nodes instead of the 15 of the radix path) ----
@@ -531,7 +584,23 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   const int tv_grid = (int)ceil_div(tv_tiles, per);
   sort_two_count_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count);
   sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count, perm);
-  // general path (every kernel returns at once when st->done)
+  // general path (returns at once when st->done)
+  static const bool multi = [] { const char* v = getenv("FGX_SORT_MULTI"); return v && atoi(v) == 1; }();
+  if (!multi) {
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_general_kernel, RS_BLOCK, 0);
+    if (e != cudaSuccess || per_sm < 1) return fail(FGX_ERR_CUDA, "fgx_argsort: occupancy query failed");
+    int64_t coop = (int64_t)sm_count() * per_sm;  // all CTAs must be co-resident for the grid-wide syncs
+    const int64_t useful = ceil_div(n, RS_BLOCK * 4);
+    if (coop > useful) coop = useful < 1 ? 1 : useful;
+    const void* keys_arg = keys;
+    int dtype_arg = key_dtype, desc_arg = desc;
+    int64_t n_arg = n, tiles_arg = tiles;
+    void* args[] = {&keys_arg, &dtype_arg, &desc_arg, &n_arg, &tiles_arg, &img0, &img1, &idx0, &idx1, &block_hist, &st};
+    e = cudaLaunchCooperativeKernel((const void*)sort_general_kernel, dim3((unsigned)coop), dim3(RS_BLOCK), args, 0, s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: cooperative launch: %s", cudaGetErrorString(e));
+    return check_launch("fgx_argsort");
+  }
   sort_prep_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, img0, st);
   sort_plan_kernel<<<1, 256, 0, s>>>(n, st);
   const int gt = (int)(tiles < (int64_t)sm_count() * 4 ? tiles : (int64_t)sm_count() * 4);

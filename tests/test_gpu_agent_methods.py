@@ -227,3 +227,21 @@ def test_sharded_create_equals_global_rows(cuda, world, stride_mode):
             np.testing.assert_array_equal(part[k], full[k][rows], err_msg=k)
         np.testing.assert_array_equal(part["state"]["draw"], full["state"]["draw"][rows])
         np.testing.assert_array_equal(part["state"]["key"], full["state"]["key"][rows])
+
+
+def test_argsort_one_launch_per_phase_variant(cuda):
+    """FGX_SORT_MULTI=1 (one launch per radix phase instead of the cooperative single launch) gives the same
+    permutation; the switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = ("import torch, foragax_b200.base.agent_methods as am\n"
+            "g = torch.Generator(device='cuda').manual_seed(1)\n"
+            "for n in (20000, 300001):\n"
+            "    k = torch.randint(-1000, 1000, (n,), device='cuda', generator=g).float() * 0.25\n"
+            "    for asc in (True, False):\n"
+            "        ref = torch.sort(k if asc else -k, stable=True).indices.to(torch.int32)\n"
+            "        assert torch.equal(am.argsort(k, ascend=asc), ref)\n"
+            "print('ok')\n")
+    env = dict(os.environ, FGX_SORT_MULTI="1", PYTHONPATH=os.path.dirname(os.path.dirname(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
