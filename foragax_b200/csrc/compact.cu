@@ -93,18 +93,6 @@ __device__ __forceinline__ unsigned tile_flags(const fgx_predicate_t& p, int64_t
   return flags_at<SEL_ITEMS>(p, tile_elem(tile, w, 0, 0), n, l);
 }
 
-__device__ __forceinline__ int tile_count(const fgx_predicate_t& p, int64_t tile, int64_t n, int* warp_sums) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const int c = __reduce_add_sync(0xffffffffu, __popc(tile_flags(p, tile, n, w, l)));
-  if (l == 0) warp_sums[w] = c;
-  __syncthreads();
-  int tot = 0;
-#pragma unroll
-  for (int k = 0; k < SEL_WARPS; ++k) tot += warp_sums[k];
-  __syncthreads();
-  return tot;
-}
-
 __device__ __forceinline__ int tile_scatter(const fgx_predicate_t& p, int64_t tile, int64_t n, int32_t tile_off,
                                             int32_t total, int32_t* __restrict__ perm, int* warp_sums) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -162,8 +150,12 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_count_kernel(const __grid_co
                                                                 int32_t* __restrict__ cta_count) {
   __shared__ int warp_sums[SEL_WARPS];
   const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
+  // per-thread partial counts over the CTA's tiles (no barrier between tiles: their loads overlap), one
+  // block reduction at the end
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int c = 0;
-  for (int64_t tile = t0; tile < t1; ++tile) c += tile_count(p, tile, n, warp_sums);
+  for (int64_t tile = t0; tile < t1; ++tile) c += __popc(tile_flags(p, tile, n, w, l));
+  c = block_sum(c, warp_sums);
   if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
 }
 

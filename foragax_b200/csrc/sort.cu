@@ -3,11 +3,11 @@
 // Reference: agent_methods.py:74-76 -- argsort(q) or argsort(-q) (jnp.argsort =
 // stable lax.sort of (key, iota); float total order with -0.0 == +0.0 and NaN
 // last).  Here: keys are mapped to order-preserving uint32 images, then
-//   1. minmax   image min / max over the keys
-//   2. two-valued fast path (the common sort on active_state or a 0/1 flag): count
-//      image==min per CTA; if every key is min or max the sort IS a stable 2-way
-//      partition -- one ballot/popc scatter pass writes the permutation and the
-//      general path below is skipped on device;
+//   1. stats    per-CTA (min, #min, max, #max) of the images in ONE read of the keys;
+//   2. two-valued fast path (the common sort on active_state or a 0/1 flag): if every
+//      key is the global min or max the sort IS a stable 2-way partition -- one
+//      ballot/popc scatter pass writes the permutation and the general path below is
+//      skipped on device;
 //   3. general path: stable LSD radix sort of (image, slot index), 8-bit digits:
 //      prep (images + 4 digit histograms), plan (digit bases, trivial passes),
 //      per pass: tile histogram -> per-digit scan over tiles -> stable scatter with
@@ -73,84 +73,94 @@ __device__ __forceinline__ uint32_t key_image(const void* keys, int dtype, int d
   return image_of(__ldg(reinterpret_cast<const uint32_t*>(keys) + i), dtype, descending);
 }
 
-// ---- 1. min / max image ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) sort_minmax_kernel(const void* __restrict__ keys, int dtype, int descending,
-                                                          int64_t n, SortState* __restrict__ st) {
-  uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = key_image(keys, dtype, descending, i);
-    lmin = min(lmin, v);
-    lmax = max(lmax, v);
-  }
-  lmin = __reduce_min_sync(0xffffffffu, lmin);
-  lmax = __reduce_max_sync(0xffffffffu, lmax);
-  __shared__ uint32_t smin[8], smax[8];
-  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lmin; smax[threadIdx.x >> 5] = lmax; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; ++k) { lmin = min(lmin, smin[k]); lmax = max(lmax, smax[k]); }
-    atomicMin(&st->kmin, lmin);
-    atomicMax(&st->kmax, lmax);
-  }
+// ---- 1. one pass of statistics: per-CTA (min, #min, max, #max) of its contiguous tile range -----------
+// (min, count) is a monoid -- combine keeps the smaller value and adds the counts on a tie -- so the
+// global extrema AND how many keys hold them come out of a single read of the keys: the scatter pass
+// derives them from the per-CTA records, no separate min/max pass.
+struct TvStat {
+  uint32_t mn, cmn, mx, cmx;
+};
+__device__ __forceinline__ void tv_merge(TvStat& a, uint32_t mn, uint32_t cmn, uint32_t mx, uint32_t cmx) {
+  a.cmn = mn < a.mn ? cmn : (mn == a.mn ? a.cmn + cmn : a.cmn);
+  a.mn = min(a.mn, mn);
+  a.cmx = mx > a.mx ? cmx : (mx == a.mx ? a.cmx + cmx : a.cmx);
+  a.mx = max(a.mx, mx);
 }
 
-// ---- 2. two-valued fast path: stable partition by (image == min) -------------------------
 __device__ __forceinline__ int64_t tv_elem(int64_t tile, int w, int r, int l) {
   return tile * TV_TILE + w * (32 * TV_ITEMS) + r * 32 + l;
 }
 
 __global__ void __launch_bounds__(RS_BLOCK)
-    sort_two_count_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t num_tiles,
-                          int64_t tiles_per_cta, SortState* __restrict__ st, int32_t* __restrict__ cta_count) {
-  const uint32_t kmin = st->kmin, kmax = st->kmax;
+    sort_two_stats_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t num_tiles,
+                          int64_t tiles_per_cta, TvStat* __restrict__ cta_stat) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
-  int cmin = 0, cmax = 0;
+  TvStat a{0xFFFFFFFFu, 0u, 0u, 0u};
   const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(keys);
   for (int64_t tile = t0; tile < t1; ++tile) {
     uint32_t raw[TV_ITEMS];  // all loads first (no control flow between them), then the compares
 #pragma unroll
     for (int r = 0; r < TV_ITEMS; ++r) raw[r] = __ldg(kw + min(tv_elem(tile, w, r, l), n - 1));
 #pragma unroll
-    for (int r = 0; r < TV_ITEMS; ++r) {
-      const bool in = tv_elem(tile, w, r, l) < n;
-      const uint32_t v = image_of(raw[r], dtype, descending);
-      cmin += in && v == kmin;
-      cmax += in && v == kmax;
-    }
+    for (int r = 0; r < TV_ITEMS; ++r)
+      if (tv_elem(tile, w, r, l) < n) {
+        const uint32_t v = image_of(raw[r], dtype, descending);
+        tv_merge(a, v, 1u, v, 1u);
+      }
   }
-  cmin = __reduce_add_sync(0xffffffffu, cmin);
-  cmax = __reduce_add_sync(0xffffffffu, cmax);
-  __shared__ int smin[RS_WARPS], smax[RS_WARPS];
-  if (l == 0) { smin[w] = cmin; smax[w] = cmax; }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    tv_merge(a, __shfl_xor_sync(0xffffffffu, a.mn, d), __shfl_xor_sync(0xffffffffu, a.cmn, d),
+             __shfl_xor_sync(0xffffffffu, a.mx, d), __shfl_xor_sync(0xffffffffu, a.cmx, d));
+  __shared__ TvStat ws[RS_WARPS];
+  if (l == 0) ws[w] = a;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int a = 0, b = 0;
-    for (int k = 0; k < RS_WARPS; ++k) { a += smin[k]; b += smax[k]; }
-    cta_count[blockIdx.x] = a;
-    if (a) atomicAdd(&st->cnt_min, (uint32_t)a);
-    if (b && kmax != kmin) atomicAdd(&st->cnt_max, (uint32_t)b);
+    for (int k = 1; k < RS_WARPS; ++k) tv_merge(a, ws[k].mn, ws[k].cmn, ws[k].mx, ws[k].cmx);
+    cta_stat[blockIdx.x] = a;
   }
 }
 
+// ---- 2. two-valued fast path: stable partition by (image == min) -------------------------
 __global__ void __launch_bounds__(RS_BLOCK)
     sort_two_scatter_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t num_tiles,
-                            int64_t tiles_per_cta, SortState* __restrict__ st, const int32_t* __restrict__ cta_count,
+                            int64_t tiles_per_cta, SortState* __restrict__ st, const TvStat* __restrict__ cta_stat,
                             int32_t* __restrict__ perm) {
-  if ((uint64_t)st->cnt_min + st->cnt_max != (uint64_t)n) return;  // more than two values: general path
-  if (blockIdx.x == 0 && threadIdx.x == 0) st->done = 1;
-  const uint32_t kmin = st->kmin;
-  const int total = (int)st->cnt_min;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __shared__ int ws[RS_WARPS];
+  __shared__ TvStat ws[RS_WARPS];
+  __shared__ int wbefore[RS_WARPS];
+  // global extrema and their multiplicities from the per-CTA records (every CTA recomputes them: <= 4096 records)
+  TvStat a{0xFFFFFFFFu, 0u, 0u, 0u};
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += RS_BLOCK) {
+    const TvStat c = cta_stat[k];
+    tv_merge(a, c.mn, c.cmn, c.mx, c.cmx);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    tv_merge(a, __shfl_xor_sync(0xffffffffu, a.mn, d), __shfl_xor_sync(0xffffffffu, a.cmn, d),
+             __shfl_xor_sync(0xffffffffu, a.mx, d), __shfl_xor_sync(0xffffffffu, a.cmx, d));
+  if (l == 0) ws[w] = a;
+  __syncthreads();
+  a = ws[0];
+  for (int k = 1; k < RS_WARPS; ++k) tv_merge(a, ws[k].mn, ws[k].cmn, ws[k].mx, ws[k].cmx);
+  const uint32_t kmin = a.mn;
+  const uint64_t covered = a.mn == a.mx ? (uint64_t)a.cmn : (uint64_t)a.cmn + a.cmx;
+  if (covered != (uint64_t)n) return;  // more than two values: general path (uniform over the grid)
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->done = 1;
+  const int total = (int)a.cmn;
+  // keys equal to the minimum in the CTAs before this one
   int before = 0;
-  for (int k = threadIdx.x; k < (int)blockIdx.x; k += RS_BLOCK) before += cta_count[k];
+  for (int k = threadIdx.x; k < (int)blockIdx.x; k += RS_BLOCK) {
+    const TvStat c = cta_stat[k];
+    before += c.mn == kmin ? (int)c.cmn : 0;
+  }
   before = __reduce_add_sync(0xffffffffu, before);
-  if (l == 0) ws[w] = before;
+  if (l == 0) wbefore[w] = before;
   __syncthreads();
   int off = 0;
-  for (int k = 0; k < RS_WARPS; ++k) off += ws[k];
-  __syncthreads();
+  for (int k = 0; k < RS_WARPS; ++k) off += wbefore[k];
+  __shared__ int wsum[RS_WARPS];
   const unsigned lt = lanemask_lt();
   const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(keys);
   const int64_t t0 = blockIdx.x * tiles_per_cta, t1 = min(num_tiles, t0 + tiles_per_cta);
@@ -169,13 +179,13 @@ __global__ void __launch_bounds__(RS_BLOCK)
       ball[r] = __ballot_sync(0xffffffffu, (flags >> r) & 1u);
       c += __popc(ball[r]);
     }
-    if (l == 0) ws[w] = c;
+    if (l == 0) wsum[w] = c;
     __syncthreads();
     int rank0 = off, tile_total = 0;
 #pragma unroll
     for (int k = 0; k < RS_WARPS; ++k) {
-      if (k < w) rank0 += ws[k];
-      tile_total += ws[k];
+      if (k < w) rank0 += wsum[k];
+      tile_total += wsum[k];
     }
     __syncthreads();
 #pragma unroll
@@ -518,7 +528,7 @@ size_t fgx_argsort_scratch_bytes(int64_t n) {
   if (n < 0) n = 0;
   const int64_t tiles = ceil_div(n, RS_TILE);
   size_t b = align_up(sizeof(SortState), 256);
-  b += align_up((size_t)TV_MAX_GRID * 4, 256);      // per-CTA counts of the two-valued path
+  b += align_up((size_t)TV_MAX_GRID * sizeof(TvStat), 256);  // per-CTA records of the two-valued path
   b += 2 * align_up((size_t)n * 4, 256);            // image ping-pong
   b += align_up((size_t)n * 4, 256);                // idx1 (idx0 is the caller's perm)
   b += align_up((size_t)tiles * 256 * 4 + 4, 256);  // block_hist[256][tiles]
@@ -559,8 +569,8 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   char* p = reinterpret_cast<char*>(scratch);
   SortState* st = reinterpret_cast<SortState*>(p);
   p += align_up(sizeof(SortState), 256);
-  int32_t* cta_count = reinterpret_cast<int32_t*>(p);
-  p += align_up((size_t)TV_MAX_GRID * 4, 256);
+  TvStat* cta_stat = reinterpret_cast<TvStat*>(p);
+  p += align_up((size_t)TV_MAX_GRID * sizeof(TvStat), 256);
   uint32_t* img0 = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)n * 4, 256);
   uint32_t* img1 = reinterpret_cast<uint32_t*>(p);
@@ -572,18 +582,16 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
 
   cudaError_t e = cudaMemsetAsync(st, 0, sizeof(SortState), s);
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
-  e = cudaMemsetAsync(&st->kmin, 0xFF, sizeof(uint32_t), s);  // kmin starts at 0xFFFFFFFF
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
   const int g = grid_for(n, 256, 8);
-  sort_minmax_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, st);
   // two-valued fast path (contiguous tile range per CTA)
   const int64_t tv_tiles = ceil_div(n, TV_TILE);
   int64_t cap = (int64_t)sm_count() * 8;
   if (cap > TV_MAX_GRID) cap = TV_MAX_GRID;
   const int64_t per = ceil_div(tv_tiles, tv_tiles < cap ? tv_tiles : cap);
   const int tv_grid = (int)ceil_div(tv_tiles, per);
-  sort_two_count_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count);
-  sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_count, perm);
+  sort_two_stats_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, cta_stat);
+  sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_stat, perm);
   // general path (returns at once when st->done)
   static const bool multi = [] { const char* v = getenv("FGX_SORT_MULTI"); return v && atoi(v) == 1; }();
   if (!multi) {

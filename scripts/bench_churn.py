@@ -84,6 +84,25 @@ tick_ms = t0.elapsed_time(t1) / args.ticks
 for _ in range(args.ticks):
     tick(True)
 acc /= args.ticks
+# the same tick replayed as ONE CUDA graph (no Python / launch overhead between the ~20 kernels)
+from foragax_b200.graphs import GraphedTick  # noqa: E402
+
+
+def graph_tick(state):
+    s.agents = state
+    tick(False)
+    return s.agents, fgx_methods.count_active(s.agents)
+
+
+g = GraphedTick(graph_tick, s.agents, warmup=1)
+for _ in range(3):
+    g.replay()
+t0.record()
+for _ in range(args.ticks):
+    g.replay()
+t1.record()
+torch.cuda.synchronize()
+graph_ms = t0.elapsed_time(t1) / args.ticks
 n_act = float(np.mean(active_hist))
 k = 0.05 * n_act
 ROW = 28  # Dice row bytes
@@ -97,12 +116,12 @@ alg = {  # algorithmic bytes per op
 peak = 6509.1
 if os.path.exists("MEASURED_PEAKS.json"):
     peak = json.load(open("MEASURED_PEAKS.json")).get("hbm_gbs", peak)
-print(f"C5 churn: {N} slots, ~{n_act:.0f} active, D{SIDES}; tick {tick_ms:.3f} ms "
+print(f"C5 churn: {N} slots, ~{n_act:.0f} active, D{SIDES}; graph-replayed tick {graph_ms:.3f} ms; eager tick {tick_ms:.3f} ms "
       f"({N / tick_ms / 1e3:.1f} M slot-steps/s, {n_act / tick_ms / 1e3:.1f} M active agent-steps/s)")
 rows = {}
 for name, ms in zip(ops, acc):
     gbs = alg[name] / (ms * 1e-3) / 1e9
     rows[name] = {"ms": float(ms), "alg_bytes": float(alg[name]), "gbs": gbs, "frac_of_hbm": gbs / peak}
     print(f"  {name:14s} {ms:8.3f} ms   {alg[name] / 1e6:9.1f} MB algorithmic   {gbs:8.1f} GB/s   {gbs / peak:5.2f} of HBM")
-print(json.dumps({"config": "C5", "slots": N, "active": n_act, "tick_ms": tick_ms,
-                  "slot_steps_per_sec": N / (tick_ms * 1e-3), "ops": rows, "hbm_peak_gbs": peak}))
+print(json.dumps({"config": "C5", "slots": N, "active": n_act, "tick_ms": tick_ms, "graph_tick_ms": graph_ms,
+                  "slot_steps_per_sec": N / (tick_ms * 1e-3), "slot_steps_per_sec_graph": N / (graph_ms * 1e-3), "ops": rows, "hbm_peak_gbs": peak}))
