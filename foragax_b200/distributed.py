@@ -175,3 +175,98 @@ def global_pack_active(agents, sort_active, n_active_local=None):
         return out.view(src.dtype).reshape(src.shape)
 
     return sort_active(struct.tree_map(exchange, agents))
+
+
+def global_add_range(n_selected_local, n_active_local, n_local, lo, n_total):
+    """``add_agents`` over a globally packed, block-sharded set (agent_methods.py:26-38 + the caller's clip
+    ``min(n_selected, N - n_active)``, README.md:124-125): the new rows are the GLOBAL slots
+    ``[a, a + k)`` with ``a`` = total active, ``k`` = clipped total of selected parents.
+
+    Returns device scalars ``(k, local_count, j0)``: this rank adds ``local_count`` rows -- they start at its
+    local active count, because :func:`global_pack_active` left its actives at the local front -- and its
+    first new row is number ``j0`` of the global add order (index into the global parent list / key
+    chain).  One all-gather of two counts; nothing is read back to the host."""
+    r, w = world()
+    dev = n_active_local.device
+    pair = torch.stack([n_selected_local.reshape(()).to(torch.int64), n_active_local.reshape(()).to(torch.int64)])
+    if w > 1:
+        flat = torch.empty(w * 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat, pair)
+        allp = flat.view(w, 2)
+        sel, act = allp[:, 0].sum(), allp[:, 1].sum()
+    else:
+        sel, act = pair[0], pair[1]
+    k = torch.minimum(sel, n_total - act)
+    start = torch.clamp(act - lo, 0, n_local)
+    end = torch.clamp(act + k - lo, 0, n_local)
+    return k.to(torch.int32), (end - start).to(torch.int32), (start + lo - act).to(torch.int32)
+
+
+def plan_parent_splits(selected_counts, active_counts, shard_sizes):
+    """Integer plan of :func:`fetch_parent_rows`: ``splits[s][d]`` = parent rows rank s sends to rank d.
+    Rank s holds the parents number ``[S_s, S_s + c_s)`` of the global selection (``S`` = exclusive prefix
+    of the selected counts); parent j seeds the new row at global slot ``a + j`` (``j < k``), owned by the
+    rank whose block contains it.  Both maps are monotone in j, so every (s, d) piece is one contiguous run."""
+    w = len(shard_sizes)
+    c = [int(v) for v in selected_counts]
+    n = [int(v) for v in shard_sizes]
+    a = sum(int(v) for v in active_counts)
+    k = min(sum(c), sum(n) - a)
+    bounds = [0]
+    for v in n:
+        bounds.append(bounds[-1] + v)
+    splits, before = [], 0
+    for s_rank in range(w):
+        j_lo, j_hi = min(before, k), min(before + c[s_rank], k)
+        splits.append([max(0, min(a + j_hi, bounds[d + 1]) - max(a + j_lo, bounds[d])) for d in range(w)])
+        before += c[s_rank]
+    return splits
+
+
+def fetch_parent_rows(agents, selected_ids, n_selected_local, n_active_local, take_rows):
+    """Parent rows for this rank's new slots: every rank gathers the rows of its selected
+    parents (``take_rows(agents, ids) -> agents`` = the native row gather; ``selected_ids`` is the local select
+    permutation, parents first), and one all-to-all per leaf delivers them to the ranks that own the new
+    slots ``[a, a + k)``.  Returns a pytree whose row leaves hold, in order, the parent of each of this rank's
+    new rows (``global_add_range``'s ``local_count`` rows).  Split sizes are host integers (one read-back of
+    2 counts per rank)."""
+    from . import struct
+    r, w = world()
+    n_local = agents.active_state.shape[0]
+    dev = agents.active_state.device
+    trio = torch.stack([torch.as_tensor(n_selected_local, device=dev).reshape(()).to(torch.int64),
+                        torch.as_tensor(n_active_local, device=dev).reshape(()).to(torch.int64),
+                        torch.as_tensor(n_local, device=dev, dtype=torch.int64)])
+    if w > 1:
+        flat3 = torch.empty(w * 3, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat3, trio)
+        allt = flat3.view(w, 3)
+    else:
+        allt = trio.reshape(1, 3)
+    sel, act, sizes = (allt[:, i].tolist() for i in range(3))
+    splits = plan_parent_splits(sel, act, sizes)
+    send = splits[r]
+    recv = [splits[s_rank][r] for s_rank in range(w)]
+    n_send, n_recv = sum(send), sum(recv)
+    # parents this rank contributes: the first n_send of its selected list (the clip drops the global tail)
+    skip = sum(sel[:r])
+    a_tot, k = sum(act), min(sum(sel), sum(sizes) - sum(act))
+    assert n_send == max(0, min(skip + sel[r], k) - min(skip, k))
+    parents = take_rows(agents, selected_ids[:n_send].contiguous())
+
+    def exchange(leaf):
+        if not isinstance(leaf, torch.Tensor) or leaf.dim() == 0 or leaf.shape[0] != n_send:
+            return leaf
+        src = leaf.contiguous()
+        row = 1
+        for d in src.shape[1:]:
+            row *= int(d)
+        flat = src.reshape(n_send, row).view(torch.uint8)
+        out = torch.empty((n_recv, flat.shape[1]), dtype=torch.uint8, device=src.device)
+        if w > 1:
+            dist.all_to_all_single(out, flat, recv, send)
+        else:
+            out.copy_(flat)
+        return out.view(src.dtype).reshape((n_recv,) + tuple(src.shape[1:]))
+
+    return struct.tree_map(exchange, parents)

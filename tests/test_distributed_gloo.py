@@ -156,3 +156,56 @@ def test_plan_pack_splits_is_a_bijection():
         sp = plan_pack_splits(a, n)
         assert [sum(row) for row in sp] == n                          # every rank sends all its rows
         assert [sum(sp[s][d] for s in range(w)) for d in range(w)] == n  # and receives a full shard
+
+
+# ---- distributed add: which rows each rank adds, and the parent rows it needs ---------------------------
+def _add_worker(rank, world, port, n, seed, sizes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import struct
+    full = _torch_sort_active(_make_set(n, seed))          # globally packed set, as global_pack_active leaves it
+    lo, hi = sum(sizes[:rank]), sum(sizes[:rank + 1])
+    mine = struct.tree_map(lambda x: x[lo:hi].clone(), full)
+    sel_mask = (mine.state.content['flag'] & (mine.active_state != 0)).numpy()
+    cnt, perm = oam.select_from_mask(sel_mask)
+    n_act = (mine.active_state != 0).sum()
+    k, local_count, j0 = fd.global_add_range(torch.tensor(int(cnt)), n_act, hi - lo, lo, n)
+    take = lambda a, ids: struct.tree_map(lambda x: x[ids.long()] if x.dim() and x.shape[0] == hi - lo else x, a)  # noqa: E731
+    parents = fd.fetch_parent_rows(mine, torch.from_numpy(perm), torch.tensor(int(cnt)), n_act, take)
+    q.put((rank, int(k), int(local_count), int(j0), [x.numpy() for x in struct.tree_leaves(parents)]))
+    dist.destroy_process_group()
+
+
+def test_distributed_add_range_and_parent_rows():
+    from foragax_b200 import struct
+    ctx = mp.get_context("spawn")
+    for world, n, sizes in ((2, 400, [200, 200]), (3, 301, [100, 1, 200])):
+        seed = 11 + world
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_add_worker, args=(r, world, port, n, seed, sizes, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        full = _torch_sort_active(_make_set(n, seed))
+        act = full.active_state.numpy() != 0
+        a = int(act.sum())
+        sel = full.state.content['flag'].numpy() & act
+        _, gperm = oam.select_from_mask(sel)
+        k = min(int(sel.sum()), n - a)
+        ref_parents = struct.tree_map(lambda x: x[torch.from_numpy(gperm[:k]).long()], full)  # parent of new slot a + j
+        ref_leaves = [x.numpy() for x in struct.tree_leaves(ref_parents)]
+        assert k > 0
+        for rank, kk, local_count, j0, leaves in res:
+            lo, hi = sum(sizes[:rank]), sum(sizes[:rank + 1])
+            want_lo, want_hi = min(max(a, lo), hi), min(max(a + k, lo), hi)     # [a, a+k) cut by this block
+            assert kk == k and local_count == want_hi - want_lo
+            if local_count:
+                assert j0 == want_lo - a
+            for got, want in zip(leaves, ref_leaves):
+                np.testing.assert_array_equal(got, want[want_lo - a:want_hi - a] if local_count else want[:0])

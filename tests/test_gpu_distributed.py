@@ -69,3 +69,72 @@ def test_two_gpu_pack_active_equals_single_gpu_sort():
     total_active = res[0][3]
     # actives are packed at the GLOBAL front: rank 0's shard fills up before rank 1 gets any
     assert res[0][2] == min(total_active, n // 2) and res[0][2] + res[1][2] == total_active
+
+
+def _churn_worker(rank, world, port, n, ticks, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import random as fgx_random
+    from foragax_b200 import struct
+    from foragax_b200.examples.hello_world import is_value, make_dice
+    sides = 20
+    D = make_dice(sides)
+    rows = lambda t, f: struct.tree_map(lambda x: f(x) if x.dim() and x.shape[0] == n else x, t)  # noqa: E731
+    s = fgx_classes.Agent_Set(agent=D, num_total_agents=n, num_active_agents=n // 2, agent_type=0)
+    s.agents = fgx_methods.create_agents(None, s, fgx_random.PRNGKey(9))
+    lo, hi = fd.shard_bounds(n)
+    n_local = hi - lo
+    mine = rows(s.agents, lambda x: x[lo:hi].clone())       # this rank's block of the same initial set
+    local = fgx_classes.Agent_Set(agent=D, num_total_agents=n_local, num_active_agents=0, agent_type=0)
+    sort_active = lambda a: fgx_methods.jit_sort_agents(a.active_state, False, a)[0]  # noqa: E731
+    ok = True
+    for _ in range(ticks):
+        # single-GPU tick on the full set (every rank computes it: the reference result)
+        s.agents = fgx_methods.step_agents(None, None, s)
+        n_dead, rem = fgx_methods.jit_select_agents(is_value(1), None, s.agents)
+        s.agents = fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}),
+                                                 s.agents)
+        s.agents = sort_active(s.agents)
+        n_add, _ = fgx_methods.jit_select_agents(is_value(sides), None, s.agents)
+        n_add = torch.minimum(n_add, n - fgx_methods.count_active(s.agents))
+        s.agents, _ = fgx_methods.jit_add_agents(D.add_agent, n_add, None, s.agents, None)
+        # the same tick on the sharded set: local step / select / remove, global pack, global add range
+        local.agents = mine
+        mine = fgx_methods.step_agents(None, None, local)
+        n_dead, rem = fgx_methods.jit_select_agents(is_value(1), None, mine)
+        mine = fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}),
+                                             mine)
+        mine = fd.global_pack_active(mine, sort_active, fgx_methods.count_active(mine))
+        n_sel, _ = fgx_methods.jit_select_agents(is_value(sides), None, mine)
+        k, local_count, _ = fd.global_add_range(n_sel, fgx_methods.count_active(mine), n_local, lo, n)
+        mine, _ = fgx_methods.jit_add_agents(D.add_agent, local_count, None, mine, None)
+        ok = ok and all(torch.equal(g, r[lo:hi]) for g, r in zip(struct.tree_leaves(mine), struct.tree_leaves(s.agents))
+                        if r.dim() and r.shape[0] == n)
+    q.put((rank, ok, int(fgx_methods.count_active(mine)), int(fgx_methods.count_active(s.agents))))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_churn_ticks_equal_single_gpu():
+    """step -> select -> remove -> GLOBAL sort (all-to-all) -> select -> clip -> GLOBAL add, 6 ticks on two
+    ranks: every rank's block equals the single-GPU set after every tick, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n = 2, 100_000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_churn_worker, args=(r, world, port, n, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res)
+    assert res[0][2] + res[1][2] == res[0][3]
