@@ -38,6 +38,14 @@ class Leaf(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("row_bytes", i64)]
 
 
+MAX_PEERS = 8
+MAX_PEER_LEAVES = 16
+
+
+class PeerLeaf(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp * MAX_PEERS), ("row_bytes", i64)]
+
+
 class Walls(C.Structure):
     _fields_ = [("x1", vp), ("y1", vp), ("x2", vp), ("y2", vp), ("n", i64)]
 
@@ -62,6 +70,7 @@ _decl("fgx_select", C.c_int, C.POINTER(Predicate), i64, vp, vp, vp, sz, vp)
 _decl("fgx_argsort_scratch_bytes", sz, i64)
 _decl("fgx_argsort", C.c_int, vp, i32, i64, i32, vp, vp, sz, vp)
 _decl("fgx_gather_rows", C.c_int, C.POINTER(Leaf), i32, vp, i64, vp)
+_decl("fgx_pack_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, vp, i64, vp, C.POINTER(i64), i32, i32, vp)
 _decl("fgx_count_active", C.c_int, vp, i64, vp, vp)
 _decl("fgx_create_base", C.c_int, C.POINTER(u32), i64, i64, i32, vp, vp, vp, vp, vp)
 _decl("fgx_create_base_shard", C.c_int, C.POINTER(u32), i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, vp)

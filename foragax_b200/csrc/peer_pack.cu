@@ -1,0 +1,189 @@
+// K3 across GPUs: sort_agents(active_state, descending) of a block-sharded set as ONE kernel that does
+// the compaction and its exchange -- every rank scatters its rows straight into the peers' buffers
+// (stores over NVLink / NVSwitch into peer-mapped memory), at the slots the rows have in the GLOBAL stable
+// order "all actives in slot order, then all inactives" (agent_methods.py:74-79 applied to the whole set).
+//
+// Inputs per rank: its local stable partition (fgx_select: front = active rows ascending, then the rest), the
+// all-gathered front counts (device int64[world]; read on device, no host round trip) and, per leaf, the
+// destination buffer of EVERY rank.  Position p of the local partition is row perm[p]; its global
+// position is A_before + p for a front row and A_total + I_before + (p - count) otherwise, which fixes the
+// owning rank and the slot.  Consecutive positions go to consecutive slots, so the peer stores coalesce.
+// The caller orders the launches across ranks (a collective after the kernel: nobody reads a
+// destination buffer before every rank's scatter has completed).  HBM / NVLink bytes: row_bytes per
+// slot read locally, row_bytes per slot written (locally or to a peer), 4 B of index.
+#include "common.cuh"
+
+namespace fgx {
+
+struct PeerTable {
+  fgx_peer_leaf_t leaf[FGX_MAX_PEER_LEAVES];
+  int32_t vec[FGX_MAX_PEER_LEAVES];
+  int64_t bounds[FGX_MAX_PEERS + 1];
+  int32_t rank, world;
+};
+
+struct PackPlan {
+  int64_t a_before, a_total, i_before, count;
+};
+
+__device__ __forceinline__ PackPlan pack_plan(const PeerTable& tab, const int64_t* __restrict__ front_counts,
+                                              const int32_t* __restrict__ n_front) {
+  PackPlan pl{0, 0, 0, (int64_t)__ldg(n_front)};
+  for (int k = 0; k < tab.world; ++k) {
+    const int64_t c = __ldg(front_counts + k);
+    if (k < tab.rank) pl.a_before += c;
+    pl.a_total += c;
+  }
+  pl.i_before = tab.bounds[tab.rank] - pl.a_before;
+  return pl;
+}
+
+// global position of local partition position p -> (owner rank, slot)
+__device__ __forceinline__ void pack_dest(const PeerTable& tab, const PackPlan& pl, int64_t p, int& d, int64_t& slot) {
+  const int64_t g = p < pl.count ? pl.a_before + p : pl.a_total + pl.i_before + (p - pl.count);
+  d = 0;
+  while (d + 1 < tab.world && g >= tab.bounds[d + 1]) ++d;
+  slot = g - tab.bounds[d];
+}
+
+template <typename T>
+__device__ __forceinline__ void pack_narrow(const PeerTable& tab, const PackPlan& pl, int li,
+                                            const int32_t* __restrict__ perm, int64_t n) {
+  const fgx_peer_leaf_t& lf = tab.leaf[li];
+  const int64_t chunks = lf.row_bytes / (int64_t)sizeof(T);
+  const T* __restrict__ src = reinterpret_cast<const T*>(lf.src);
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p0 < n; p0 += 4 * nthreads) {
+    int64_t s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = p0 + u * nthreads;
+      s[u] = p < n ? (int64_t)__ldg(perm + p) : 0;
+    }
+    if (chunks == 1) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + s[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t p = p0 + u * nthreads;
+        if (p < n) {
+          int d;
+          int64_t slot;
+          pack_dest(tab, pl, p, d, slot);
+          reinterpret_cast<T*>(lf.dst[d])[slot] = v[u];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t p = p0 + u * nthreads;
+        if (p < n) {
+          int d;
+          int64_t slot;
+          pack_dest(tab, pl, p, d, slot);
+          T* dst = reinterpret_cast<T*>(lf.dst[d]) + slot * chunks;
+          for (int64_t c = 0; c < chunks; ++c) dst[c] = __ldg(src + s[u] * chunks + c);
+        }
+      }
+    }
+  }
+}
+
+// grid.y = leaf; narrow leaves: one thread per row
+__global__ void __launch_bounds__(256) pack_narrow_kernel(const __grid_constant__ PeerTable tab,
+                                                          const int32_t* __restrict__ perm,
+                                                          const int32_t* __restrict__ n_front,
+                                                          const int64_t* __restrict__ front_counts, int64_t n) {
+  const PackPlan pl = pack_plan(tab, front_counts, n_front);
+  switch (tab.vec[blockIdx.y]) {
+    case 16: pack_narrow<uint4>(tab, pl, blockIdx.y, perm, n); break;
+    case 8: pack_narrow<uint2>(tab, pl, blockIdx.y, perm, n); break;
+    case 4: pack_narrow<uint32_t>(tab, pl, blockIdx.y, perm, n); break;
+    case 2: pack_narrow<uint16_t>(tab, pl, blockIdx.y, perm, n); break;
+    default: pack_narrow<uint8_t>(tab, pl, blockIdx.y, perm, n); break;
+  }
+}
+
+// wide leaves (per-agent weight matrices): one warp per row, lanes stride the chunks
+__global__ void __launch_bounds__(256) pack_wide_kernel(const __grid_constant__ PeerTable tab,
+                                                        const int32_t* __restrict__ perm,
+                                                        const int32_t* __restrict__ n_front,
+                                                        const int64_t* __restrict__ front_counts, int64_t n) {
+  const PackPlan pl = pack_plan(tab, front_counts, n_front);
+  const fgx_peer_leaf_t& lf = tab.leaf[blockIdx.y];
+  const int v = tab.vec[blockIdx.y];
+  const int64_t chunks = lf.row_bytes / v;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; p < n; p += nwarps) {
+    const int64_t s = __ldg(perm + p);
+    int d;
+    int64_t slot;
+    pack_dest(tab, pl, p, d, slot);
+    const char* __restrict__ src = reinterpret_cast<const char*>(lf.src) + s * lf.row_bytes;
+    char* dst = reinterpret_cast<char*>(lf.dst[d]) + slot * lf.row_bytes;
+    for (int64_t c = lane; c < chunks; c += 32) {
+      if (v == 16) reinterpret_cast<uint4*>(dst)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+      else if (v == 8) reinterpret_cast<uint2*>(dst)[c] = __ldg(reinterpret_cast<const uint2*>(src) + c);
+      else if (v == 4) reinterpret_cast<uint32_t*>(dst)[c] = __ldg(reinterpret_cast<const uint32_t*>(src) + c);
+      else if (v == 2) reinterpret_cast<uint16_t*>(dst)[c] = __ldg(reinterpret_cast<const uint16_t*>(src) + c);
+      else dst[c] = __ldg(src + c);
+    }
+  }
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm,
+                       const int32_t* n_front, int64_t n_local, const int64_t* front_counts,
+                       const int64_t* bounds_host, int32_t rank, int32_t world, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(world >= 1 && world <= FGX_MAX_PEERS && rank >= 0 && rank < world, "fgx_pack_rows_peer: bad rank / world");
+  FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_PEER_LEAVES, "fgx_pack_rows_peer: at most %d leaves per call",
+              FGX_MAX_PEER_LEAVES);
+  FGX_REQUIRE(bounds_host, "fgx_pack_rows_peer: null bounds");
+  for (int k = 0; k < world; ++k)
+    FGX_REQUIRE(bounds_host[k] <= bounds_host[k + 1], "fgx_pack_rows_peer: shard bounds must ascend");
+  FGX_REQUIRE(bounds_host[0] == 0 && bounds_host[rank + 1] - bounds_host[rank] == n_local,
+              "fgx_pack_rows_peer: n_local does not match this rank's shard bounds");
+  FGX_REQUIRE(n_local >= 0 && n_local < (1ll << 31), "fgx_pack_rows_peer: n_local out of range");
+  if (n_local == 0 || n_leaves == 0) return FGX_OK;
+  FGX_REQUIRE(leaves_host && perm && n_front && front_counts, "fgx_pack_rows_peer: null pointer");
+  PeerTable narrow, wide;
+  int nn = 0, nw = 0;
+  for (int k = 0; k < n_leaves; ++k) {
+    const fgx_peer_leaf_t& lf = leaves_host[k];
+    FGX_REQUIRE(lf.src && lf.row_bytes > 0, "fgx_pack_rows_peer: leaf %d is malformed", k);
+    uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | (uintptr_t)lf.row_bytes;
+    for (int d = 0; d < world; ++d) {
+      FGX_REQUIRE(lf.dst[d], "fgx_pack_rows_peer: leaf %d has no destination on rank %d", k, d);
+      FGX_REQUIRE(lf.dst[d] != lf.src, "fgx_pack_rows_peer: leaf %d aliases its destination", k);
+      bits |= reinterpret_cast<uintptr_t>(lf.dst[d]);
+    }
+    int v = 16;
+    while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
+    PeerTable& t = lf.row_bytes / v <= 8 ? narrow : wide;
+    int& cnt = lf.row_bytes / v <= 8 ? nn : nw;
+    t.leaf[cnt] = lf;
+    t.vec[cnt++] = v;
+  }
+  for (PeerTable* t : {&narrow, &wide}) {
+    for (int k = 0; k <= world; ++k) t->bounds[k] = bounds_host[k];
+    t->rank = rank;
+    t->world = world;
+  }
+  cudaStream_t s = as_stream(stream);
+  if (nn) {
+    dim3 grid(grid_for(ceil_div(n_local, 4), 256, 8), nn);
+    pack_narrow_kernel<<<grid, 256, 0, s>>>(narrow, perm, n_front, front_counts, n_local);
+  }
+  if (nw) {
+    dim3 grid(grid_for(n_local * 32, 256, 8), nw);
+    pack_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n_front, front_counts, n_local);
+  }
+  return check_launch("fgx_pack_rows_peer");
+}
+}

@@ -1,0 +1,110 @@
+"""Block-sharded agent state in peer-mapped (symmetric) device memory, and the global "actives first" pack as
+ONE kernel per rank that compacts and exchanges at once (``fgx_pack_rows_peer``: stores over NVLink /
+NVSwitch straight into the destination ranks' buffers).
+
+``distributed.global_pack_active`` does the same job with NCCL: local sort, counts to the HOST (the
+collective needs split sizes), one all-to-all per leaf, local sort again.  Here nothing leaves the device:
+the local stable partition (``fgx_select``) is never materialised as sorted rows -- each row is written
+once, directly to its slot of the global order on whichever GPU owns it -- and the only collectives are an
+all-gather of one count per rank and the all-reduce that orders the ranks afterwards.
+
+The state is double-buffered (the pack reads buffer set ``cur`` and writes set ``1 - cur`` on every rank),
+so a rank never overwrites rows a peer may still be reading: set ``1 - cur`` was last READ by the pack two
+generations ago, and every rank passed the ordering all-reduce since.
+
+Requires ``active_state`` to hold flags (1.0 / 0.0, agent_methods.py:14): the order is the stable partition
+by ``active_state != 0``, which is what ``argsort(-active_state)`` gives for flags.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import struct
+from .base.predicates import P
+
+
+class PeerPackedSet:
+    def __init__(self, agents, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > L.MAX_PEERS:
+            raise L.FgxError(f"at most {L.MAX_PEERS} ranks of one node")
+        dev = agents.active_state.device
+        self.n_local = int(agents.active_state.shape[0])
+        sizes = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([self.n_local], dtype=torch.int64, device=dev), group=self.group)
+        self.bounds = [0]
+        for v in sizes.tolist():  # once, at construction
+            self.bounds.append(self.bounds[-1] + int(v))
+        self.n_max = max(self.bounds[i + 1] - self.bounds[i] for i in range(self.world))
+        self._template = agents
+        leaves = struct.tree_leaves(agents)
+        self._is_row = [x.dim() > 0 and x.shape[0] == self.n_local for x in leaves]
+        # one symmetric allocation per buffer set; every rank uses the layout of the LARGEST shard so that a
+        # leaf sits at the same offset on every rank
+        self._offsets, off = [], 0
+        for x, row in zip(leaves, self._is_row):
+            self._offsets.append(off)
+            if row:
+                row_bytes = x.element_size() * (x.numel() // max(self.n_local, 1)) if self.n_local else x.element_size()
+                off += (row_bytes * self.n_max + 255) // 256 * 256
+        self._row_bytes = [x.element_size() * (x.numel() // self.n_local) if row and self.n_local else 0
+                           for x, row in zip(leaves, self._is_row)]
+        total = max(off, 256)
+        self._bufs, self._ptrs, self._handles = [], [], []
+        for _ in range(2):
+            buf = symm.empty(total, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(buf, self.group)
+            self._bufs.append(buf)
+            self._handles.append(hdl)
+            self._ptrs.append([int(p) for p in hdl.buffer_ptrs])
+        self._views = [self._make_views(b, leaves) for b in self._bufs]
+        for v, x, row in zip(self._views[0], leaves, self._is_row):
+            if row:
+                v.copy_(x)
+        self.cur = 0
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._counts = torch.empty(self.world, dtype=torch.int64, device=dev)
+        self._bounds_c = (C.c_int64 * (self.world + 1))(*self.bounds)
+        dist.all_reduce(self._token, group=self.group)  # every rank's buffers exist before anyone writes to them
+
+    def _make_views(self, buf, leaves):
+        out = []
+        for x, row, off in zip(leaves, self._is_row, self._offsets):
+            if not row:
+                out.append(x)
+                continue
+            nbytes = x.numel() * x.element_size()
+            out.append(buf[off:off + nbytes].view(x.dtype).reshape(x.shape))
+        return out
+
+    @property
+    def agents(self):
+        """The agent pytree over the CURRENT buffer set (in-place ops update it directly)."""
+        it = iter(self._views[self.cur])
+        return struct.tree_map(lambda x: next(it), self._template)
+
+    def pack_active(self):
+        """``sort_agents(active_state, descending)`` over the whole sharded set; returns the new local block."""
+        from .base.agent_methods import select_agents
+        agents = self.agents
+        count, perm = select_agents(lambda a, p: P(a.active_state).nonzero(), None, agents)
+        dist.all_gather_into_tensor(self._counts, count.reshape(1).to(torch.int64), group=self.group)
+        src, dst = self._views[self.cur], 1 - self.cur
+        rows = [(v, off, rb) for v, off, rb, row in zip(src, self._offsets, self._row_bytes, self._is_row) if row]
+        for s in range(0, len(rows), L.MAX_PEER_LEAVES):
+            part = rows[s:s + L.MAX_PEER_LEAVES]
+            arr = (L.PeerLeaf * len(part))()
+            for k, (v, off, rb) in enumerate(part):
+                arr[k].src = v.data_ptr()
+                arr[k].row_bytes = rb
+                for d in range(self.world):
+                    arr[k].dst[d] = self._ptrs[dst][d] + off
+            L.check(L.lib.fgx_pack_rows_peer(arr, len(part), L.ptr(perm), L.ptr(count), self.n_local,
+                                             L.ptr(self._counts), self._bounds_c, self.rank, self.world, L.stream()))
+        dist.all_reduce(self._token, group=self.group)  # orders the ranks: every scatter has landed
+        self.cur = dst
+        return self.agents

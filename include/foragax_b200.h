@@ -103,6 +103,23 @@ typedef struct {
  * for every leaf (jnp.take, indices clamped).  src and dst must not alias.  */
 int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
                     fgx_stream_t stream);
+/* sort_agents(active_state, descending) (agent_methods.py:74-79) over a set sharded in contiguous blocks
+ * across the GPUs of one node, compaction and exchange in ONE kernel: every rank scatters its rows into
+ * the peers' destination buffers (peer-mapped device memory, stores over NVLink) at their slots of the
+ * global stable order.  perm / n_front: this rank's stable partition from fgx_select (front = active).
+ * front_counts: device int64[world], the all-gathered n_front.  bounds_host: int64[world+1] shard
+ * bounds.  dst[d] of a leaf = that leaf's destination buffer on rank d (dst[rank] is local).  The caller
+ * must order the ranks (a collective after this call) before anyone reads a destination buffer.       */
+#define FGX_MAX_PEERS 8
+#define FGX_MAX_PEER_LEAVES 16
+typedef struct {
+  const void* src;
+  void* dst[FGX_MAX_PEERS];
+  int64_t row_bytes;
+} fgx_peer_leaf_t;
+int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm,
+                       const int32_t* n_front, int64_t n_local, const int64_t* front_counts,
+                       const int64_t* bounds_host, int32_t rank, int32_t world, fgx_stream_t stream);
 /* jnp.sum(active_state, dtype=int32) (agent_methods.py:27): out int32[1] */
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream);
 /* the argument construction of create_agents (agent_methods.py:10-15), fused:

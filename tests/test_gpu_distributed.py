@@ -138,3 +138,71 @@ def test_two_gpu_sharded_churn_ticks_equal_single_gpu():
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
     assert res[0][2] + res[1][2] == res[0][3]
+
+
+def _peer_worker(rank, world, port, n, ticks, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import random as fgx_random
+    from foragax_b200 import struct
+    from foragax_b200.examples.hello_world import is_value, make_dice
+    from foragax_b200.peer import PeerPackedSet
+    sides = 20
+    D = make_dice(sides)
+    s = fgx_classes.Agent_Set(agent=D, num_total_agents=n, num_active_agents=n // 2, agent_type=0)
+    s.agents = fgx_methods.create_agents(None, s, fgx_random.PRNGKey(4))
+    lo, hi = fd.shard_bounds(n)
+    n_local = hi - lo
+    mine = struct.tree_map(lambda x: x[lo:hi].clone() if x.dim() and x.shape[0] == n else x, s.agents)
+    st = PeerPackedSet(mine)
+    local = fgx_classes.Agent_Set(agent=D, num_total_agents=n_local, num_active_agents=0, agent_type=0)
+    sort_active = lambda a: fgx_methods.jit_sort_agents(a.active_state, False, a)[0]  # noqa: E731
+    ok = True
+    for _ in range(ticks):
+        s.agents = fgx_methods.step_agents(None, None, s)
+        n_dead, rem = fgx_methods.jit_select_agents(is_value(1), None, s.agents)
+        s.agents = fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}),
+                                                 s.agents)
+        s.agents = sort_active(s.agents)
+        n_add, _ = fgx_methods.jit_select_agents(is_value(sides), None, s.agents)
+        n_add = torch.minimum(n_add, n - fgx_methods.count_active(s.agents))
+        s.agents, _ = fgx_methods.jit_add_agents(D.add_agent, n_add, None, s.agents, None)
+        # sharded tick, state in peer-mapped memory: in-place local ops + ONE scatter kernel for the global pack
+        local.agents = st.agents
+        fgx_methods.step_agents(None, None, local)
+        n_dead, rem = fgx_methods.jit_select_agents(is_value(1), None, st.agents)
+        fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}), st.agents)
+        packed = st.pack_active()
+        n_sel, _ = fgx_methods.jit_select_agents(is_value(sides), None, packed)
+        k, local_count, _ = fd.global_add_range(n_sel, fgx_methods.count_active(packed), n_local, lo, n)
+        fgx_methods.jit_add_agents(D.add_agent, local_count, None, packed, None)
+        ok = ok and all(torch.equal(g, r[lo:hi]) for g, r in zip(struct.tree_leaves(st.agents), struct.tree_leaves(s.agents))
+                        if r.dim() and r.shape[0] == n)
+    q.put((rank, ok, int(fgx_methods.count_active(st.agents)), int(fgx_methods.count_active(s.agents))))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_peer_memory_pack_equals_single_gpu():
+    """The same sharded churn ticks with the state in symmetric memory and the global pack done by
+    fgx_pack_rows_peer (one kernel: compaction + stores into the peer's buffers over NVLink)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n = 2, 100_001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res)
+    assert res[0][2] + res[1][2] == res[0][3]
