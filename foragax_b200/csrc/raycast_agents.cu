@@ -51,11 +51,17 @@ __device__ __forceinline__ int cell_of(const GridDesc& g, float x, float y) {
   return cell_coord(y, g.y0, g.inv_cs, g.gy) * g.gx + cell_coord(x, g.x0, g.inv_cs, g.gx);
 }
 
-// histogram of points per cell; remembers each point's cell
+// histogram of points per cell; remembers each point's cell.  Points whose `active` flag is 0 (targets only:
+// an inactive target can never be hit, space_methods.py:92) get cell -1 and stay out of the grid.
 __global__ void __launch_bounds__(256) grid_count_kernel(GridDesc g, const float* __restrict__ x,
-                                                         const float* __restrict__ y, int64_t stride, int64_t n,
+                                                         const float* __restrict__ y,
+                                                         const float* __restrict__ active, int64_t stride, int64_t n,
                                                          int32_t* __restrict__ cell, uint32_t* __restrict__ count) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (active != nullptr && active[i * stride] == 0.0f) {
+      cell[i] = -1;
+      continue;
+    }
     const int c = cell_of(g, x[i * stride], y[i * stride]);
     cell[i] = c;
     atomicAdd(count + c, 1u);
@@ -131,30 +137,41 @@ __global__ void __launch_bounds__(256) grid_scatter_targets_kernel(const float* 
                                                                    int32_t* __restrict__ sorted_idx) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = cell[i];
+    if (c < 0) continue;  // inactive target
     const uint32_t pos = tstart[c] + atomicAdd(cursor + c, 1u);
     sorted[pos] = make_float4(tx[i * stride], ty[i * stride], tr[i * stride], ta[i * stride]);
     sorted_idx[pos] = (int32_t)i;
   }
 }
 
-__global__ void __launch_bounds__(256) grid_scatter_agents_kernel(int64_t n, const int32_t* __restrict__ cell,
-                                                                  const uint32_t* __restrict__ astart,
-                                                                  uint32_t* __restrict__ cursor,
-                                                                  int32_t* __restrict__ order) {
+// sensing agents in cell order: their index and a (x, y, heading, active | cell) record, so that the sensing
+// kernel reads everything it needs about agent number i of the order with independent, coalesced loads
+struct SensorRec {
+  float x, y, ang;
+  int32_t cell;  // -1: inactive sensor
+};
+
+__global__ void __launch_bounds__(256)
+    grid_scatter_agents_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ y,
+                               const float* __restrict__ ang, const float* __restrict__ active,
+                               const int32_t* __restrict__ cell, const uint32_t* __restrict__ astart,
+                               uint32_t* __restrict__ cursor, int32_t* __restrict__ order, SensorRec* __restrict__ rec) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = cell[i];
-    order[astart[c] + atomicAdd(cursor + c, 1u)] = (int32_t)i;
+    const uint32_t pos = astart[c] + atomicAdd(cursor + c, 1u);
+    order[pos] = (int32_t)i;
+    rec[pos] = SensorRec{x[i], y[i], ang[i], (active == nullptr || active[i] != 0.0f) ? c : -1};
   }
 }
 
 struct RaycastAgentsArgs {
   GridDesc g;
-  const float *ax, *ay, *aang, *aactive;  // sensing agents [n]
   int64_t n, m;
   int n_rays;
   float span, L, max_rad;
   const uint32_t* tstart;
-  const int32_t *order, *acell;
+  const int32_t* order;
+  const SensorRec* rec;  // sensing agents in cell order
   const float4* targets;
   const int32_t* tidx;
   int merge_walls;
@@ -182,23 +199,34 @@ __global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const
   const int RG = (a.n_rays + RA_G - 1) / RA_G;
   const float L = a.L;
   // far-target bound: a hit needs |s| <= L + r, i.e. c = |s|^2 - r^2 <= L^2 + 2 L r
-  const float L2 = f_mul(L, L), twoL = f_mul(2.0f, L);
-  const float reach = (L + a.max_rad) * 1.0001f, reach2 = reach * reach;
+  const float reach = (L + a.max_rad) * 1.0001f;
   const bool fan_convex = a.span < 1.5f;  // the whole fan is a convex cone: cells can be culled against it
   const float cs = 1.0f / a.g.inv_cs, cell_margin = 1e-3f * cs + 1e-3f;
   const int K = a.g.K;
   const int64_t n_warps = (int64_t)gridDim.x * RA_WARPS;
-  for (int64_t i = blockIdx.x * (int64_t)RA_WARPS + warp; i < a.n; i += n_warps) {
-    const int64_t agent = a.order[i];
-    if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {  // inactive sensor: zeros, as the reference's cond
+  int64_t i = blockIdx.x * (int64_t)RA_WARPS + warp;
+  int next_agent = 0;
+  int4 next_rec = make_int4(0, 0, 0, -1);
+  if (i < a.n) {
+    next_agent = a.order[i];
+    next_rec = *reinterpret_cast<const int4*>(a.rec + i);
+  }
+  for (; i < a.n; i += n_warps) {
+    const int64_t agent = next_agent;
+    const int4 rec = next_rec;
+    if (i + n_warps < a.n) {  // the next agent's record is in flight while this one is processed
+      next_agent = a.order[i + n_warps];
+      next_rec = *reinterpret_cast<const int4*>(a.rec + i + n_warps);
+    }
+    const int cell = rec.w;
+    if (cell < 0) {  // inactive sensor: zeros, as the reference's cond
       for (int r = lane; r < a.n_rays; r += 32) {
         a.dist[agent * a.n_rays + r] = 0.0f;
         a.hit[agent * a.n_rays + r] = -1;
       }
       continue;
     }
-    const int cell = a.acell[agent];
-    const float ox = a.ax[agent], oy = a.ay[agent], ang = a.aang[agent];
+    const float ox = __int_as_float(rec.x), oy = __int_as_float(rec.y), ang = __int_as_float(rec.z);
     float dx[RPL], dy[RPL], best[RPL], kb[RPL];
     int bidx[RPL];
     {
@@ -236,8 +264,12 @@ __global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const
     const float fax = bdx[0], fay = bdy[0], fbx = bdx[RA_G], fby = bdy[RA_G], fmx = fax + fbx, fmy = fay + fby;
 
     int cnt[RA_G];
+    float gm[RA_G];  // largest current minimum among a group's rays: a circle whose nearest point is farther cannot improve any
 #pragma unroll
-    for (int k = 0; k < RA_G; ++k) cnt[k] = 0;
+    for (int k = 0; k < RA_G; ++k) {
+      cnt[k] = 0;
+      gm[k] = L;
+    }
 
     // narrow phase, lanes = rays: every group walks its own survivor list, two entries per trip
     auto drain = [&]() {
@@ -282,71 +314,102 @@ __global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const
           }
         }
       }
+      float mb = 0.0f;  // lanes that own no ray contribute nothing
 #pragma unroll
-      for (int k = 0; k < RA_G; ++k) cnt[k] = 0;
+      for (int q = 0; q < RPL; ++q)
+        if (q * RA_GW + w < RG && ray_of(g, w, q, RG) < a.n_rays) mb = fmaxf(mb, best[q]);
+#pragma unroll
+      for (int d = 1; d < RA_GW; d <<= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, d));
+#pragma unroll
+      for (int k = 0; k < RA_G; ++k) {
+        gm[k] = __shfl_sync(0xffffffffu, mb, k * RA_GW);
+        cnt[k] = 0;
+      }
       __syncwarp();
     };
 
     const int cx = cell % a.g.gx, cy = cell / a.g.gx;
-    for (int step = 0; step <= 2 * K; ++step) {
-      // rows nearest first (cy, cy+1, cy-1, cy+2, ...): the minima settle early and the cheap rejection in
-      // drain() then skips the exact evaluation for most of the farther survivors
-      const int ry = cy + ((step & 1) ? (step + 1) / 2 : -(step / 2));
-      if (ry < 0 || ry >= a.g.gy) continue;
-      // cells of this row that can hold a target in reach and (convex fan) inside the widened fan; lane <-> cell
-      const int ccx = cx - K + lane;
-      bool keep = lane <= 2 * K && ccx >= 0 && ccx < a.g.gx;
-      if (keep) {
-        // rectangle of target centres in the cell, relative to the sensor; border cells are unbounded outwards
-        const float x0 = ccx == 0 ? -1e30f : (a.g.x0 + ccx * cs - cell_margin) - ox;
-        const float x1 = ccx == a.g.gx - 1 ? 1e30f : (a.g.x0 + (ccx + 1) * cs + cell_margin) - ox;
-        const float y0 = ry == 0 ? -1e30f : (a.g.y0 + ry * cs - cell_margin) - oy;
-        const float y1 = ry == a.g.gy - 1 ? 1e30f : (a.g.y0 + (ry + 1) * cs + cell_margin) - oy;
-        const float ddx = fmaxf(fmaxf(x0, -x1), 0.0f), ddy = fmaxf(fmaxf(y0, -y1), 0.0f);
-        keep = ddx * ddx + ddy * ddy <= reach2;
-        if (fan_convex) {
-          const float R = a.max_rad * 1.0001f + 1e-3f;
-          keep = keep && rect_max(-fay, fax, x0, x1, y0, y1) >= -R    // cross(d_first, p) >= -R
-                      && rect_max(fby, -fbx, x0, x1, y0, y1) >= -R    // cross(p, d_last) >= -R
-                      && rect_max(fmx, fmy, x0, x1, y0, y1) >= -2.0f * R;  // not behind the sensor
+    // Cells are visited in rings around the sensor's cell (ring r = Chebyshev distance r): the minima settle
+    // on the nearest targets first, after every ring the groups' largest minima are refreshed (drain), and
+    // the reach that the farther cells, targets and rings are culled against shrinks accordingly.
+    for (int ring = 0; ring <= K; ++ring) {
+      float gmax = gm[0];
+#pragma unroll
+      for (int k = 1; k < RA_G; ++k) gmax = fmaxf(gmax, gm[k]);
+      const float rdyn = fminf(reach, (gmax + a.max_rad) * 1.0001f + 1e-3f);
+      // every cell of ring r >= 2 is at least (r - 1) cells away from any point of the sensor's cell
+      if (ring >= 2 && (ring - 1) * cs - cell_margin > rdyn) break;
+      for (int dy = -ring; dy <= ring; ++dy) {
+        const int ry = cy + dy;
+        if (ry < 0 || ry >= a.g.gy) continue;
+        const bool full_row = dy == -ring || dy == ring;  // top / bottom row of the ring, else its two side cells
+        // a 3 x 3 neighbourhood (K == 1) takes the sensor's whole row at once: three segments instead of five
+        if (K == 1 && ring == 1 && !full_row) continue;
+        const int wide0 = (K == 1 && ring == 0) ? 1 : 0;
+        for (int part = 0; part < (full_row ? 1 : 2); ++part) {
+          const int c_first = (full_row || part == 0) ? cx - ring - wide0 : cx + ring;
+          const int c_last = full_row ? cx + ring + wide0 : c_first;
+          // cells that can hold a target in reach and (convex fan) inside the widened fan; lane <-> cell
+          const int ccx = c_first + lane;
+          bool keep = ccx <= c_last && ccx >= 0 && ccx < a.g.gx;
+          if (keep) {
+            // rectangle of target centres in the cell, relative to the sensor; border cells are unbounded outwards
+            const float x0 = ccx == 0 ? -1e30f : (a.g.x0 + ccx * cs - cell_margin) - ox;
+            const float x1 = ccx == a.g.gx - 1 ? 1e30f : (a.g.x0 + (ccx + 1) * cs + cell_margin) - ox;
+            const float y0 = ry == 0 ? -1e30f : (a.g.y0 + ry * cs - cell_margin) - oy;
+            const float y1 = ry == a.g.gy - 1 ? 1e30f : (a.g.y0 + (ry + 1) * cs + cell_margin) - oy;
+            const float ddx = fmaxf(fmaxf(x0, -x1), 0.0f), ddy = fmaxf(fmaxf(y0, -y1), 0.0f);
+            keep = ddx * ddx + ddy * ddy <= rdyn * rdyn;
+            if (fan_convex) {
+              const float R = a.max_rad * 1.0001f + 1e-3f;
+              keep = keep && rect_max(-fay, fax, x0, x1, y0, y1) >= -R    // cross(d_first, p) >= -R
+                          && rect_max(fby, -fbx, x0, x1, y0, y1) >= -R    // cross(p, d_last) >= -R
+                          && rect_max(fmx, fmy, x0, x1, y0, y1) >= -2.0f * R;  // not behind the sensor
+            }
+          }
+          const unsigned km = __ballot_sync(0xffffffffu, keep);
+          if (km == 0u) continue;
+          const int c_lo = ry * a.g.gx + c_first + (__ffs(km) - 1), c_hi = ry * a.g.gx + c_first + (31 - __clz(km));
+          const uint32_t r0 = a.tstart[c_lo], r1 = a.tstart[c_hi + 1];  // the row's cells are contiguous
+          for (uint32_t base = r0; base < r1; base += 32) {
+            // broad phase: lane <-> target
+            const uint32_t k = base + lane;
+            const bool in = k < r1;
+            const float4 t = a.targets[in ? k : r1 - 1];
+            const int id = a.tidx[in ? k : r1 - 1];
+            const float sx = f_sub(ox, t.x), sy = f_sub(oy, t.y);
+            const float c = f_sub(f_add(f_mul(sx, sx), f_mul(sy, sy)), f_mul(t.z, t.z));
+            // reach: a hit at distance <= m needs |s| <= m + r, i.e. c = |s|^2 - r^2 <= m (m + 2 r); m = the group's
+            // largest current minimum (ray_length at first), tested per group below
+            const bool pass = in && t.w != 0.0f;
+            const float two_r = t.z + t.z;
+            // a circle farther than r from the cone spanned by a group's rays cannot be hit by any of them.
+            // v = target - sensor = -s:  cross(bd, v) = bdy*sx - bdx*sy,  cross(v, bd) = -cross(bd, v)
+            const float slack = 1e-4f * (fabsf(sx) + fabsf(sy)) + 1e-6f;  // >> the rounding of t = -b - sqrt(b*b - c)
+            const float tol = t.z * 1.0001f + slack;
+            float cr[RA_G + 1];
+#pragma unroll
+            for (int k = 0; k <= RA_G; ++k) cr[k] = bdy[k] * sx - bdx[k] * sy;
+            const bool front_fan = -(fmx * sx + fmy * sy) >= -2.0f * tol;  // not behind the sensor (convex fan)
+            const float4 entry = make_float4(sx, sy, c, __int_as_float(id));
+            bool full = false;
+#pragma unroll
+            for (int gg = 0; gg < RA_G; ++gg) {
+              bool pg = pass && gok[gg] && cr[gg] >= -tol && cr[gg + 1] <= tol &&
+                        !(c > (gm[gg] + slack) * (gm[gg] + slack + two_r) * 1.0001f);
+              if (fan_convex) pg = pg && front_fan;
+              else pg = pg && -((bdx[gg] + bdx[gg + 1]) * sx + (bdy[gg] + bdy[gg + 1]) * sy) >= -2.0f * tol;
+              const unsigned m = __ballot_sync(0xffffffffu, pg);
+              if (pg) mine[gg][cnt[gg] + __popc(m & lt)] = entry;
+              cnt[gg] += __popc(m);
+              full = full || cnt[gg] > RA_CAP - 32;
+            }
+            if (full) drain();
+          }
         }
       }
-      const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (km == 0u) continue;
-      const int c_lo = ry * a.g.gx + cx - K + (__ffs(km) - 1), c_hi = ry * a.g.gx + cx - K + (31 - __clz(km));
-      const uint32_t r0 = a.tstart[c_lo], r1 = a.tstart[c_hi + 1];  // the row's cells are contiguous
-      for (uint32_t base = r0; base < r1; base += 32) {
-        // broad phase: lane <-> target
-        const uint32_t k = base + lane;
-        const bool in = k < r1;
-        const float4 t = a.targets[in ? k : r1 - 1];
-        const int id = a.tidx[in ? k : r1 - 1];
-        const float sx = f_sub(ox, t.x), sy = f_sub(oy, t.y);
-        const float c = f_sub(f_add(f_mul(sx, sx), f_mul(sy, sy)), f_mul(t.z, t.z));
-        const bool pass = in && t.w != 0.0f && !(c > f_mul(f_add(L2, f_mul(twoL, t.z)), 1.0001f));
-        // a circle farther than r from the cone spanned by a group's rays cannot be hit by any of them.
-        // v = target - sensor = -s:  cross(bd, v) = bdy*sx - bdx*sy,  cross(v, bd) = -cross(bd, v)
-        const float tol = t.z * 1.0001f + 1e-4f * (fabsf(sx) + fabsf(sy)) + 1e-6f;
-        float cr[RA_G + 1];
-#pragma unroll
-        for (int k = 0; k <= RA_G; ++k) cr[k] = bdy[k] * sx - bdx[k] * sy;
-        const bool front_fan = -(fmx * sx + fmy * sy) >= -2.0f * tol;  // not behind the sensor (convex fan)
-        const float4 entry = make_float4(sx, sy, c, __int_as_float(id));
-        bool full = false;
-#pragma unroll
-        for (int gg = 0; gg < RA_G; ++gg) {
-          bool pg = pass && gok[gg] && cr[gg] >= -tol && cr[gg + 1] <= tol;
-          if (fan_convex) pg = pg && front_fan;
-          else pg = pg && -((bdx[gg] + bdx[gg + 1]) * sx + (bdy[gg] + bdy[gg + 1]) * sy) >= -2.0f * tol;
-          const unsigned m = __ballot_sync(0xffffffffu, pg);
-          if (pg) mine[gg][cnt[gg] + __popc(m & lt)] = entry;
-          cnt[gg] += __popc(m);
-          full = full || cnt[gg] > RA_CAP - 32;
-        }
-        if (full) drain();
-      }
+      drain();  // per ring: refreshes the groups' minima before the farther cells are culled against them
     }
-    drain();
 
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
@@ -375,6 +438,7 @@ static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 struct RaScratch {
   uint32_t *tcount, *acount, *tstart, *astart;
   int32_t *tcell, *acell, *order, *tidx;
+  SensorRec* rec;
   float4* sorted;
 };
 static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s) {
@@ -390,6 +454,7 @@ static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s)
   p = take((size_t)n * 4); if (s) s->order = (int32_t*)p;
   p = take((size_t)m * 4); if (s) s->tidx = (int32_t*)p;
   p = take((size_t)m * 16); if (s) s->sorted = (float4*)p;
+  p = take((size_t)n * 16); if (s) s->rec = (SensorRec*)p;
   return o;
 }
 
@@ -451,17 +516,17 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(s.tcount, 0, al256((size_t)n_cells * 4) * 2, st);  // tcount + acount
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_agents: %s", cudaGetErrorString(e));
-  if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, target_stride, n_targets, s.tcell, s.tcount);
-  grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, 1, n_agents, s.acell, s.acount);
+  if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, tactive, target_stride, n_targets, s.tcell, s.tcount);
+  grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, nullptr, 1, n_agents, s.acell, s.acount);
   grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, s.tcount, s.acount, s.tstart, s.astart);
   if (n_targets)
     grid_scatter_targets_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(tx, ty, trad, tactive, target_stride,
                                                                              n_targets, s.tcell, s.tstart, s.tcount,
                                                                              s.sorted, s.tidx);
-  grid_scatter_agents_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(n_agents, s.acell, s.astart, s.acount,
-                                                                        s.order);
-  RaycastAgentsArgs a{g, x, y, ang, active, n_agents, n_targets, n_rays, ray_span, ray_length, max_rad,
-                      s.tstart, s.order, s.acell, s.sorted, s.tidx, merge_walls ? 1 : 0, dist, hit};
+  grid_scatter_agents_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(n_agents, x, y, ang, active, s.acell, s.astart,
+                                                                        s.acount, s.order, s.rec);
+  RaycastAgentsArgs a{g, n_agents, n_targets, n_rays, ray_span, ray_length, max_rad,
+                      s.tstart, s.order, s.rec, s.sorted, s.tidx, merge_walls ? 1 : 0, dist, hit};
   // one warp per agent, walking the cell-sorted agent list (neighbouring warps share their targets in L1/L2)
   const int64_t ctas = ceil_div(n_agents, RA_WARPS);
   const int64_t cap = (int64_t)sm_count() * 16;
