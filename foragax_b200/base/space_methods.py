@@ -121,12 +121,20 @@ def create_space(x_min, x_max, y_min, y_max, torous, wall_array):
     return Space(x_min, x_max, y_min, y_max, torous, Wall(wall_begin_points, wall_end_points))
 
 
+GRID_MIN_WALLS = 32  # below this the all-pairs kernel is as fast as building the wall grid
+
+
 def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_rays=None, want_hit=True,
-                  out=None):
+                  out=None, bounds=None):
     """The fused hot loop: ``ray_generator`` + ``ray_wall_sensor`` over agents x rays x walls,
     reduced per ray to (min distance, first wall index attaining it or -1) -- what
     ``EcoEvoJax/sim.py:418-457`` computes for wall entities.  Returns
-    ``(dist float32[n,R], hit int32[n,R] | None)``; inactive agents get zeros / -1."""
+    ``(dist float32[n,R], hit int32[n,R] | None)``; inactive agents get zeros / -1.
+
+    ``bounds = (x_min, x_max, y_min, y_max)`` (the ``Space``'s extent) selects the spatially culled kernel
+    when there are enough walls for it to pay: per grid cell only the walls that can matter are tested.
+    The result is bit-identical to the all-pairs evaluation (``bounds=None``), agents outside the bounds
+    included."""
     x, y, ang = (_f32(a) for a in agent_pos)
     n = x.shape[0]
     r = int(RESOLUTION if n_rays is None else n_rays)
@@ -137,6 +145,14 @@ def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_r
     else:
         dist, hit = out
     w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
+    if bounds is not None and nw >= GRID_MIN_WALLS:
+        b = [float(v) for v in bounds]
+        nbytes = L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length))
+        scr = L.scratch(nbytes)
+        L.check(L.lib.fgx_raycast_walls_grid(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
+                                             float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2], b[3],
+                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), nbytes, L.stream()))
+        return dist, hit
     L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                     float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))
     return dist, hit

@@ -1,0 +1,313 @@
+// K1 with a spatial cull: the same agents x rays x walls reduction as fgx_raycast_walls, evaluated only
+// against the walls that can possibly produce a distance below ray_length -- bit-identical results.
+//
+// Reference: ray_wall_sensor (space_methods.py:96-143) + min / first-argmin over walls
+// (EcoEvoJax/sim.py:444-447).  The reference is all-pairs; a 1 M-agent arena with 1,000 walls has ~6 walls
+// anywhere near an agent.  A wall can yield d < L for a ray from p1 only if
+//   (a) the wall SEGMENT is within L (+ margin) of p1: proper crossings (d1) and the collinear
+//       touch cases d2, d3, d5 put a wall point inside the ray's bounding box; or
+//   (b) p1 lies within the float32 noise of the wall's infinite LINE: then the computed orientation
+//       signs o3 / o4 are arbitrary, `o1 != o2 && o3 != o4` can hold spuriously and the intercept
+//       formula (with its 1e-6 denominator bias) can return a point near p1 for a wall that is far
+//       away; likewise d4 = 0 needs o3 == 0 exactly.  The all-pairs kernel reproduces these cases,
+//       so the cull must not drop them.
+// Orientation determinants are accurate to ~4e-7 * S in distance units (S = coordinate scale), so the
+// cull uses eps_line = 1e-4 * S for (b) and margin = 5e-4 * S for (a) -- hundreds of times the noise.
+// Every listed (ray, wall) pair is evaluated by the same op-for-op code as the all-pairs kernel
+// (sure-miss filter on the four determinants, then ray_wall_exact), and ties resolve to the lowest
+// wall index, so the output equals fgx_raycast_walls bit for bit.
+//
+//   1. wall lists per cell of a uniform grid: one thread per (wall, grid column along the wall's major
+//      axis); in a column the wall's line occupies a short run of cells -- a band of half-width
+//      L + margin where the column is within reach of the segment, eps_line elsewhere (count pass,
+//      scan, fill pass);
+//   2. one thread per (agent, ray): the lanes of a warp share an agent (32 rays), read its cell's wall
+//      list (broadcast loads, wall data L1-resident) and test their own ray.
+// Agents outside the grid bounds, walls with coordinates beyond the declared scale and list overflow
+// fall back to the all-walls loop for the affected agents / launch (exact, just slower).
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace fgx {
+
+struct WGrid {
+  float x0, y0, cs, inv_cs;
+  int gx, gy;
+  float thick, eps, scale;  // band half-widths (perpendicular) and the coordinate scale they assume
+};
+
+struct WState {
+  uint32_t total;     // entries written by the fill pass
+  int32_t fallback;   // != 0: lists unusable (overflow / out-of-scale wall): every agent scans all walls
+};
+
+__device__ __forceinline__ int wg_coord(float v, float v0, float inv_cs, int n) {
+  const float f = floorf((v - v0) * inv_cs);
+  return f >= (float)(n - 1) ? n - 1 : (f > 0.0f ? (int)f : 0);
+}
+
+// cells of major-axis column `cu` whose agents may need wall (ax,ay)-(bx,by).  One thread per (wall, column):
+// in a column the wall's line occupies a short run of cells.  emit(cell) may be called for a cell by two
+// neighbouring columns' pads (harmless: evaluating a wall twice changes nothing).
+template <class F>
+__device__ __forceinline__ void wall_column_cells(const WGrid& g, float ax, float ay, float bx, float by, int cu, F emit) {
+  const bool xmajor = fabsf(bx - ax) >= fabsf(by - ay);
+  const int nu = xmajor ? g.gx : g.gy, nv = xmajor ? g.gy : g.gx;
+  if (cu >= nu) return;
+  float au = xmajor ? ax : ay, av = xmajor ? ay : ax, bu = xmajor ? bx : by, bv = xmajor ? by : bx;
+  if (au > bu) {
+    float t = au; au = bu; bu = t;
+    t = av; av = bv; bv = t;
+  }
+  const float du = bu - au;
+  const float m = du > 0.0f ? (bv - av) / du : 0.0f;  // |m| <= 1 along the major axis
+  const float wv = sqrtf(1.0f + m * m);                // perpendicular half-width -> extent along the minor axis
+  const float u0 = xmajor ? g.x0 : g.y0, v0 = xmajor ? g.y0 : g.x0;
+  const float pad = 0.02f * g.cs + 1e-5f * g.scale;    // cell assignment of agents on a cell edge, rounding here
+  // agents OUTSIDE the grid take the all-walls loop in the sensing kernel, so columns are the plain intervals
+  const float ulo = u0 + cu * g.cs - pad, uhi = u0 + (cu + 1) * g.cs + pad;
+  const bool thick = uhi >= au - g.thick && ulo <= bu + g.thick;
+  const float hw = (thick ? g.thick : g.eps) * wv + pad;
+  const float v1 = av + m * (ulo - au), v2 = av + m * (uhi - au);
+  const float vlo = fminf(v1, v2) - hw, vhi = fmaxf(v1, v2) + hw;
+  if (vhi < v0 || vlo > v0 + nv * g.cs) return;
+  const int c0 = wg_coord(vlo, v0, g.inv_cs, nv), c1 = wg_coord(vhi, v0, g.inv_cs, nv);
+  for (int cv = c0; cv <= c1; ++cv) emit(xmajor ? cv * g.gx + cu : cu * g.gx + cv);
+}
+
+__device__ __forceinline__ bool wall_in_scale(const WGrid& g, float ax, float ay, float bx, float by) {
+  const float s = g.scale;  // NaN coordinates fail every comparison -> out of scale
+  return fabsf(ax) <= s && fabsf(ay) <= s && fabsf(bx) <= s && fabsf(by) <= s;
+}
+
+// grid = (columns / 128, walls): thread <-> (wall, major-axis column)
+__global__ void __launch_bounds__(128) wall_count_kernel(WGrid g, const float* __restrict__ wx1,
+                                                         const float* __restrict__ wy1, const float* __restrict__ wx2,
+                                                         const float* __restrict__ wy2, int n_walls,
+                                                         uint32_t* __restrict__ count, WState* __restrict__ st) {
+  const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int w = blockIdx.y; w < n_walls; w += gridDim.y) {
+    const float ax = wx1[w], ay = wy1[w], bx = wx2[w], by = wy2[w];
+    if (!wall_in_scale(g, ax, ay, bx, by)) {
+      if (cu == 0) st->fallback = 1;
+      continue;
+    }
+    wall_column_cells(g, ax, ay, bx, by, cu, [&](int cell) { atomicAdd(count + cell, 1u); });
+  }
+}
+
+// single CTA exclusive scan (cells <= ~100k); the counts become the fill cursors (reset to 0)
+__global__ void __launch_bounds__(1024) wall_scan_kernel(int n_cells, uint32_t capacity, uint32_t* __restrict__ count,
+                                                         uint32_t* __restrict__ start, WState* __restrict__ st) {
+  __shared__ uint32_t carry;
+  __shared__ uint32_t wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  constexpr int ITEMS = 8;
+  for (int base = 0; base < n_cells; base += 1024 * ITEMS) {
+    const int c0 = base + threadIdx.x * ITEMS;
+    uint32_t v[ITEMS], tot = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      v[j] = c0 + j < n_cells ? count[c0 + j] : 0u;
+      tot += v[j];
+    }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (l >= d) inc += o;
+    }
+    if (l == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t run = carry + inc - tot;
+    for (int q = 0; q < w; ++q) run += wsum[q];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (c0 + j < n_cells) {
+        start[c0 + j] = run;
+        count[c0 + j] = 0;
+      }
+      run += v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    start[n_cells] = carry;
+    st->total = carry;
+    if (carry > capacity) st->fallback = 1;
+  }
+}
+
+__global__ void __launch_bounds__(128) wall_fill_kernel(WGrid g, const float* __restrict__ wx1,
+                                                        const float* __restrict__ wy1, const float* __restrict__ wx2,
+                                                        const float* __restrict__ wy2, int n_walls,
+                                                        const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                                        int32_t* __restrict__ entries, const WState* __restrict__ st) {
+  if (st->fallback) return;
+  const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int w = blockIdx.y; w < n_walls; w += gridDim.y)
+    wall_column_cells(g, wx1[w], wy1[w], wx2[w], wy2[w], cu,
+                      [&](int cell) { entries[start[cell] + atomicAdd(cursor + cell, 1u)] = w; });
+}
+
+struct WallsGridArgs {
+  WGrid g;
+  const float *ax, *ay, *aang, *aactive;
+  int64_t n;
+  int n_rays;
+  float span, L;
+  const float *wx1, *wy1, *wx2, *wy2;
+  int n_walls;
+  const uint32_t* start;
+  const int32_t* entries;
+  const WState* st;
+  float* dist;
+  int32_t* hit;
+};
+
+// one (ray, wall) pair, exactly as the all-pairs kernel decides it: sure miss <=> no candidate distance of
+// ray_wall_sensor can apply (max(o1*o2, o3*o4) > 0 and all four determinants nonzero); otherwise the op-for-op
+// restatement.  (distance, wall) minima are lexicographic = argmin's first-index rule for any visiting order.
+__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
+                                          float q2x, float q2y, int w, float& best, int& bidx) {
+  const float o1 = orient_val(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_val(p1x, p1y, q1x, q1y, q2x, q2y);
+  const float o3 = orient_val(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
+  const float A = f_mul(o1, o2), B = f_mul(o3, o4);
+  if (fmaxf(A, B) > 0.0f && fabsf(f_mul(A, B)) > 0.0f) return;
+  const float d = ray_wall_exact(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y);
+  if (d < best || (d == best && bidx >= 0 && w < bidx)) {
+    best = d;
+    bidx = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a) {
+  const int64_t total = a.n * a.n_rays;
+  const bool all_walls = a.st->fallback != 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t agent = t / a.n_rays;
+    const int j = (int)(t - agent * a.n_rays);
+    if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
+      a.dist[t] = 0.0f;
+      if (a.hit) a.hit[t] = -1;
+      continue;
+    }
+    const float p1x = a.ax[agent], p1y = a.ay[agent], ang = a.aang[agent], L = a.L;
+    float s, c;
+    sincosf(linspace_elem(f_sub(ang, a.span), f_add(ang, a.span), a.n_rays, j), &s, &c);  // ray_generator
+    const float q1x = f_add(p1x, f_mul(c, L)), q1y = f_add(p1y, f_mul(s, L));
+    float best = L;
+    int bidx = -1;
+    // strictly inside the grid (NaN positions fail and take the all-walls loop)
+    const float fx = (p1x - a.g.x0) * a.g.inv_cs, fy = (p1y - a.g.y0) * a.g.inv_cs;
+    const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)a.g.gx && fy < (float)a.g.gy;
+    if (inside && !all_walls) {
+      const int cell = min((int)fy, a.g.gy - 1) * a.g.gx + min((int)fx, a.g.gx - 1);
+      const uint32_t e0 = a.start[cell], e1 = a.start[cell + 1];
+      for (uint32_t e = e0; e < e1; ++e) {
+        const int w = a.entries[e];
+        test_wall(p1x, p1y, q1x, q1y, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w], w, best, bidx);
+      }
+    } else {
+      for (int w = 0; w < a.n_walls; ++w)
+        test_wall(p1x, p1y, q1x, q1y, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w], w, best, bidx);
+    }
+    a.dist[t] = best;
+    if (a.hit) a.hit[t] = bidx;
+  }
+}
+
+static inline size_t wg_al(size_t x) { return (x + 255) / 256 * 256; }
+
+static int wgrid_dims(float x_min, float x_max, float y_min, float y_max, float L, WGrid* g) {
+  if (!(L > 0.0f) || !(x_max > x_min) || !(y_max > y_min)) return -1;
+  const float ext = fmaxf(x_max - x_min, y_max - y_min);
+  const float scale = 2.0f * fmaxf(fmaxf(fabsf(x_min), fabsf(x_max)), fmaxf(fabsf(y_min), fabsf(y_max)));
+  float cs = L / 4.0f;  // a wall's band is ~2 (L + margin) wide: ~10 cells; short lists per cell
+  if (ext / cs > 512.0f) cs = ext / 512.0f;
+  g->x0 = x_min; g->y0 = y_min; g->cs = cs; g->inv_cs = 1.0f / cs;
+  g->gx = (int)ceilf((x_max - x_min) / cs); g->gy = (int)ceilf((y_max - y_min) / cs);
+  if (g->gx < 1) g->gx = 1;
+  if (g->gy < 1) g->gy = 1;
+  g->scale = scale;
+  g->eps = 1e-4f * scale + 1e-6f;
+  g->thick = L * 1.0001f + 5e-4f * scale + 1e-6f;
+  return 0;
+}
+
+// worst case of wall_cells: per major-axis column the band covers (2 * half-width * sqrt2 + 2 pads) / cs + 2 cells
+static size_t wgrid_capacity(const WGrid& g, int64_t n_walls) {
+  const int nmaj = g.gx > g.gy ? g.gx : g.gy;
+  const double thick_cells = 2.0 * 1.4143 * g.thick / g.cs + 4.0, thin_cells = 2.0 * 1.4143 * g.eps / g.cs + 4.0;
+  // thick columns: the segment's extent is unknown on the host; allow every wall a reach-wide band over a
+  // quarter of the grid plus the thin line over the rest, and let the device flag an overflow (fallback = exact)
+  const double per_wall = thin_cells * nmaj + thick_cells * (nmaj / 4.0 + 2.0 * g.thick / g.cs + 2.0);
+  double cap = per_wall * (double)n_walls;
+  if (cap > 64e6) cap = 64e6;
+  if (cap < 1024) cap = 1024;
+  return (size_t)cap;
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+size_t fgx_raycast_walls_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max,
+                                            float ray_length) {
+  fgx::WGrid g;
+  if (n_walls < 0 || fgx::wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
+  const size_t cells = (size_t)g.gx * g.gy;
+  return fgx::wg_al(sizeof(fgx::WState)) + 2 * fgx::wg_al((cells + 1) * 4) +
+         fgx::wg_al(fgx::wgrid_capacity(g, n_walls) * 4);
+}
+
+int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
+                           int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                           const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
+                           float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
+                           fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_agents >= 0 && n_walls >= 0 && n_walls < (1ll << 31), "fgx_raycast_walls_grid: bad sizes");
+  FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls_grid: n_rays must be > 0");
+  if (n_agents == 0) return FGX_OK;
+  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls_grid: null pointer");
+  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_raycast_walls_grid: null wall array");
+  WGrid g;
+  FGX_REQUIRE(wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g) == 0,
+              "fgx_raycast_walls_grid: bad arena bounds / ray_length");
+  const size_t need = fgx_raycast_walls_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
+  FGX_REQUIRE(scratch && scratch_bytes >= need, "fgx_raycast_walls_grid: scratch too small");
+  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "fgx_raycast_walls_grid: scratch must be 256-byte aligned");
+  const int n_cells = g.gx * g.gy;
+  const size_t capacity = wgrid_capacity(g, n_walls);
+  char* p = reinterpret_cast<char*>(scratch);
+  WState* st = reinterpret_cast<WState*>(p);
+  p += wg_al(sizeof(WState));
+  uint32_t* count = reinterpret_cast<uint32_t*>(p);
+  p += wg_al(((size_t)n_cells + 1) * 4);
+  uint32_t* start = reinterpret_cast<uint32_t*>(p);
+  p += wg_al(((size_t)n_cells + 1) * 4);
+  int32_t* entries = reinterpret_cast<int32_t*>(p);
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + wg_al(((size_t)n_cells + 1) * 4), s);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
+  if (n_walls) {
+    const int nmaj = g.gx > g.gy ? g.gx : g.gy;
+    const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
+    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, st);
+    wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
+    wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
+  } else {
+    e = cudaMemsetAsync(start, 0, ((size_t)n_cells + 1) * 4, s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
+  }
+  WallsGridArgs a{g, x, y, ang, active, n_agents, n_rays, ray_span, ray_length, wx1, wy1, wx2, wy2, (int)n_walls,
+                  start, entries, st, dist, hit};
+  raycast_walls_grid_kernel<<<grid_for(n_agents * n_rays, 256, 8), 256, 0, s>>>(a);
+  return check_launch("fgx_raycast_walls_grid");
+}
+}

@@ -251,3 +251,81 @@ def test_check_collision(cuda, n_walls):
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
     if n_walls >= 100:
         assert ref.any() and not ref.all()
+
+
+# ---- the spatially culled kernel (fgx_raycast_walls_grid) must equal the all-pairs kernel bit for bit ------------
+def _both_paths(x, y, ang, n_rays, walls, cuda, bounds, active=None):
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200.base.space_classes import Point, Wall
+    w = Wall(Point(dev(walls[0], cuda), dev(walls[1], cuda)), Point(dev(walls[2], cuda), dev(walls[3], cuda)))
+    pos = (dev(x, cuda), dev(y, cuda), dev(ang, cuda))
+    act = None if active is None else dev(active, cuda)
+    d0, h0 = sm.raycast_walls(pos, SPAN, LEN, w, active_state=act, n_rays=n_rays)
+    d1, h1 = sm.raycast_walls(pos, SPAN, LEN, w, active_state=act, n_rays=n_rays, bounds=bounds)
+    torch.cuda.synchronize()
+    return d0.cpu().numpy(), h0.cpu().numpy(), d1.cpu().numpy(), h1.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,n_rays,n_walls,size", [(200_000, 32, 1000, 4096.0), (50_000, 9, 300, 1500.0),
+                                                   (30_000, 33, 64, 400.0), (20_000, 1, 2000, 4096.0)])
+def test_grid_cull_equals_all_pairs(cuda, n, n_rays, n_walls, size):
+    rng = np.random.default_rng(n_walls + n_rays)
+    walls = arena_walls(rng, n_walls, size)
+    x, y, ang = agents(rng, n, size)
+    act = (rng.random(n) < 0.9).astype(np.float32)
+    d0, h0, d1, h1 = _both_paths(x, y, ang, n_rays, walls, cuda, (0.0, size, 0.0, size), act)
+    np.testing.assert_array_equal(d1, d0)
+    np.testing.assert_array_equal(h1, h0)
+    assert (h0 >= 0).mean() > 0.01
+
+
+def test_grid_cull_adversarial_geometry(cuda):
+    """Agents ON the infinite lines of far walls looking along them (the float32 sign noise of the orientation
+    tests can make such a wall 'hit'), agents on walls and wall endpoints, axis-aligned rays along the boundary
+    walls, zero-length and duplicate walls, walls and agents outside the bounds: the cull must reproduce the
+    all-pairs result exactly, whatever it is."""
+    rng = np.random.default_rng(5)
+    size = 2048.0
+    walls = arena_walls(rng, 400, size)
+    wx1, wy1, wx2, wy2 = [w.copy() for w in walls]
+    wx2[10], wy2[10] = wx1[10], wy1[10]                       # zero-length wall
+    wx1[11], wy1[11], wx2[11], wy2[11] = wx1[12], wy1[12], wx2[12], wy2[12]   # duplicate
+    wx1[13], wx2[13] = -500.0, -300.0                          # outside the bounds
+    wx1[14], wy1[14], wx2[14], wy2[14] = 100.0, 100.0, 1900.0, 1900.0         # long diagonal
+    wx1[15], wy1[15], wx2[15], wy2[15] = 50.0, 700.0, 2000.0, 700.0           # long horizontal
+    walls = [wx1, wy1, wx2, wy2]
+    xs, ys, angs = [], [], []
+    for w in range(0, 400):
+        ax, ay, bx, by = wx1[w], wy1[w], wx2[w], wy2[w]
+        th = np.arctan2(by - ay, bx - ax)
+        for t in (-30.0, -9.0, -2.0, -0.4, 0.0, 0.5, 1.0, 1.3, 3.0, 12.0, 25.0):
+            px, py = np.float32(ax + t * (bx - ax)), np.float32(ay + t * (by - ay))
+            for da in (0.0, np.pi, SPAN, -SPAN, 1e-4, np.pi / 2):
+                xs.append(px), ys.append(py), angs.append(np.float32(th + da))
+    # axis-aligned positions and headings along the boundary walls
+    for v in (0.0, 1.0, 60.0, 700.0, size):
+        for u in np.linspace(-100.0, size + 100.0, 23):
+            for a in (0.0, np.pi / 2, np.pi, -np.pi / 2):
+                xs.append(np.float32(u)), ys.append(np.float32(v)), angs.append(np.float32(a))
+                xs.append(np.float32(v)), ys.append(np.float32(u)), angs.append(np.float32(a))
+    x, y, ang = np.array(xs, np.float32), np.array(ys, np.float32), np.array(angs, np.float32)
+    for n_rays in (9, 32):
+        d0, h0, d1, h1 = _both_paths(x, y, ang, n_rays, walls, cuda, (0.0, size, 0.0, size))
+        np.testing.assert_array_equal(d1, d0)
+        np.testing.assert_array_equal(h1, h0)
+    assert (h0 >= 0).mean() > 0.2
+
+
+def test_grid_cull_vs_oracle_and_edge_sizes(cuda):
+    rng = np.random.default_rng(8)
+    size = 600.0
+    walls = arena_walls(rng, 120, size)
+    x, y, ang = agents(rng, 3000, size)
+    ref_d, ref_h = oracle_with_device_dirs(x, y, ang, 16, walls, cuda)
+    _, _, d1, h1 = _both_paths(x, y, ang, 16, walls, cuda, (0.0, size, 0.0, size))
+    np.testing.assert_array_equal(d1, ref_d)
+    np.testing.assert_array_equal(h1, ref_h)
+    # bounds that do not cover the agents or the walls at all: everything takes the all-walls loop
+    d0, h0, d2, h2 = _both_paths(x, y, ang, 16, walls, cuda, (5000.0, 5100.0, 5000.0, 5100.0))
+    np.testing.assert_array_equal(d2, d0)
+    np.testing.assert_array_equal(h2, h0)
