@@ -270,9 +270,15 @@ def run_ours(args):
     step_params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0,
                                   'energy_max': 15.0})
     step_input = Signal(content={'obs': dist_out, 'energy_in': energy_in})
-    launches_per_step = 2
+    launches_per_step = 5  # wall-grid count / scan / fill, culled ray cast, forager step
+    BOUNDS = (0.0, ARENA, 0.0, ARENA)
 
     def k1():
+        # default product path: the spatially culled kernel (bit-identical to all-pairs; tests/test_gpu_raycast.py)
+        sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
+                         n_rays=N_RAYS, out=(dist_out, hit_out), bounds=BOUNDS)
+
+    def k1_all_pairs():
         sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
                          n_rays=N_RAYS, out=(dist_out, hit_out))
 
@@ -324,6 +330,21 @@ def run_ours(args):
         k2_ms.append(ev[1].elapsed_time(ev[2]))
     k1_ms, k2_ms = float(np.mean(k1_ms)), float(np.mean(k2_ms))
 
+    # the same tick with the all-pairs ray cast (every (ray, wall) pair evaluates all four determinants): the
+    # FP32-bound kernel whose roofline fraction is reported next to the culled default
+    ap_k1, ap_tick = [], []
+    k1_all_pairs()
+    for _ in range(max(3, min(args.steps, 10))):
+        ev[0].record(stream)
+        k1_all_pairs()
+        ev[1].record(stream)
+        k2()
+        ev[2].record(stream)
+        ev[2].synchronize()
+        ap_k1.append(ev[0].elapsed_time(ev[1]))
+        ap_tick.append(ev[0].elapsed_time(ev[2]))
+    ap_k1_ms, ap_tick_ms = max_over_ranks(float(np.mean(ap_k1))), max_over_ranks(float(np.mean(ap_tick)))
+
     # end to end through the public API with HOST buffers: every step copies the agents' pose and active
     # flags from pinned host memory (H2D), runs the tick and reads back its result (ray distances, hit
     # indices and the stepped positions, D2H).  The result read-back of step i runs on a side stream
@@ -354,7 +375,7 @@ def run_ours(args):
             stream.wait_event(ev_out[b])      # this output buffer's previous read-back has landed
         d_o, h_o = outs[b]
         sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
-                         n_rays=N_RAYS, out=(d_o, h_o))
+                         n_rays=N_RAYS, out=(d_o, h_o), bounds=BOUNDS)
         fset.agents = step_agents(step_params, Signal(content={'obs': d_o, 'energy_in': energy_in}), fset)
         ev_done[b].record(stream)
         with torch.cuda.stream(side):
@@ -415,34 +436,48 @@ def run_ours(args):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_tflops = sms * 128 * sm_max * 1e6 / 1e12  # non-FMA FP32 lanes x clock
-        ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (k1_ms * 1e-3) / 1e12
-        roof = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": measured_traffic("raycast_walls_kernel", n_local),
-                "algorithmic_bytes": float(n_local) * (16 + 8 * N_RAYS),
-                "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": k1_ms,
-                "share_of_step": k1_ms / (k1_ms + k2_ms),
-                "peak_basis": f"{sms} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz, {peak_src} "
-                              "MEASURED_PEAKS.json), non-FMA; 20 FLOP per ray-wall test (SURVEY.md 8d)"}
+        # all-pairs ray cast: FP32 / issue bound, 20 algorithmic FLOP per (ray, wall) test
+        ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (ap_k1_ms * 1e-3) / 1e12
+        roof_ap = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                   "traffic": measured_traffic("raycast_walls_kernel", n_local),
+                   "algorithmic_bytes": float(n_local) * (16 + 8 * N_RAYS),
+                   "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": ap_k1_ms,
+                   "share_of_step": ap_k1_ms / ap_tick_ms,
+                   "peak_basis": f"{sms} SMs x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz, {peak_src} "
+                                 "MEASURED_PEAKS.json), non-FMA; 20 FLOP per ray-wall test (SURVEY.md 8d)"}
         if clocks and clocks.get("sm_mhz"):
-            roof["frac_at_sampled_clock"] = ach / (sms * 128 * clocks["sm_mhz"] * 1e6 / 1e12)
+            roof_ap["frac_at_sampled_clock"] = ach / (sms * 128 * clocks["sm_mhz"] * 1e6 / 1e12)
+        all_pairs = {"ms_per_step": ap_tick_ms, "value": tests_per_step / (ap_tick_ms * 1e-3), "unit": UNIT,
+                     "agent_steps_per_sec": N_AGENTS / (ap_tick_ms * 1e-3), "roofline": roof_ap,
+                     "note": "same tick with fgx_raycast_walls (no cull: every (ray, wall) pair evaluates all four "
+                             "orientation determinants); outputs identical to the default path"}
+        # the default tick's dominant kernel is the forager step (HBM bound)
         k2_bytes = K2_BYTES_ACTIVE * n_active_local + 4 * (n_local - n_active_local)
         k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        roof2 = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
-                 "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
-                 "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
-                 "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
+        roof = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
+                "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
+                "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
+                "share_of_step": k2_ms / (k1_ms + k2_ms),
+                "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
+        roof_rc = {"kernel": "wall_count / wall_scan / wall_fill + raycast_walls_grid_kernel", "kernel_ms": k1_ms,
+                   "share_of_step": k1_ms / (k1_ms + k2_ms),
+                   "algorithmic_tests_per_sec": float(n_local) * N_RAYS * N_WALLS / (k1_ms * 1e-3),
+                   "speedup_vs_all_pairs_kernel": ap_k1_ms / k1_ms,
+                   "note": "spatial cull: per grid cell only the walls that can matter are tested (~14 of 1000 here); "
+                           "bit-identical to the all-pairs kernel, so a FLOP roofline no longer describes it"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents": N_AGENTS, "active_agents": int(0.9 * N_AGENTS), "rays": N_RAYS,
                        "walls": N_WALLS, "sharding": f"agents by slot index, round-robin over {world} rank(s), walls replicated",
-                       "tick": ["fgx_raycast_walls (ray_generator + ray_wall_sensor + min/argmin)",
+                       "tick": ["fgx_raycast_walls_grid (ray_generator + ray_wall_sensor + min/argmin over the walls a "
+                                "uniform grid lists for the agent's cell; results bit-identical to all-pairs)",
                                 "fgx_forager_step (WilsonCowan policy + physics)"],
                        "l2": "per-step working set 11.6 GB of per-agent weights + 272 MB ray I/O >> 126 MB L2"},
             "agent_steps_per_sec": N_AGENTS / (ms_step * 1e-3),
-            "roofline": roof, "roofline_step_kernel": roof2,
+            "roofline": roof, "raycast_stage": roof_rc, "all_pairs": all_pairs,
             "e2e": {"value": tests_per_step / (e2e_ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step,
                     "agent_steps_per_sec": N_AGENTS / (e2e_ms_step * 1e-3)},
