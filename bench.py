@@ -270,7 +270,7 @@ def run_ours(args):
     step_params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0,
                                   'energy_max': 15.0})
     step_input = Signal(content={'obs': dist_out, 'energy_in': energy_in})
-    launches_per_step = 5  # wall-grid count / scan / fill, culled ray cast, forager step
+    launches_per_step = 2  # culled ray cast (its wall grid is built once and cached), forager step
     BOUNDS = (0.0, ARENA, 0.0, ARENA)
 
     def k1():

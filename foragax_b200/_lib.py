@@ -77,7 +77,7 @@ _decl("fgx_create_base_shard", C.c_int, C.POINTER(u32), i64, i64, i64, i64, i64,
 _decl("fgx_raycast_walls", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, vp, vp, vp)
 _decl("fgx_raycast_walls_grid_scratch_bytes", sz, i64, f32, f32, f32, f32, f32)
 _decl("fgx_raycast_walls_grid", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, f32, f32, f32, f32,
-      vp, vp, vp, sz, vp)
+      vp, vp, vp, sz, i32, vp)
 _decl("fgx_raycast_agents_scratch_bytes", sz, i64, i64, f32, f32, f32, f32, f32, f32)
 _decl("fgx_raycast_agents", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, i64, f32, f32, f32, f32,
       f32, i32, vp, vp, vp, sz, vp)

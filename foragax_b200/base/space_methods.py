@@ -7,6 +7,8 @@ reference functions handle ONE ray / ONE entity and are ``jax.vmap``-ed by the c
 leading ray / entity axes -- and run as CUDA kernels through the C ABI.  The fused
 agents x rays x walls hot loop is :func:`raycast_walls`.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -122,6 +124,14 @@ def create_space(x_min, x_max, y_min, y_max, torous, wall_array):
 
 
 GRID_MIN_WALLS = 32  # below this the all-pairs kernel is as fast as building the wall grid
+_wall_grids = weakref.WeakKeyDictionary()  # Wall -> (key, scratch holding its grid): walls are static (create_space)
+
+
+def invalidate_wall_grid(walls):
+    """Forget the cached grid of ``walls`` (only needed after mutating its coordinate tensors IN PLACE; new
+    tensors, bounds or ray lengths are detected)."""
+    _wall_grids.pop(walls, None)
+
 
 
 def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_rays=None, want_hit=True,
@@ -147,11 +157,18 @@ def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_r
     w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
     if bounds is not None and nw >= GRID_MIN_WALLS:
         b = [float(v) for v in bounds]
-        nbytes = L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length))
-        scr = L.scratch(nbytes)
+        key = (tuple(b), float(ray_length), nw, w1, w2, w3, w4, x.device.index)
+        ent = _wall_grids.get(walls)
+        reuse = ent is not None and ent[0] == key
+        if reuse:
+            scr = ent[1]
+        else:  # the wall lists are built once per (walls, bounds, ray_length) and reused by later ticks
+            scr = L.scratch(L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length)))
+            _wall_grids[walls] = (key, scr)
         L.check(L.lib.fgx_raycast_walls_grid(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                              float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2], b[3],
-                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), nbytes, L.stream()))
+                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), scr.numel(), 1 if reuse else 0,
+                                             L.stream()))
         return dist, hit
     L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                     float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))

@@ -84,10 +84,12 @@ __device__ __forceinline__ bool wall_in_scale(const WGrid& g, float ax, float ay
 __global__ void __launch_bounds__(128) wall_count_kernel(WGrid g, const float* __restrict__ wx1,
                                                          const float* __restrict__ wy1, const float* __restrict__ wx2,
                                                          const float* __restrict__ wy2, int n_walls,
-                                                         uint32_t* __restrict__ count, WState* __restrict__ st) {
+                                                         uint32_t* __restrict__ count, float4* __restrict__ wall4,
+                                                         WState* __restrict__ st) {
   const int cu = blockIdx.x * blockDim.x + threadIdx.x;
   for (int w = blockIdx.y; w < n_walls; w += gridDim.y) {
     const float ax = wx1[w], ay = wy1[w], bx = wx2[w], by = wy2[w];
+    if (cu == 0) wall4[w] = make_float4(ax, ay, bx, by);
     if (!wall_in_scale(g, ax, ay, bx, by)) {
       if (cu == 0) st->fallback = 1;
       continue;
@@ -164,6 +166,7 @@ struct WallsGridArgs {
   int n_walls;
   const uint32_t* start;
   const int32_t* entries;
+  const float4* wall4;  // (p2x, p2y, q2x, q2y) per wall, packed by the grid build
   const WState* st;
   float* dist;
   int32_t* hit;
@@ -210,7 +213,8 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
       const uint32_t e0 = a.start[cell], e1 = a.start[cell + 1];
       for (uint32_t e = e0; e < e1; ++e) {
         const int w = a.entries[e];
-        test_wall(p1x, p1y, q1x, q1y, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w], w, best, bidx);
+        const float4 wl = a.wall4[w];
+        test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, w, best, bidx);
       }
     } else {
       for (int w = 0; w < a.n_walls; ++w)
@@ -261,7 +265,7 @@ size_t fgx_raycast_walls_grid_scratch_bytes(int64_t n_walls, float x_min, float 
   fgx::WGrid g;
   if (n_walls < 0 || fgx::wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return fgx::wg_al(sizeof(fgx::WState)) + 2 * fgx::wg_al((cells + 1) * 4) +
+  return fgx::wg_al(sizeof(fgx::WState)) + 2 * fgx::wg_al((cells + 1) * 4) + fgx::wg_al((size_t)n_walls * 16 + 16) +
          fgx::wg_al(fgx::wgrid_capacity(g, n_walls) * 4);
 }
 
@@ -269,7 +273,7 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
                            int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
                            const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
                            float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
-                           fgx_stream_t stream) {
+                           int32_t reuse_grid, fgx_stream_t stream) {
   using namespace fgx;
   FGX_REQUIRE(n_agents >= 0 && n_walls >= 0 && n_walls < (1ll << 31), "fgx_raycast_walls_grid: bad sizes");
   FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls_grid: n_rays must be > 0");
@@ -291,22 +295,27 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
   p += wg_al(((size_t)n_cells + 1) * 4);
   uint32_t* start = reinterpret_cast<uint32_t*>(p);
   p += wg_al(((size_t)n_cells + 1) * 4);
+  float4* wall4 = reinterpret_cast<float4*>(p);
+  p += wg_al((size_t)n_walls * 16 + 16);
   int32_t* entries = reinterpret_cast<int32_t*>(p);
   cudaStream_t s = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + wg_al(((size_t)n_cells + 1) * 4), s);
-  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
-  if (n_walls) {
+  cudaError_t e = cudaSuccess;
+  if (reuse_grid) {
+    // the scratch holds the grid a previous call built from the same walls, bounds and ray_length
+  } else if (n_walls) {
+    e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + wg_al(((size_t)n_cells + 1) * 4), s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
     const int nmaj = g.gx > g.gy ? g.gx : g.gy;
     const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
-    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, st);
+    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, st);
     wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
   } else {
-    e = cudaMemsetAsync(start, 0, ((size_t)n_cells + 1) * 4, s);
+    e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4), s);
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
   }
   WallsGridArgs a{g, x, y, ang, active, n_agents, n_rays, ray_span, ray_length, wx1, wy1, wx2, wy2, (int)n_walls,
-                  start, entries, st, dist, hit};
+                  start, entries, wall4, st, dist, hit};
   raycast_walls_grid_kernel<<<grid_for(n_agents * n_rays, 256, 8), 256, 0, s>>>(a);
   return check_launch("fgx_raycast_walls_grid");
 }

@@ -155,14 +155,16 @@ int fgx_raycast_walls(const float* x, const float* y, const float* ang, const fl
  * agent in that cell -- walls within reach of the cell, plus walls whose infinite line passes through it
  * (float32 sign noise of the orientation tests, space_methods.py:112-125, can make a far collinear wall
  * "hit"; the all-pairs evaluation reproduces that and so does this).  Agents outside the bounds and walls
- * with coordinates beyond twice the bounds fall back to the all-walls loop (exact).                    */
+ * with coordinates beyond twice the bounds fall back to the all-walls loop (exact).  reuse_grid != 0: the
+ * scratch still holds the grid a previous call built from the SAME walls, bounds and ray_length (walls are
+ * static in the reference: create_space, space_methods.py:146-156) and only the sensing kernel runs.     */
 size_t fgx_raycast_walls_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max,
                                             float ray_length);
 int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
                            int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
                            const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
                            float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
-                           fgx_stream_t stream);
+                           int32_t reuse_grid, fgx_stream_t stream);
 /* The agents x rays x agent-targets loop: ray_generator + ray_agent_sensor (space_methods.py:71-94)
  * for every ray of every sensing agent against every target circle (tx, ty, trad, tactive:
  * float32, element i at [i*target_stride] -- stride 4 for the interleaved float4 rows of a position
