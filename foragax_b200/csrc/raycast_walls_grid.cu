@@ -231,8 +231,10 @@ static int wgrid_dims(float x_min, float x_max, float y_min, float y_max, float 
   if (!(L > 0.0f) || !(x_max > x_min) || !(y_max > y_min)) return -1;
   const float ext = fmaxf(x_max - x_min, y_max - y_min);
   const float scale = 2.0f * fmaxf(fmaxf(fabsf(x_min), fabsf(x_max)), fmaxf(fabsf(y_min), fabsf(y_max)));
-  float cs = L / 4.0f;  // a wall's band is ~2 (L + margin) wide: ~10 cells; short lists per cell
-  if (ext / cs > 512.0f) cs = ext / 512.0f;
+  // finer cells shorten the per-cell lists (the thin line bands scale with the cell size); FGX_WG_DIV tunes
+  static const float div = [] { const char* v = getenv("FGX_WG_DIV"); const float d = v ? (float)atof(v) : 0.0f; return d >= 1.0f ? d : 8.0f; }();
+  float cs = L / div;
+  if (ext / cs > 1024.0f) cs = ext / 1024.0f;
   g->x0 = x_min; g->y0 = y_min; g->cs = cs; g->inv_cs = 1.0f / cs;
   g->gx = (int)ceilf((x_max - x_min) / cs); g->gy = (int)ceilf((y_max - y_min) / cs);
   if (g->gx < 1) g->gx = 1;
