@@ -191,8 +191,10 @@ __device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float
 __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a) {
   const int64_t total = a.n * a.n_rays;
   const bool all_walls = a.st->fallback != 0;
+  const bool small = total < (1ll << 31);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t agent = t / a.n_rays;
+    // (agent, ray) of flat index t: 32-bit division whenever the index fits (the 64-bit one is ~40 instructions)
+    const int64_t agent = small ? (int64_t)((uint32_t)t / (uint32_t)a.n_rays) : t / a.n_rays;
     const int j = (int)(t - agent * a.n_rays);
     if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
       a.dist[t] = 0.0f;
@@ -211,10 +213,16 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
     if (inside && !all_walls) {
       const int cell = min((int)fy, a.g.gy - 1) * a.g.gx + min((int)fx, a.g.gx - 1);
       const uint32_t e0 = a.start[cell], e1 = a.start[cell + 1];
-      for (uint32_t e = e0; e < e1; ++e) {
-        const int w = a.entries[e];
-        const float4 wl = a.wall4[w];
-        test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, w, best, bidx);
+      for (uint32_t e = e0; e < e1; e += 4) {  // four independent (index -> wall record) load chains in flight
+        int w[4];
+        float4 wl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = a.entries[min(e + u, e1 - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wl[u] = a.wall4[w[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (e + u < e1) test_wall(p1x, p1y, q1x, q1y, L, wl[u].x, wl[u].y, wl[u].z, wl[u].w, w[u], best, bidx);
       }
     } else {
       for (int w = 0; w < a.n_walls; ++w)

@@ -329,3 +329,34 @@ def test_grid_cull_vs_oracle_and_edge_sizes(cuda):
     d0, h0, d2, h2 = _both_paths(x, y, ang, 16, walls, cuda, (5000.0, 5100.0, 5000.0, 5100.0))
     np.testing.assert_array_equal(d2, d0)
     np.testing.assert_array_equal(h2, h0)
+
+
+def test_grid_cache_follows_the_walls(cuda):
+    """The wall lists are cached per Wall object: another Wall object, other bounds or another ray length rebuild;
+    an in-place edit of the coordinates needs invalidate_wall_grid()."""
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200.base.space_classes import Point, Wall
+    rng = np.random.default_rng(21)
+    size = 800.0
+    x, y, ang = agents(rng, 5000, size)
+    pos = (dev(x, cuda), dev(y, cuda), dev(ang, cuda))
+    bounds = (0.0, size, 0.0, size)
+
+    def wall_obj(seed):
+        w = arena_walls(np.random.default_rng(seed), 100, size)
+        return Wall(Point(dev(w[0], cuda), dev(w[1], cuda)), Point(dev(w[2], cuda), dev(w[3], cuda)))
+
+    def check(walls, length=LEN, b=bounds):
+        d0, h0 = sm.raycast_walls(pos, SPAN, length, walls, n_rays=16)
+        d1, h1 = sm.raycast_walls(pos, SPAN, length, walls, n_rays=16, bounds=b)
+        assert torch.equal(d0, d1) and torch.equal(h0, h1)
+
+    wa, wb = wall_obj(1), wall_obj(2)
+    for _ in range(2):      # second call reuses the cached grid
+        check(wa)
+    check(wb)               # different Wall object
+    check(wa, length=35.0)  # different ray length
+    check(wa, b=(0.0, size + 50.0, -20.0, size))  # different bounds
+    wa.p1.x.add_(37.0)      # in-place edit: the cache cannot see it ...
+    sm.invalidate_wall_grid(wa)  # ... so the caller says so
+    check(wa)
