@@ -120,6 +120,8 @@ class ResourceState(C.Structure):
 
 _P = C.POINTER
 _decl("fgx_forager_step", C.c_int, _P(ForagerParams), i64, vp, vp, vp, _P(ForagerState), _P(WcPolicy), vp, vp)
+_decl("fgx_forager_sense_step", C.c_int, _P(ForagerParams), i64, vp, vp, _P(ForagerState), _P(WcPolicy), vp, i32, f32,
+      f32, vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, sz, i32, vp, vp, vp)
 _decl("fgx_wilson_cowan_step", C.c_int, i64, i32, i32, i32, f32, f32, vp, vp, _P(WcPolicy), vp, vp)
 _decl("fgx_resource_step", C.c_int, _P(ResourceParams), i64, vp, vp, _P(ResourceState), vp, vp, vp, vp)
 _decl("fgx_forager_resource_interaction", C.c_int, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp)

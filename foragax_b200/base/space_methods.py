@@ -127,6 +127,20 @@ GRID_MIN_WALLS = 32  # below this the all-pairs kernel is as fast as building th
 _wall_grids = weakref.WeakKeyDictionary()  # Wall -> (key, scratch holding its grid): walls are static (create_space)
 
 
+def wall_grid(walls, bounds, ray_length):
+    """``(bounds as floats, scratch tensor, reuse flag)`` of the wall lists for ``fgx_raycast_walls_grid`` /
+    ``fgx_forager_sense_step``: built by the first call that passes ``reuse == 0`` and cached per Wall object."""
+    w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
+    b = [float(v) for v in bounds]
+    key = (tuple(b), float(ray_length), nw, w1, w2, w3, w4, keep[0].device.index if keep else None)
+    ent = _wall_grids.get(walls)
+    if ent is not None and ent[0] == key:
+        return b, ent[1], 1
+    scr = L.scratch(L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length)))
+    _wall_grids[walls] = (key, scr)
+    return b, scr, 0
+
+
 def invalidate_wall_grid(walls):
     """Forget the cached grid of ``walls`` (only needed after mutating its coordinate tensors IN PLACE; new
     tensors, bounds or ray lengths are detected)."""
@@ -156,19 +170,10 @@ def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_r
         dist, hit = out
     w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
     if bounds is not None and nw >= GRID_MIN_WALLS:
-        b = [float(v) for v in bounds]
-        key = (tuple(b), float(ray_length), nw, w1, w2, w3, w4, x.device.index)
-        ent = _wall_grids.get(walls)
-        reuse = ent is not None and ent[0] == key
-        if reuse:
-            scr = ent[1]
-        else:  # the wall lists are built once per (walls, bounds, ray_length) and reused by later ticks
-            scr = L.scratch(L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length)))
-            _wall_grids[walls] = (key, scr)
+        b, scr, reuse = wall_grid(walls, bounds, ray_length)
         L.check(L.lib.fgx_raycast_walls_grid(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                              float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2], b[3],
-                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), scr.numel(), 1 if reuse else 0,
-                                             L.stream()))
+                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), scr.numel(), reuse, L.stream()))
         return dist, hit
     L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                     float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))

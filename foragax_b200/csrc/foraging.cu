@@ -15,6 +15,7 @@
 #include "geometry.cuh"
 #include "threefry.cuh"
 #include "tma.cuh"
+#include "walls_grid.cuh"
 
 namespace fgx {
 
@@ -116,6 +117,19 @@ struct ActiveScan {
   }
 };
 
+// Fused sensing (the sensor feeds the policy directly): when enabled, the warp that owns an
+// agent casts the agent's rays against the wall grid right after issuing the copies of its weights -- in the
+// shadow of their HBM latency, where the step kernel has idle issue slots -- writes the distances into the
+// agent's obs slot in shared memory (no [N, R] round trip for the policy) and to the dist / hit outputs.
+struct SenseArgs {
+  int enabled;
+  WallsGridView v;
+  int n_rays;
+  float span, L;
+  float* dist;
+  int32_t* hit;
+};
+
 // NN / NOBS / NACT > 0 fix the policy shape at compile time (constant trip counts, immediate
 // shared-memory offsets, no shape branches); 0 = read it from the params (any shape).
 template <int NN, int NOBS, int NACT>
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
                         const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
-                        float* __restrict__ actions_out, int slots) {
+                        float* __restrict__ actions_out, int slots, const SenseArgs sense) {
   // actions_out != nullptr: policy-only mode (WilsonCowan.step_policy on its own): obs has all n_obs
   // columns, actions are written out and the Forager physics is skipped.
   // slots == 2: each warp owns two weight slots -- while it computes agent i from one, the TMA copies
@@ -144,7 +158,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   const uint32_t bJ = leaf_tma_bytes(pol.J, n * n), bE = leaf_tma_bytes(pol.E, n * nobs),
                  bD = leaf_tma_bytes(pol.D, nact * n), bT = leaf_tma_bytes(pol.tau, n),
                  bB = leaf_tma_bytes(pol.B, n), bZ = leaf_tma_bytes(pol.Z, n),
-                 bO = leaf_tma_bytes(obs_in, obs_cols);
+                 bO = sense.enabled ? 0u : leaf_tma_bytes(obs_in, obs_cols);
   const uint32_t tx = bJ + bE + bD + bT + bB + bZ + bO;
 
   // lane l < 11 owns state leaf l of an agent, lane 11 its age, lane 12 its energy_in: the scalars are
@@ -178,8 +192,27 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     if (!bT) for (int i = lane; i < n; i += 32) sm[L.tau + i] = __ldg(gT + i);
     if (!bB) for (int i = lane; i < n; i += 32) sm[L.B + i] = __ldg(gB + i);
     if (!bZ) for (int i = lane; i < n; i += 32) sm[L.Z + i] = gZ[i];
-    if (!bO) for (int k = lane; k < obs_cols; k += 32) sm[L.obs + k] = __ldg(gO + k);
+    if (!bO && !sense.enabled) for (int k = lane; k < obs_cols; k += 32) sm[L.obs + k] = __ldg(gO + k);
     return my_leaf ? my_leaf[a] : 0.0f;
+  };
+  // ray_generator + ray_wall_sensor + min / argmin for agent g (pose in the scalars `svv` just fetched), one lane
+  // per ray, while the agent's weight copies are in flight; results go to obs slot s and to dist / hit
+  auto cast_rays = [&](int64_t g, float svv, int s) {
+    float* sm = slot0 + (size_t)s * L.total;
+    const float px = __shfl_sync(0xffffffffu, svv, 0), py = __shfl_sync(0xffffffffu, svv, 3);
+    const float ang = __shfl_sync(0xffffffffu, svv, 6);
+    const float lo = f_sub(ang, sense.span), hi = f_add(ang, sense.span);
+    for (int j = lane; j < sense.n_rays; j += 32) {
+      float sn, cs;
+      sincosf(linspace_elem(lo, hi, sense.n_rays, j), &sn, &cs);
+      const float q1x = f_add(px, f_mul(cs, sense.L)), q1y = f_add(py, f_mul(sn, sense.L));
+      float best = sense.L;
+      int bidx = -1;
+      walls_grid_cast(sense.v, px, py, q1x, q1y, sense.L, best, bidx);
+      sm[L.obs + j] = best;
+      sense.dist[g * sense.n_rays + j] = best;
+      if (sense.hit) sense.hit[g * sense.n_rays + j] = bidx;
+    }
   };
 
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
@@ -187,11 +220,17 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   int64_t a = scan.next(active, GW, n_agents, lane);
   int s = 0;
   float sv = 0.0f;
-  if (a < n_agents) sv = issue(a, 0);
+  if (a < n_agents) {
+    sv = issue(a, 0);
+    if (sense.enabled) cast_rays(a, sv, 0);
+  }
   while (a < n_agents) {
     const int64_t a_next = scan.next(active, GW, n_agents, lane);
     float sv_next = 0.0f;
-    if (slots == 2 && a_next < n_agents) sv_next = issue(a_next, s ^ 1);  // slot s^1 was released by the last __syncwarp
+    if (slots == 2 && a_next < n_agents) {  // slot s^1 was released by the last __syncwarp
+      sv_next = issue(a_next, s ^ 1);
+      if (sense.enabled) cast_rays(a_next, sv_next, s ^ 1);
+    }
     float* sm = slot0 + (size_t)s * L.total;
     float* gZ = pol.Z + a * n;
     const float energy = __shfl_sync(0xffffffffu, sv, 7);
@@ -258,7 +297,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     }
     __syncwarp();  // all lanes are done with slot s before the copies of a later agent land in it
     if (slots == 1) {
-      if (a_next < n_agents) sv_next = issue(a_next, 0);
+      if (a_next < n_agents) {
+        sv_next = issue(a_next, 0);
+        if (sense.enabled) cast_rays(a_next, sv_next, 0);
+      }
     } else {
       s ^= 1;
     }
@@ -478,7 +520,8 @@ extern "C" {
 template <int NN, int NOBS, int NACT>
 static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
                                  const float* obs, const float* energy_in, const fgx_forager_state_t& st,
-                                 const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
+                                 const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s,
+                                 const fgx::SenseArgs& sense) {
   using namespace fgx;
   const WcLayout L = wc_layout(p.n_neurons, p.n_obs, p.n_act);
   // one weight slot per warp and two CTAs per SM when that fits (most memory-level parallelism);
@@ -501,21 +544,22 @@ static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p
   const int64_t need = ceil_div(n, warps);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
-                                                              slots);
+                                                              slots, sense);
   return check_launch(what);
 }
 
 static int launch_forager_step(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
                                const float* obs, const float* energy_in, const fgx_forager_state_t& st,
-                               const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s) {
+                               const fgx_wc_policy_t& pol, float* age, float* actions, cudaStream_t s,
+                               const fgx::SenseArgs& sense = fgx::SenseArgs{}) {
 #define FGX_FS_SHAPE(NN, NOBS, NACT)                                                              \
   if (p.n_neurons == NN && p.n_obs == NOBS && p.n_act == NACT)                                    \
-    return launch_forager_step_t<NN, NOBS, NACT>(what, p, n, active, obs, energy_in, st, pol, age, actions, s);
+    return launch_forager_step_t<NN, NOBS, NACT>(what, p, n, active, obs, energy_in, st, pol, age, actions, s, sense);
   FGX_FS_SHAPE(40, 28, 2)  // EcoEvoJax/sim.py:712
   FGX_FS_SHAPE(30, 28, 2)  // EcoEvoJax/sim.ipynb
   FGX_FS_SHAPE(40, 33, 2)  // bench C4: 32 ray distances + own energy
 #undef FGX_FS_SHAPE
-  return launch_forager_step_t<0, 0, 0>(what, p, n, active, obs, energy_in, st, pol, age, actions, s);
+  return launch_forager_step_t<0, 0, 0>(what, p, n, active, obs, energy_in, st, pol, age, actions, s, sense);
 }
 
 extern "C" {
@@ -531,6 +575,48 @@ int fgx_forager_step(const fgx_forager_params_t* p, int64_t n, const float* acti
   FGX_REQUIRE(active_state && obs && energy_in && age, "fgx_forager_step: null pointer");
   return launch_forager_step("fgx_forager_step", *p, n, active_state, obs, energy_in, *state, *policy, age, nullptr,
                              as_stream(stream));
+}
+
+// rows of inactive agents: dist 0, hit -1 (the fused kernel only visits active agents)
+__global__ void __launch_bounds__(256) fill_inactive_rays_kernel(int64_t n, int n_rays, const float* __restrict__ active,
+                                                                 float* __restrict__ dist, int32_t* __restrict__ hit) {
+  const int64_t total = n * n_rays;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    if (active[t / n_rays] == 0.0f) {
+      dist[t] = 0.0f;
+      if (hit) hit[t] = -1;
+    }
+  }
+}
+
+int fgx_forager_sense_step(const fgx_forager_params_t* p, int64_t n, const float* active_state, const float* energy_in,
+                           const fgx_forager_state_t* state, const fgx_wc_policy_t* policy, float* age,
+                           int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                           const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
+                           float y_max, void* wall_scratch, size_t wall_scratch_bytes, int32_t reuse_grid, float* dist,
+                           int32_t* hit, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(p && state && policy, "fgx_forager_sense_step: null struct");
+  FGX_REQUIRE(n >= 0, "fgx_forager_sense_step: bad n");
+  FGX_REQUIRE(p->n_neurons > 0 && p->n_obs > 0 && p->n_act >= 2, "fgx_forager_sense_step: bad policy shape");
+  FGX_REQUIRE(n_rays > 0 && n_rays == p->n_obs - 1,
+              "fgx_forager_sense_step: the policy observes the ray distances and its own energy: n_rays must be n_obs - 1");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state && energy_in && age && dist, "fgx_forager_sense_step: null pointer");
+  cudaStream_t s = as_stream(stream);
+  SenseArgs sense{};
+  const int rc = wall_grid_prepare("fgx_forager_sense_step", wx1, wy1, wx2, wy2, n_walls, x_min, x_max, y_min, y_max,
+                                   ray_length, wall_scratch, wall_scratch_bytes, reuse_grid, s, &sense.v);
+  if (rc != FGX_OK) return rc;
+  sense.enabled = 1;
+  sense.n_rays = n_rays;
+  sense.span = ray_span;
+  sense.L = ray_length;
+  sense.dist = dist;
+  sense.hit = hit;
+  fill_inactive_rays_kernel<<<grid_for(n * n_rays, 256, 8), 256, 0, s>>>(n, n_rays, active_state, dist, hit);
+  return launch_forager_step("fgx_forager_sense_step", *p, n, active_state, nullptr, energy_in, *state, *policy, age,
+                             nullptr, s, sense);
 }
 
 int fgx_wilson_cowan_step(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, float policy_dt,

@@ -25,21 +25,9 @@
 //      list (broadcast loads, wall data L1-resident) and test their own ray.
 // Agents outside the grid bounds, walls with coordinates beyond the declared scale and list overflow
 // fall back to the all-walls loop for the affected agents / launch (exact, just slower).
-#include "common.cuh"
-#include "geometry.cuh"
+#include "walls_grid.cuh"
 
 namespace fgx {
-
-struct WGrid {
-  float x0, y0, cs, inv_cs;
-  int gx, gy;
-  float thick, eps, scale;  // band half-widths (perpendicular) and the coordinate scale they assume
-};
-
-struct WState {
-  uint32_t total;     // entries written by the fill pass
-  int32_t fallback;   // != 0: lists unusable (overflow / out-of-scale wall): every agent scans all walls
-};
 
 __device__ __forceinline__ int wg_coord(float v, float v0, float inv_cs, int n) {
   const float f = floorf((v - v0) * inv_cs);
@@ -157,40 +145,17 @@ __global__ void __launch_bounds__(128) wall_fill_kernel(WGrid g, const float* __
 }
 
 struct WallsGridArgs {
-  WGrid g;
+  WallsGridView v;
   const float *ax, *ay, *aang, *aactive;
   int64_t n;
   int n_rays;
   float span, L;
-  const float *wx1, *wy1, *wx2, *wy2;
-  int n_walls;
-  const uint32_t* start;
-  const int32_t* entries;
-  const float4* wall4;  // (p2x, p2y, q2x, q2y) per wall, packed by the grid build
-  const WState* st;
   float* dist;
   int32_t* hit;
 };
 
-// one (ray, wall) pair, exactly as the all-pairs kernel decides it: sure miss <=> no candidate distance of
-// ray_wall_sensor can apply (max(o1*o2, o3*o4) > 0 and all four determinants nonzero); otherwise the op-for-op
-// restatement.  (distance, wall) minima are lexicographic = argmin's first-index rule for any visiting order.
-__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
-                                          float q2x, float q2y, int w, float& best, int& bidx) {
-  const float o1 = orient_val(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_val(p1x, p1y, q1x, q1y, q2x, q2y);
-  const float o3 = orient_val(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
-  const float A = f_mul(o1, o2), B = f_mul(o3, o4);
-  if (fmaxf(A, B) > 0.0f && fabsf(f_mul(A, B)) > 0.0f) return;
-  const float d = ray_wall_exact(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y);
-  if (d < best || (d == best && bidx >= 0 && w < bidx)) {
-    best = d;
-    bidx = w;
-  }
-}
-
 __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a) {
   const int64_t total = a.n * a.n_rays;
-  const bool all_walls = a.st->fallback != 0;
   const bool small = total < (1ll << 31);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     // (agent, ray) of flat index t: 32-bit division whenever the index fits (the 64-bit one is ~40 instructions)
@@ -207,27 +172,7 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
     const float q1x = f_add(p1x, f_mul(c, L)), q1y = f_add(p1y, f_mul(s, L));
     float best = L;
     int bidx = -1;
-    // strictly inside the grid (NaN positions fail and take the all-walls loop)
-    const float fx = (p1x - a.g.x0) * a.g.inv_cs, fy = (p1y - a.g.y0) * a.g.inv_cs;
-    const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)a.g.gx && fy < (float)a.g.gy;
-    if (inside && !all_walls) {
-      const int cell = min((int)fy, a.g.gy - 1) * a.g.gx + min((int)fx, a.g.gx - 1);
-      const uint32_t e0 = a.start[cell], e1 = a.start[cell + 1];
-      for (uint32_t e = e0; e < e1; e += 4) {  // four independent (index -> wall record) load chains in flight
-        int w[4];
-        float4 wl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = a.entries[min(e + u, e1 - 1)];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) wl[u] = a.wall4[w[u]];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (e + u < e1) test_wall(p1x, p1y, q1x, q1y, L, wl[u].x, wl[u].y, wl[u].z, wl[u].w, w[u], best, bidx);
-      }
-    } else {
-      for (int w = 0; w < a.n_walls; ++w)
-        test_wall(p1x, p1y, q1x, q1y, L, a.wx1[w], a.wy1[w], a.wx2[w], a.wy2[w], w, best, bidx);
-    }
+    walls_grid_cast(a.v, p1x, p1y, q1x, q1y, L, best, bidx);
     a.dist[t] = best;
     if (a.hit) a.hit[t] = bidx;
   }
@@ -266,36 +211,24 @@ static size_t wgrid_capacity(const WGrid& g, int64_t n_walls) {
   return (size_t)cap;
 }
 
-}  // namespace fgx
-
-extern "C" {
-
-size_t fgx_raycast_walls_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max,
-                                            float ray_length) {
-  fgx::WGrid g;
-  if (n_walls < 0 || fgx::wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
+size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max, float ray_length) {
+  WGrid g;
+  if (n_walls < 0 || wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return fgx::wg_al(sizeof(fgx::WState)) + 2 * fgx::wg_al((cells + 1) * 4) + fgx::wg_al((size_t)n_walls * 16 + 16) +
-         fgx::wg_al(fgx::wgrid_capacity(g, n_walls) * 4);
+  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((size_t)n_walls * 16 + 16) +
+         wg_al(wgrid_capacity(g, n_walls) * 4);
 }
 
-int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
-                           int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
-                           const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
-                           float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
-                           int32_t reuse_grid, fgx_stream_t stream) {
-  using namespace fgx;
-  FGX_REQUIRE(n_agents >= 0 && n_walls >= 0 && n_walls < (1ll << 31), "fgx_raycast_walls_grid: bad sizes");
-  FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls_grid: n_rays must be > 0");
-  if (n_agents == 0) return FGX_OK;
-  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls_grid: null pointer");
-  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "fgx_raycast_walls_grid: null wall array");
+int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
+                      int64_t n_walls, float x_min, float x_max, float y_min, float y_max, float ray_length,
+                      void* scratch, size_t scratch_bytes, int reuse_grid, cudaStream_t s, WallsGridView* view) {
+  FGX_REQUIRE(n_walls >= 0 && n_walls < (1ll << 31), "%s: bad wall count", what);
+  FGX_REQUIRE(n_walls == 0 || (wx1 && wy1 && wx2 && wy2), "%s: null wall array", what);
   WGrid g;
-  FGX_REQUIRE(wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g) == 0,
-              "fgx_raycast_walls_grid: bad arena bounds / ray_length");
-  const size_t need = fgx_raycast_walls_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
-  FGX_REQUIRE(scratch && scratch_bytes >= need, "fgx_raycast_walls_grid: scratch too small");
-  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "fgx_raycast_walls_grid: scratch must be 256-byte aligned");
+  FGX_REQUIRE(wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g) == 0, "%s: bad arena bounds / ray_length", what);
+  const size_t need = wall_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
+  FGX_REQUIRE(scratch && scratch_bytes >= need, "%s: wall-grid scratch too small", what);
+  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "%s: wall-grid scratch must be 256-byte aligned", what);
   const int n_cells = g.gx * g.gy;
   const size_t capacity = wgrid_capacity(g, n_walls);
   char* p = reinterpret_cast<char*>(scratch);
@@ -308,13 +241,12 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
   float4* wall4 = reinterpret_cast<float4*>(p);
   p += wg_al((size_t)n_walls * 16 + 16);
   int32_t* entries = reinterpret_cast<int32_t*>(p);
-  cudaStream_t s = as_stream(stream);
   cudaError_t e = cudaSuccess;
   if (reuse_grid) {
     // the scratch holds the grid a previous call built from the same walls, bounds and ray_length
   } else if (n_walls) {
     e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + wg_al(((size_t)n_cells + 1) * 4), s);
-    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     const int nmaj = g.gx > g.gy ? g.gx : g.gy;
     const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
     wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, st);
@@ -322,10 +254,39 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
   } else {
     e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4), s);
-    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
-  WallsGridArgs a{g, x, y, ang, active, n_agents, n_rays, ray_span, ray_length, wx1, wy1, wx2, wy2, (int)n_walls,
-                  start, entries, wall4, st, dist, hit};
+  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, st};
+  return FGX_OK;
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+size_t fgx_raycast_walls_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max,
+                                            float ray_length) {
+  return fgx::wall_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
+}
+
+int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, const float* active, int64_t n_agents,
+                           int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                           const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
+                           float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
+                           int32_t reuse_grid, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_agents >= 0, "fgx_raycast_walls_grid: bad sizes");
+  FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls_grid: n_rays must be > 0");
+  if (n_agents == 0) return FGX_OK;
+  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls_grid: null pointer");
+  cudaStream_t s = as_stream(stream);
+  WallsGridArgs a{};
+  const int rc = wall_grid_prepare("fgx_raycast_walls_grid", wx1, wy1, wx2, wy2, n_walls, x_min, x_max, y_min, y_max,
+                                   ray_length, scratch, scratch_bytes, reuse_grid, s, &a.v);
+  if (rc != FGX_OK) return rc;
+  a.ax = x; a.ay = y; a.aang = ang; a.aactive = active;
+  a.n = n_agents; a.n_rays = n_rays; a.span = ray_span; a.L = ray_length;
+  a.dist = dist; a.hit = hit;
   raycast_walls_grid_kernel<<<grid_for(n_agents * n_rays, 256, 8), 256, 0, s>>>(a);
   return check_launch("fgx_raycast_walls_grid");
 }

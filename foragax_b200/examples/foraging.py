@@ -146,6 +146,30 @@ class Forager(Agent):
                                        L.ptr(forager.age), L.stream()))
         return forager
 
+    @staticmethod
+    def sense_step(params, energy_in, forager, walls, bounds, ray_span, ray_length, out=None):
+        """``sensor -> step_agents`` of a tick (sim.py:652-660) in ONE kernel, for a Forager that observes its wall
+        distances + own energy (``num_obs == n_rays + 1``): each agent's rays are cast against the wall grid while
+        its weights are in flight and fed to the policy from shared memory.  Returns ``(forager, dist, hit)`` --
+        the same bits as ``raycast_walls(..., bounds=bounds)`` followed by ``step_agent`` with ``obs = dist``."""
+        from ..base import space_methods as sm
+        n = forager.unique_id.shape[0]
+        pshape = _policy_shape(forager)
+        p = _forager_params(params.content['space'], forager.params.content['dt'], pshape, params.content)
+        r = pshape['num_obs'] - 1
+        if out is None:
+            dist = torch.empty((n, r), dtype=torch.float32, device=forager.age.device)
+            hit = torch.empty((n, r), dtype=torch.int32, device=forager.age.device)
+        else:
+            dist, hit = out
+        w1, w2, w3, w4, nw, keep = sm._wall_ptrs(walls)
+        b, scr, reuse = sm.wall_grid(walls, bounds, ray_length)
+        L.check(L.lib.fgx_forager_sense_step(p, n, L.ptr(forager.active_state), L.ptr(energy_in.reshape(n).contiguous()),
+                                             _fstate(forager), wc_struct(forager.policy), L.ptr(forager.age), r,
+                                             float(ray_span), float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2],
+                                             b[3], L.ptr(scr), scr.numel(), reuse, L.ptr(dist), L.ptr(hit), L.stream()))
+        return forager, dist, hit
+
     # sim.py:139-151
     @staticmethod
     @native

@@ -253,6 +253,18 @@ int fgx_forager_step(const fgx_forager_params_t* p, int64_t n, const float* acti
                      const float* energy_in, const fgx_forager_state_t* state, const fgx_wc_policy_t* policy,
                      float* age, fgx_stream_t stream);
 
+/* Sensing fused into the step (the composition EcoEvoJax/sim.py:652-660 makes per tick: sensor_model ->
+ * step_agents), for a Forager whose observation is its n_rays wall distances + own energy: the warp that
+ * steps an agent first casts its rays against the wall grid of fgx_raycast_walls_grid (same arguments,
+ * same bits) while the agent's weights are in flight, feeds the distances to the policy from shared memory
+ * and writes them to dist / hit (float32 / int32 [n, n_rays]; hit may be NULL).  Equals
+ * fgx_raycast_walls_grid followed by fgx_forager_step with obs = dist.                              */
+int fgx_forager_sense_step(const fgx_forager_params_t* p, int64_t n, const float* active_state, const float* energy_in,
+                           const fgx_forager_state_t* state, const fgx_wc_policy_t* policy, float* age,
+                           int32_t n_rays, float ray_span, float ray_length, const float* wx1, const float* wy1,
+                           const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
+                           float y_max, void* wall_scratch, size_t wall_scratch_bytes, int32_t reuse_grid, float* dist,
+                           int32_t* hit, fgx_stream_t stream);
 /* WilsonCowan.step_policy (wilson_cowan.py:34-51) on its own, vmapped: obs float32[n, n_obs],
  * actions float32[n, n_act]; Z updated in place; inactive slots (active_state == 0) are skipped. */
 int fgx_wilson_cowan_step(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, float policy_dt,

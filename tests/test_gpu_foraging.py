@@ -191,3 +191,43 @@ def test_cuda_graph_replay_equals_eager_ticks(cuda):
         np.testing.assert_array_equal(w_graph.key.cpu().numpy(), w_eager.key.cpu().numpy())
     finally:
         fg.use_variant("sim")
+
+
+def test_fused_sense_step_equals_raycast_then_step(cuda):
+    """fgx_forager_sense_step (rays cast inside the step kernel, distances fed to the policy from shared memory)
+    must give the same bits as fgx_raycast_walls_grid followed by fgx_forager_step: distances, hit indices and
+    every state / policy leaf, over several ticks, with inactive agents and agents outside the bounds."""
+    import copy
+
+    import bench
+    from foragax_b200.base.agent_classes import Params, Signal
+    from foragax_b200.base.agent_methods import step_agents
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200 import struct
+    from foragax_b200.examples.foraging import Forager
+    n = 30_000
+    old = bench.N_AGENTS
+    bench.N_AGENTS = n
+    try:
+        work = bench.make_workload(n)
+        fa, space = bench.build_foragers(work, 0, 1, cuda)
+        fb, _ = bench.build_foragers(work, 0, 1, cuda)
+    finally:
+        bench.N_AGENTS = old
+    for f in (fa, fb):   # some agents outside the arena (all-walls loop) and on the boundary
+        f.agents.state.content["X"][:50] -= 300.0
+        f.agents.state.content["Y"][50:100] = 0.0
+    bounds = (0.0, bench.ARENA, 0.0, bench.ARENA)
+    params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0, 'energy_max': 15.0})
+    energy_in = torch.rand(n, device=cuda) * 0.1
+    for _ in range(4):
+        A, B = fa.agents, fb.agents
+        sa = A.state.content
+        d0, h0 = sm.raycast_walls((sa["X"], sa["Y"], sa["ang"]), bench.RAY_SPAN, bench.RAY_LEN, space.walls,
+                                  active_state=A.active_state, n_rays=bench.N_RAYS, bounds=bounds)
+        fa.agents = step_agents(params, Signal(content={'obs': d0, 'energy_in': energy_in}), fa)
+        fb.agents, d1, h1 = Forager.sense_step(params, energy_in, B, space.walls, bounds, bench.RAY_SPAN, bench.RAY_LEN)
+        assert torch.equal(d0, d1) and torch.equal(h0, h1)
+        for x, y in zip(struct.tree_leaves(fa.agents), struct.tree_leaves(fb.agents)):
+            assert torch.equal(x, y)
+    assert float((h0 >= 0).float().mean()) > 0.01
