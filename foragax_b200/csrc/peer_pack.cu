@@ -187,3 +187,142 @@ int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, con
   return check_launch("fgx_pack_rows_peer");
 }
 }
+
+// ---- general keys: the global stable sort of a block-sharded set ("general float keys") ----
+// Every rank sorts its keys locally (fgx_argsort), publishes the SORTED key images of its block (an
+// all-gather: 4 B per slot), and finds the global position of each of its rows without any exchange of
+// rows: position of local sorted row p with image k =  p  +  sum over earlier ranks of #{images <= k}
+// +  sum over later ranks of #{images < k}   (ties keep rank order, then local order = the stable
+// order of the concatenated set), each count one binary search.  The row is then written once,
+// straight to its slot on the owning GPU, exactly like the 1-bit pack above.
+#include "key_image.cuh"
+
+namespace fgx {
+
+struct SortTable {
+  PeerTable t;
+  const uint32_t* images;  // [world][n_pad] sorted key images of every rank's block
+  int64_t n_pad;
+};
+
+__global__ void __launch_bounds__(256) sort_images_kernel(const void* __restrict__ keys, int dtype, int descending,
+                                                          const int32_t* __restrict__ perm, int64_t n,
+                                                          uint32_t* __restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = key_image(keys, dtype, descending, perm[p]);
+}
+
+// #{a[0..n) < k} (strict) or #{a[0..n) <= k}
+__device__ __forceinline__ int64_t count_below(const uint32_t* __restrict__ a, int64_t n, uint32_t k, bool or_equal) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const uint32_t v = __ldg(a + mid);
+    if (v < k || (or_equal && v == k)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// global position of every local sorted row -> gpos[p]
+__global__ void __launch_bounds__(256) sort_positions_kernel(const __grid_constant__ SortTable st, int64_t n,
+                                                             int64_t* __restrict__ gpos) {
+  const PeerTable& tab = st.t;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = __ldg(st.images + (int64_t)tab.rank * st.n_pad + p);
+    int64_t g = p;
+    for (int s = 0; s < tab.world; ++s) {
+      if (s == tab.rank) continue;
+      g += count_below(st.images + (int64_t)s * st.n_pad, tab.bounds[s + 1] - tab.bounds[s], k, s < tab.rank);
+    }
+    gpos[p] = g;
+  }
+}
+
+// row perm[p] of every leaf -> slot of global position gpos[p] on its owner (grid.y = leaf)
+__global__ void __launch_bounds__(256) sort_scatter_peer_kernel(const __grid_constant__ PeerTable tab,
+                                                                const int32_t* __restrict__ perm,
+                                                                const int64_t* __restrict__ gpos, int64_t n) {
+  const fgx_peer_leaf_t& lf = tab.leaf[blockIdx.y];
+  const int v = tab.vec[blockIdx.y];
+  const int64_t chunks = lf.row_bytes / v;
+  // narrow rows: a thread per row; wide rows: a warp per row (lanes stride the chunks)
+  const bool wide = chunks > 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t workers = wide ? ((int64_t)gridDim.x * blockDim.x) >> 5 : (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = wide ? (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5
+                             : blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t p = first; p < n; p += workers) {
+    const int64_t s = __ldg(perm + p), g = __ldg(gpos + p);
+    int d = 0;
+    while (d + 1 < tab.world && g >= tab.bounds[d + 1]) ++d;
+    const char* __restrict__ src = reinterpret_cast<const char*>(lf.src) + s * lf.row_bytes;
+    char* dst = reinterpret_cast<char*>(lf.dst[d]) + (g - tab.bounds[d]) * lf.row_bytes;
+    for (int64_t c = wide ? lane : 0; c < chunks; c += wide ? 32 : 1) {
+      if (v == 16) reinterpret_cast<uint4*>(dst)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+      else if (v == 8) reinterpret_cast<uint2*>(dst)[c] = __ldg(reinterpret_cast<const uint2*>(src) + c);
+      else if (v == 4) reinterpret_cast<uint32_t*>(dst)[c] = __ldg(reinterpret_cast<const uint32_t*>(src) + c);
+      else if (v == 2) reinterpret_cast<uint16_t*>(dst)[c] = __ldg(reinterpret_cast<const uint16_t*>(src) + c);
+      else dst[c] = __ldg(src + c);
+    }
+  }
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+int fgx_sort_key_images(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, const int32_t* perm,
+                        uint32_t* images, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && (key_dtype == FGX_F32 || key_dtype == FGX_I32), "fgx_sort_key_images: bad arguments");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(keys && perm && images, "fgx_sort_key_images: null pointer");
+  sort_images_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(keys, key_dtype, descending ? 1 : 0, perm, n,
+                                                                        images);
+  return check_launch("fgx_sort_key_images");
+}
+
+int fgx_sort_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n_local,
+                       const uint32_t* images_all, int64_t n_pad, const int64_t* bounds_host, int32_t rank,
+                       int32_t world, int64_t* gpos_scratch, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(world >= 1 && world <= FGX_MAX_PEERS && rank >= 0 && rank < world, "fgx_sort_rows_peer: bad rank / world");
+  FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_PEER_LEAVES, "fgx_sort_rows_peer: at most %d leaves per call",
+              FGX_MAX_PEER_LEAVES);
+  FGX_REQUIRE(bounds_host, "fgx_sort_rows_peer: null bounds");
+  for (int k = 0; k < world; ++k) {
+    FGX_REQUIRE(bounds_host[k] <= bounds_host[k + 1], "fgx_sort_rows_peer: shard bounds must ascend");
+    FGX_REQUIRE(bounds_host[k + 1] - bounds_host[k] <= n_pad, "fgx_sort_rows_peer: n_pad smaller than a shard");
+  }
+  FGX_REQUIRE(bounds_host[0] == 0 && bounds_host[rank + 1] - bounds_host[rank] == n_local,
+              "fgx_sort_rows_peer: n_local does not match this rank's shard bounds");
+  FGX_REQUIRE(n_local >= 0 && n_local < (1ll << 31), "fgx_sort_rows_peer: n_local out of range");
+  if (n_local == 0 || n_leaves == 0) return FGX_OK;
+  FGX_REQUIRE(leaves_host && perm && images_all && gpos_scratch, "fgx_sort_rows_peer: null pointer");
+  SortTable st;
+  int cnt = 0;
+  for (int k = 0; k < n_leaves; ++k) {
+    const fgx_peer_leaf_t& lf = leaves_host[k];
+    FGX_REQUIRE(lf.src && lf.row_bytes > 0, "fgx_sort_rows_peer: leaf %d is malformed", k);
+    uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | (uintptr_t)lf.row_bytes;
+    for (int d = 0; d < world; ++d) {
+      FGX_REQUIRE(lf.dst[d] && lf.dst[d] != lf.src, "fgx_sort_rows_peer: leaf %d has a bad destination on rank %d", k, d);
+      bits |= reinterpret_cast<uintptr_t>(lf.dst[d]);
+    }
+    int v = 16;
+    while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
+    st.t.leaf[cnt] = lf;
+    st.t.vec[cnt++] = v;
+  }
+  for (int k = 0; k <= world; ++k) st.t.bounds[k] = bounds_host[k];
+  st.t.rank = rank;
+  st.t.world = world;
+  st.images = images_all;
+  st.n_pad = n_pad;
+  cudaStream_t s = as_stream(stream);
+  sort_positions_kernel<<<grid_for(n_local, 256, 8), 256, 0, s>>>(st, n_local, gpos_scratch);
+  dim3 grid(grid_for(n_local, 256, 8), cnt);
+  sort_scatter_peer_kernel<<<grid, 256, 0, s>>>(st.t, perm, gpos_scratch, n_local);
+  return check_launch("fgx_sort_rows_peer");
+}
+}

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "key_image.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -53,24 +54,6 @@ __device__ __forceinline__ int passes_done(const SortState* st, int pass) {
 __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid) {
   const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
   if (valid && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
-}
-
-// order-preserving uint32 image of a raw 32-bit key word (float32 or int32)
-__device__ __forceinline__ uint32_t image_of(uint32_t raw, int dtype, int descending) {
-  if (dtype == FGX_F32) {
-    float v = __uint_as_float(raw);
-    if (descending) v = -v;
-    if (v != v) return 0xFFFFFFFFu;  // every NaN sorts last
-    if (v == 0.0f) v = 0.0f;         // -0.0 -> +0.0
-    const uint32_t b = __float_as_uint(v);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  }
-  int32_t v = (int32_t)raw;
-  if (descending) v = (int32_t)(0u - (uint32_t)v);
-  return (uint32_t)v ^ 0x80000000u;
-}
-__device__ __forceinline__ uint32_t key_image(const void* keys, int dtype, int descending, int64_t i) {
-  return image_of(__ldg(reinterpret_cast<const uint32_t*>(keys) + i), dtype, descending);
 }
 
 // ---- 1. one pass of statistics: per-CTA (min, #min, max, #max) of its contiguous tile range -----------

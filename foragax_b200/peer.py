@@ -87,6 +87,47 @@ class PeerPackedSet:
         it = iter(self._views[self.cur])
         return struct.tree_map(lambda x: next(it), self._template)
 
+    def _peer_table(self, src, dst, part):
+        arr = (L.PeerLeaf * len(part))()
+        for k, (v, off, rb) in enumerate(part):
+            arr[k].src = v.data_ptr()
+            arr[k].row_bytes = rb
+            for d in range(self.world):
+                arr[k].dst[d] = self._ptrs[dst][d] + off
+        return arr
+
+    def sort(self, quantity, ascend):
+        """``sort_agents(quantity, ascend, agents)`` (agent_methods.py:74-79) over the whole sharded set for a
+        GENERAL float32 / int32 key: local native argsort, all-gather of every rank's sorted key images (4 B per
+        slot), global positions by binary search (ties: rank order, then local order = the stable order of the
+        concatenated set), rows written once to their slots on the owning GPUs.  ``quantity``: a row leaf of
+        ``self.agents`` or a callable ``agents -> leaf``.  Returns the new local block."""
+        from .base.agent_methods import argsort
+        agents = self.agents
+        q = quantity(agents) if callable(quantity) else quantity
+        q = q.reshape(-1)
+        if q.dtype == torch.bool:
+            q = q.to(torch.int32)
+        q = q.contiguous()
+        n, dev = self.n_local, q.device
+        perm = argsort(q, ascend)
+        images = torch.full((self.n_max,), -1, dtype=torch.int32, device=dev)  # padding = 0xFFFFFFFF
+        L.check(L.lib.fgx_sort_key_images(L.ptr(q), L.dtype_code(q), n, 0 if ascend else 1, L.ptr(perm), L.ptr(images),
+                                          L.stream()))
+        all_images = torch.empty(self.world * self.n_max, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_images, images, group=self.group)
+        gpos = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        src, dst = self._views[self.cur], 1 - self.cur
+        rows = [(v, off, rb) for v, off, rb, row in zip(src, self._offsets, self._row_bytes, self._is_row) if row]
+        for s in range(0, len(rows), L.MAX_PEER_LEAVES):
+            part = rows[s:s + L.MAX_PEER_LEAVES]
+            L.check(L.lib.fgx_sort_rows_peer(self._peer_table(src, dst, part), len(part), L.ptr(perm), n,
+                                             L.ptr(all_images), self.n_max, self._bounds_c, self.rank, self.world,
+                                             L.ptr(gpos), L.stream()))
+        dist.all_reduce(self._token, group=self.group)  # orders the ranks: every scatter has landed
+        self.cur = dst
+        return self.agents
+
     def pack_active(self):
         """``sort_agents(active_state, descending)`` over the whole sharded set; returns the new local block."""
         from .base.agent_methods import select_agents

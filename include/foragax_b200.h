@@ -120,6 +120,16 @@ typedef struct {
 int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm,
                        const int32_t* n_front, int64_t n_local, const int64_t* front_counts,
                        const int64_t* bounds_host, int32_t rank, int32_t world, fgx_stream_t stream);
+/* sort_agents on a GENERAL key over the same block-sharded set: images[p] = order-preserving uint32 image of
+ * keys[perm[p]] (perm = this rank's fgx_argsort); after an all-gather of every rank's sorted images
+ * (images_all: [world][n_pad], rows padded), fgx_sort_rows_peer finds each local row's position in the
+ * global stable order by binary searches (ties: rank order, then local order) and writes the row to its
+ * slot on the owning GPU.  gpos_scratch: device int64[n_local].  Same ordering rule as fgx_pack_rows_peer. */
+int fgx_sort_key_images(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, const int32_t* perm,
+                        uint32_t* images, fgx_stream_t stream);
+int fgx_sort_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n_local,
+                       const uint32_t* images_all, int64_t n_pad, const int64_t* bounds_host, int32_t rank,
+                       int32_t world, int64_t* gpos_scratch, fgx_stream_t stream);
 /* jnp.sum(active_state, dtype=int32) (agent_methods.py:27): out int32[1] */
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream);
 /* the argument construction of create_agents (agent_methods.py:10-15), fused:

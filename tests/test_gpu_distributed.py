@@ -206,3 +206,63 @@ def test_two_gpu_peer_memory_pack_equals_single_gpu():
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
     assert res[0][2] + res[1][2] == res[0][3]
+
+
+def _sort_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import foragax_b200.base.agent_classes as fgx_classes
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import random as fgx_random
+    from foragax_b200 import struct
+    from foragax_b200.examples.hello_world import make_dice
+    from foragax_b200.peer import PeerPackedSet
+    D = make_dice(20)
+    s = fgx_classes.Agent_Set(agent=D, num_total_agents=n, num_active_agents=n * 2 // 3, agent_type=0)
+    s.agents = fgx_methods.create_agents(None, s, fgx_random.PRNGKey(6))
+    for _ in range(3):
+        s.agents = fgx_methods.step_agents(None, None, s)
+    g = torch.Generator(device="cuda").manual_seed(5)   # same on every rank
+    keyf = torch.randint(-50, 50, (n,), device="cuda", generator=g).float() * 0.5   # many ties
+    keyf[::97] = float("nan")
+    keyf[5::101] = -0.0
+    s.agents = s.agents.replace(age=keyf)
+    lo, hi = fd.shard_bounds(n)
+    mine = struct.tree_map(lambda x: x[lo:hi].clone() if x.dim() and x.shape[0] == n else x, s.agents)
+    st = PeerPackedSet(mine)
+    ok = True
+    for leaf, asc in (("age", True), ("age", False), ("draw", True), ("draw", False)):
+        get = (lambda a: a.age) if leaf == "age" else (lambda a: a.state.content['draw'])  # noqa: E731
+        ref, _ = fgx_methods.jit_sort_agents(get(s.agents), asc, s.agents)
+        got = st.sort(get, asc)
+        for gl, rl in zip(struct.tree_leaves(got), struct.tree_leaves(ref)):
+            if rl.dim() and rl.shape[0] == n:
+                a, b = gl, rl[lo:hi]
+                same = torch.equal(a, b) if a.dtype != torch.float32 else torch.equal(a.view(torch.int32), b.view(torch.int32))
+                ok = ok and same
+        s.agents = ref   # keep both sides in the same state for the next sort
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_general_sort_equals_single_gpu():
+    """PeerPackedSet.sort: float keys with ties, NaN and -0.0 (ascending / descending) and an int key, on ragged
+    shards -- every rank ends with its block of the single-GPU sort_agents, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n = 2, 60_001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sort_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
