@@ -70,7 +70,9 @@ _decl("fgx_select", C.c_int, C.POINTER(Predicate), i64, vp, vp, vp, sz, vp)
 _decl("fgx_argsort_scratch_bytes", sz, i64)
 _decl("fgx_argsort", C.c_int, vp, i32, i64, i32, vp, vp, sz, vp)
 _decl("fgx_gather_rows", C.c_int, C.POINTER(Leaf), i32, vp, i64, vp)
+_decl("fgx_gather_rows_from", C.c_int, C.POINTER(Leaf), i32, vp, i64, i64, vp)
 _decl("fgx_pack_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, vp, i64, vp, C.POINTER(i64), i32, i32, vp)
+_decl("fgx_key_chain_advance", C.c_int, i32, vp, vp, vp, vp)
 _decl("fgx_sort_key_images", C.c_int, vp, i32, i64, i32, vp, vp, vp)
 _decl("fgx_sort_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, i64, vp, i64, C.POINTER(i64), i32, i32, vp, vp)
 _decl("fgx_count_active", C.c_int, vp, i64, vp, vp)

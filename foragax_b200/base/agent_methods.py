@@ -158,26 +158,28 @@ def argsort(quantity, ascend=True):
 
 
 def take_rows(agents, ids):
-    """``tree_map(lambda x: jnp.take(x, ids, axis=0), agents)`` in one launch per 32 leaves."""
+    """``tree_map(lambda x: jnp.take(x, ids, axis=0), agents)`` in one launch per 32 leaves; ``ids`` may be shorter
+    (or longer) than the slot axis: the result has ``len(ids)`` rows."""
     n = ids.shape[0]
     leaves = struct.tree_leaves(agents)
+    n_src = leaves[0].shape[0] if leaves else 0
     outs = []
     table = []
     for x in leaves:
-        if x.shape[0] != n:
+        if x.shape[0] != n_src:
             raise L.FgxError("every agent leaf must have the slot axis first")
         src = x if x.is_contiguous() else x.contiguous()
-        dst = torch.empty_like(src)
+        dst = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
         outs.append(dst)
-        row_bytes = src.element_size() * (src.numel() // n) if n else 0
+        row_bytes = src.element_size() * (src.numel() // n_src) if n_src else 0
         table.append((src, dst, row_bytes))
-    if n:
+    if n and n_src:
         for s in range(0, len(table), L.MAX_LEAVES):
             part = table[s:s + L.MAX_LEAVES]
             arr = (L.Leaf * len(part))()
             for k, (src, dst, rb) in enumerate(part):
                 arr[k].src, arr[k].dst, arr[k].row_bytes = L.ptr(src), L.ptr(dst), rb
-            L.check(L.lib.fgx_gather_rows(arr, len(part), L.ptr(ids), n, L.stream()))
+            L.check(L.lib.fgx_gather_rows_from(arr, len(part), L.ptr(ids), n, n_src, L.stream()))
     it = iter(outs)
     return struct.tree_map(lambda x: next(it), agents)
 

@@ -274,6 +274,25 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace fgx
 
+// the key add_agents' serial chain holds after `steps` added rows (no rows are touched): lets a rank of a sharded
+// set start the chain at the global index of its first new row, and every rank compute the final key
+__global__ void key_chain_advance_kernel(int mode, const uint32_t* __restrict__ key_in, const int32_t* __restrict__ steps,
+                                         uint32_t* __restrict__ key_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  fgx::Key key{key_in[0], key_in[1]};
+  const int64_t k = *steps;
+  for (int64_t j = 0; j < k; ++j) {
+    if (mode == 0) {
+      key = fgx::split_child(key, 6, 0);
+    } else {
+      key = fgx::split_child(key, 4, 0);
+      key = fgx::split_child(key, 2, 0);
+    }
+  }
+  key_out[0] = key.a;
+  key_out[1] = key.b;
+}
+
 extern "C" {
 
 int fgx_forager_create(const fgx_forager_params_t* p, int64_t n, const uint32_t* create_keys,
@@ -327,6 +346,15 @@ int fgx_forager_add(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, 
                                                               active_state, age);
   reset_age_rows_kernel<<<grid_for(n, 256, 4), 256, 0, s>>>(n, n_active, k, age);
   return check_launch("fgx_forager_add");
+}
+
+int fgx_key_chain_advance(int32_t mode, const uint32_t* key_in, const int32_t* steps, uint32_t* key_out,
+                          fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(mode == 0 || mode == 1, "fgx_key_chain_advance: mode must be 0 (Forager) or 1 (Resource)");
+  FGX_REQUIRE(key_in && steps && key_out, "fgx_key_chain_advance: null pointer");
+  key_chain_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(mode, key_in, steps, key_out);
+  return check_launch("fgx_key_chain_advance");
 }
 
 int fgx_forager_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_forager_state_t* state,

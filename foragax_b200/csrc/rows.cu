@@ -24,7 +24,8 @@ struct LeafTable {
 __device__ __forceinline__ int64_t clamp_index(int64_t s, int64_t n) { return s < 0 ? 0 : (s >= n ? n - 1 : s); }
 
 template <typename T>
-__device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n) {
+__device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n,
+                                              int64_t n_src) {
   const int64_t chunks = lf.row_bytes / (int64_t)sizeof(T);
   const T* __restrict__ src = reinterpret_cast<const T*>(lf.src);
   T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
@@ -34,7 +35,7 @@ __device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t r = row + u * nthreads;
-      s[u] = r < n ? clamp_index(__ldg(perm + r), n) : 0;  // jnp.take clamps
+      s[u] = r < n ? clamp_index(__ldg(perm + r), n_src) : 0;  // jnp.take clamps
     }
     if (chunks == 1) {
       T v[4];
@@ -57,26 +58,27 @@ __device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_
 }
 
 __global__ void __launch_bounds__(256) gather_narrow_kernel(const __grid_constant__ LeafTable tab,
-                                                            const int32_t* __restrict__ perm, int64_t n) {
+                                                            const int32_t* __restrict__ perm, int64_t n,
+                                                            int64_t n_src) {
   const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
   switch (tab.vec[blockIdx.y]) {
-    case 16: gather_narrow<uint4>(lf, perm, n); break;
-    case 8: gather_narrow<uint2>(lf, perm, n); break;
-    case 4: gather_narrow<uint32_t>(lf, perm, n); break;
-    case 2: gather_narrow<uint16_t>(lf, perm, n); break;
-    default: gather_narrow<uint8_t>(lf, perm, n); break;
+    case 16: gather_narrow<uint4>(lf, perm, n, n_src); break;
+    case 8: gather_narrow<uint2>(lf, perm, n, n_src); break;
+    case 4: gather_narrow<uint32_t>(lf, perm, n, n_src); break;
+    case 2: gather_narrow<uint16_t>(lf, perm, n, n_src); break;
+    default: gather_narrow<uint8_t>(lf, perm, n, n_src); break;
   }
 }
 
 __global__ void __launch_bounds__(256) gather_wide_kernel(const __grid_constant__ LeafTable tab,
-                                                          const int32_t* __restrict__ perm, int64_t n) {
+                                                          const int32_t* __restrict__ perm, int64_t n, int64_t n_src) {
   const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
   const int v = tab.vec[blockIdx.y];
   const int64_t chunks = lf.row_bytes / v;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
-    const int64_t s = clamp_index(__ldg(perm + row), n);
+    const int64_t s = clamp_index(__ldg(perm + row), n_src);
     if (v == 16) {
       const uint4* __restrict__ src = reinterpret_cast<const uint4*>(lf.src) + s * chunks;
       uint4* __restrict__ dst = reinterpret_cast<uint4*>(lf.dst) + row * chunks;
@@ -133,8 +135,13 @@ extern "C" {
 
 int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
                     fgx_stream_t stream) {
+  return fgx_gather_rows_from(leaves_host, n_leaves, perm, n, n, stream);
+}
+
+int fgx_gather_rows_from(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
+                         int64_t n_src, fgx_stream_t stream) {
   using namespace fgx;
-  FGX_REQUIRE(n >= 0 && n < (1ll << 31), "fgx_gather_rows: n out of range");
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31) && n_src >= 1 && n_src < (1ll << 31), "fgx_gather_rows: n out of range");
   FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_LEAVES, "fgx_gather_rows: at most %d leaves per call",
               FGX_MAX_LEAVES);
   if (n == 0 || n_leaves == 0) return FGX_OK;
@@ -160,11 +167,11 @@ int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32
   cudaStream_t s = as_stream(stream);
   if (nn) {
     dim3 grid(grid_for(ceil_div(n, 4), 256, 8), nn);
-    gather_narrow_kernel<<<grid, 256, 0, s>>>(narrow, perm, n);
+    gather_narrow_kernel<<<grid, 256, 0, s>>>(narrow, perm, n, n_src);
   }
   if (nw) {
     dim3 grid(grid_for(n * 32, 256, 8), nw);
-    gather_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n);
+    gather_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n, n_src);
   }
   return check_launch("fgx_gather_rows");
 }

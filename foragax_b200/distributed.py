@@ -223,7 +223,7 @@ def plan_parent_splits(selected_counts, active_counts, shard_sizes):
     return splits
 
 
-def fetch_parent_rows(agents, selected_ids, n_selected_local, n_active_local, take_rows):
+def fetch_parent_rows(agents, selected_ids, n_selected_local, n_active_local, take_rows, n_local=None):
     """Parent rows for this rank's new slots: every rank gathers the rows of its selected
     parents (``take_rows(agents, ids) -> agents`` = the native row gather; ``selected_ids`` is the local select
     permutation, parents first), and one all-to-all per leaf delivers them to the ranks that own the new
@@ -232,8 +232,9 @@ def fetch_parent_rows(agents, selected_ids, n_selected_local, n_active_local, ta
     2 counts per rank)."""
     from . import struct
     r, w = world()
-    n_local = agents.active_state.shape[0]
-    dev = agents.active_state.device
+    if n_local is None:  # `agents` may be any pytree of row leaves when n_local is given
+        n_local = agents.active_state.shape[0]
+    dev = selected_ids.device
     trio = torch.stack([torch.as_tensor(n_selected_local, device=dev).reshape(()).to(torch.int64),
                         torch.as_tensor(n_active_local, device=dev).reshape(()).to(torch.int64),
                         torch.as_tensor(n_local, device=dev, dtype=torch.int64)])
@@ -270,3 +271,50 @@ def fetch_parent_rows(agents, selected_ids, n_selected_local, n_active_local, ta
         return out.view(src.dtype).reshape((n_recv,) + tuple(src.shape[1:]))
 
     return struct.tree_map(exchange, parents)
+
+
+def key_chain_advance(mode, key, steps):
+    """The key ``add_agents``' serial chain holds after ``steps`` added rows (``fgx_key_chain_advance``; mode 0 =
+    Forager, 1 = Resource).  ``key`` uint32[2] device tensor, ``steps`` device scalar or int."""
+    from . import _lib as L
+    out = torch.empty_like(key)
+    st = L.device_i32(steps)
+    L.check(L.lib.fgx_key_chain_advance(int(mode), L.ptr(key), L.ptr(st), L.ptr(out), L.stream()))
+    return out
+
+
+def global_add_agents(add_func, make_add_params, agents, parent_leaves, selected_ids, n_selected_local, key, lo,
+                      n_total, chain_mode):
+    """``add_agents`` (agent_methods.py:26-38) + the caller's clip over a globally packed, block-sharded set, for
+    add functions that copy from PARENT rows and thread a key (Forager / Resource, sim.py:154-210,316-344).
+
+    The new rows are the global slots ``[a, a + k)``; child j descends from the j-th selected agent of the GLOBAL
+    select order and uses link j of the serial key chain.  Per rank: :func:`global_add_range` gives the local
+    part of the range and the global index ``j0`` of its first child; :func:`fetch_parent_rows` brings the rows
+    of the leaves the add function READS from a parent (``parent_leaves(agents)`` -> list of row leaves, all of
+    which it overwrites in the child) and they are written INTO the new slots, so the unmodified native add runs
+    with ``good_ids = identity`` (its kernels read a parent element before they overwrite it) from the chain key
+    advanced by ``j0`` links.  Returns ``(agents, key_out, n_parents_local)``: ``key_out`` is the key after all k
+    links (the same on every rank) and the first ``n_parents_local`` of ``selected_ids`` are this rank's parents
+    that did reproduce (what the caller's ``set_agents`` applies to)."""
+    from .base.agent_methods import add_agents, count_active, take_rows
+    n_local = agents.active_state.shape[0]
+    dev = agents.active_state.device
+    n_act = count_active(agents)
+    k, local_count, j0 = global_add_range(n_selected_local, n_act, n_local, lo, n_total)
+    leaves = list(parent_leaves(agents))
+    parents = fetch_parent_rows(leaves, selected_ids, n_selected_local, n_act, take_rows, n_local=n_local)
+    n_new = int(parents[0].shape[0]) if parents else 0
+    start = int(n_act)  # the counts were read back by fetch_parent_rows already
+    if n_new:
+        for dst, src in zip(leaves, parents):
+            dst[start:start + n_new].copy_(src)
+    ids = torch.arange(start, start + max(n_new, 1), dtype=torch.int32, device=dev)
+    key_r = key_chain_advance(chain_mode, key, j0)
+    agents, _ = add_agents(add_func, local_count, make_add_params(ids), agents, key_r)
+    # parents of this rank that reproduced: its selected agents whose global index is below k
+    r, w = world()
+    sel_all = all_gather_counts(torch.as_tensor(n_selected_local, device=dev).reshape(()))
+    before = sel_all[:r].sum()
+    n_parents_local = torch.minimum(torch.clamp(k.to(torch.int64) - before, min=0), sel_all[r]).to(torch.int32)
+    return agents, key_chain_advance(chain_mode, key, k), n_parents_local

@@ -103,6 +103,9 @@ typedef struct {
  * for every leaf (jnp.take, indices clamped).  src and dst must not alias.  */
 int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
                     fgx_stream_t stream);
+/* the same with n output rows taken from leaves of n_src rows (x[ids] for a shorter id list) */
+int fgx_gather_rows_from(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
+                         int64_t n_src, fgx_stream_t stream);
 /* sort_agents(active_state, descending) (agent_methods.py:74-79) over a set sharded in contiguous blocks
  * across the GPUs of one node, compaction and exchange in ONE kernel: every rank scatters its rows into
  * the peers' destination buffers (peer-mapped device memory, stores over NVLink) at their slots of the
@@ -334,6 +337,12 @@ int fgx_forager_add(int64_t n, int32_t n_neurons, int32_t n_obs, int32_t n_act, 
 /* set_agents with Forager.set_agent (sim.py:213-225) */
 int fgx_forager_set(int64_t n, const int32_t* set_ids, const int32_t* k, const fgx_forager_state_t* state,
                     fgx_stream_t stream);
+/* The key held by add_agents' serial chain (agent_methods.py:29-35) after `steps` (device int32) added rows, without
+ * touching any row: mode 0 = Forager.add_agent's `key, *ks = split(key, 6)` (sim.py:181), mode 1 =
+ * Resource.add_agent's two splits (sim.py:322,335).  Lets a rank of a sharded set start the chain at the global
+ * index of its first new row.                                                                          */
+int fgx_key_chain_advance(int32_t mode, const uint32_t* key_in, const int32_t* steps, uint32_t* key_out,
+                          fgx_stream_t stream);
 /* vmapped Resource.create_agent (sim.py:231-261); x_lo..y_hi = create bounds of X, Y (sim.py:248-249) */
 int fgx_resource_create(int64_t n, float x_lo, float x_hi, float y_lo, float y_hi, const uint32_t* create_keys,
                         const float* active_state, const fgx_resource_state_t* state, float* growth_rate,

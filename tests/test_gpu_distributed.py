@@ -12,6 +12,24 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
+def _collect(procs, q, world, timeout=240):
+    """Results of all workers; fails as soon as one of them dies instead of waiting for the queue to time out."""
+    import queue as _queue
+    import time
+    out, t0 = [], time.time()
+    while len(out) < world:
+        try:
+            out.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"worker failed (exit codes {dead}) or timed out")
+    return sorted(out)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -61,7 +79,7 @@ def test_two_gpu_pack_active_equals_single_gpu_sort():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = _collect(procs, q, world)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -132,7 +150,7 @@ def test_two_gpu_sharded_churn_ticks_equal_single_gpu():
     procs = [ctx.Process(target=_churn_worker, args=(r, world, port, n, 6, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = _collect(procs, q, world)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -200,7 +218,7 @@ def test_two_gpu_peer_memory_pack_equals_single_gpu():
     procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n, 6, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = _collect(procs, q, world)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -261,8 +279,81 @@ def test_two_gpu_general_sort_equals_single_gpu():
     procs = [ctx.Process(target=_sort_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = _collect(procs, q, world)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def _forager_add_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import distributed as fd
+    from foragax_b200 import random as fgx_random
+    from foragax_b200 import struct
+    from foragax_b200.base.agent_classes import Agent_Set, Params
+    from foragax_b200.base.predicates import P
+    from foragax_b200.base.space_methods import create_space
+    from foragax_b200.examples import foraging as fg
+    fg.use_variant("sim")
+    space = create_space(0.0, 1000.0, 0.0, 500.0, False, None)
+    fset = Agent_Set(agent=fg.Forager, num_total_agents=n, num_active_agents=n * 3 // 5, agent_type=1)
+    cp = Params(content={'policy_params': {'num_neurons': 40, 'num_obs': 28, 'num_actions': 2, 'dt': 0.1,
+                                           'action_scale': 1.0, 'deterministic': True}, 'dt': 0.1, 'space': space})
+    full = fgx_methods.create_agents(cp, fset, fgx_random.PRNGKey(2))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    full.state.content['time_above_rep_thresh'].copy_(torch.rand((n, 1), device="cuda", generator=g))
+    full.state.content['energy'].copy_(torch.rand((n, 1), device="cuda", generator=g) * 10)
+    full.age.copy_(torch.rand(n, device="cuda", generator=g) * 50)
+
+    def good(a, p):
+        return (P(a.active_state) == 1.0) & (P(a.state.content['time_above_rep_thresh']) > 0.55)
+
+    lo, hi = fd.shard_bounds(n)
+    mine = struct.tree_map(lambda x: x[lo:hi].clone() if x.dim() and x.shape[0] == n else x, full)
+    key = fgx_random.PRNGKey(11)
+    # single-GPU reference (sim.py:518-524): select, clip, add, set
+    n_add, ids = fgx_methods.jit_select_agents(good, None, full)
+    n_add = torch.minimum(n_add, n - fgx_methods.count_active(full))
+    ref, key_ref = fgx_methods.jit_add_agents(fg.Forager.add_agent, n_add, Params(content={'good_ids': ids}), full, key)
+    ref, _ = fgx_methods.jit_set_agents(fg.Forager.set_agent, n_add, Params(content={'set_ids': ids}), ref, key_ref)
+    # the same on the sharded set
+    n_sel, lids = fgx_methods.jit_select_agents(good, None, mine)
+    def parent_leaves(a):   # what Forager.add_agent reads from a parent (sim.py:158-200) -- and overwrites in the child
+        c, pc = a.state.content, a.policy.params.content
+        return [c['X'], c['Y'], c['energy'], a.age, pc['J'], pc['tau'], pc['E'], pc['B'], pc['D']]
+
+    got, key_got, n_par = fd.global_add_agents(fg.Forager.add_agent, lambda i: Params(content={'good_ids': i}), mine,
+                                               parent_leaves, lids, n_sel, key, lo, n, chain_mode=0)
+    got, _ = fgx_methods.jit_set_agents(fg.Forager.set_agent, n_par, Params(content={'set_ids': lids}), got, key_got)
+    ok = torch.equal(key_got, key_ref)
+    for a, b in zip(struct.tree_leaves(got), struct.tree_leaves(ref)):
+        if b.dim() and b.shape[0] == n:
+            ok = ok and torch.equal(a, b[lo:hi])
+    q.put((rank, ok, int(n_add), int(fgx_methods.count_active(got))))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_forager_add_with_parents_equals_single_gpu():
+    """Neuroevolution's add step (select good foragers -> clip -> add_agents with mutated copies of the parents'
+    networks, serial key chain -> set_agents on the parents) on two ranks: parents' 12 KB rows travel to the ranks
+    that own the new slots; every leaf and the returned key equal the single-GPU result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n = 2, 3001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_forager_add_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = _collect(procs, q, world)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res) and res[0][2] > 100
