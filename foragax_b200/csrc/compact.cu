@@ -4,10 +4,13 @@
 // argsort(-mask) -> (count, permutation).  The permutation is "selected slots
 // ascending, then unselected slots ascending", so the O(N log N) comparison
 // sort of the reference is a 1-bit stable partition here:
-//   pass A  per-tile selected counts (warp ballots + popc), last CTA scans them
-//   pass B  re-evaluates the predicate (the leaves are L2-resident after pass
-//           A), ranks each slot with ballot/popc prefix sums and writes
-//           perm[rank] or perm[total + i - rank].
+//   pass A  selected count of each CTA's contiguous tile range (warp ballots + popc)
+//   pass B  every CTA sums the counts of the CTAs before it (its offset) and of all CTAs
+//           (the total), re-evaluates the predicate (the leaves are L2-resident after
+//           pass A), ranks each slot with ballot/popc prefix sums and writes
+//           perm[rank] or perm[total + i - rank]
+//   small   up to 16,384 slots: ONE 1024-thread CTA holds every flag in registers
+//           (one round of loads, one block scan, one scatter).
 // The predicate is evaluated in-kernel from the agent leaves (up to four
 // comparisons combined by a truth table), so no mask array is materialised.
 // Algorithmic HBM bytes: predicate leaves read once + 4 B/slot written.

@@ -11,7 +11,8 @@
 //   3. general path: stable LSD radix sort of (image, slot index), 8-bit digits:
 //      prep (images + 4 digit histograms), plan (digit bases, trivial passes),
 //      per pass: tile histogram -> per-digit scan over tiles -> stable scatter with
-//      warp match/ballot ranking; finish copies to the caller's perm if needed.
+//      warp match/ballot ranking; finish copies to the caller's perm if needed -- all phases in
+//      ONE cooperative launch separated by grid-wide syncs (FGX_SORT_MULTI=1: a launch per phase).
 // Small inputs order the unique 64-bit (image, index) composite (hence stable): n <= 256 by a
 // single-CTA bitonic network in shared memory, n <= 16384 by an all-pairs rank sort over every SM.
 #include <cooperative_groups.h>
