@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     const float Y = __shfl_sync(0xffffffffu, sv, 3), Yv = __shfl_sync(0xffffffffu, sv, 4);
     const float tar = __shfl_sync(0xffffffffu, sv, 9), tbd = __shfl_sync(0xffffffffu, sv, 10);
     const float age0 = __shfl_sync(0xffffffffu, sv, 11), e_in = __shfl_sync(0xffffffffu, sv, 12);
-    if (lane == 0 && !actions_out) {
-      // Forager.step_agent physics (sim.py:89-128)
+    if (!actions_out) {
+      // Forager.step_agent physics (sim.py:89-128): every lane evaluates the same scalars (no divergence), then
+      // lane l < 12 stores the leaf it owns (my_leaf: the 11 state leaves and age) -- one store instruction
+      // instead of thirteen single-lane ones
       const float dt = p.dt;
       float Xn = f_add(X, f_mul(Xv, dt)), Yn = f_add(Y, f_mul(Yv, dt));
       float Xvn = f_add(Xv, f_mul(act0, dt)), Yvn = f_add(Yv, f_mul(act1, dt));
@@ -287,13 +289,19 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
       float en = f_sub(f_add(energy, e_in), f_mul(p.energy_cost_dt, f_add(fabsf(act0), fabsf(act1))));
       en = fminf(en, p.energy_max);
       if (p.clip_min) en = fmaxf(en, p.energy_min);
-      st.X[a] = Xn; st.Y[a] = Yn; st.X_vel[a] = Xvn; st.Y_vel[a] = Yvn;
-      st.X_acc[a] = act0; st.Y_acc[a] = act1;
-      st.ang[a] = atan2f(Yvn, Xvn);
-      st.energy[a] = en; st.rad[a] = en;
-      st.time_above_rep_thresh[a] = en > p.repr_thresh ? f_add(tar, dt) : 0.0f;
-      st.time_below_die_thresh[a] = en < p.die_thresh ? f_add(tbd, dt) : 0.0f;
-      age[a] = f_add(age0, dt);
+      // leaf order of fgx_forager_state_t: X X_vel X_acc Y Y_vel Y_acc ang energy rad t_above t_below | age
+      float val = Xn;
+      val = lane == 1 ? Xvn : val;
+      val = lane == 2 ? act0 : val;
+      val = lane == 3 ? Yn : val;
+      val = lane == 4 ? Yvn : val;
+      val = lane == 5 ? act1 : val;
+      val = lane == 6 ? atan2f(Yvn, Xvn) : val;
+      val = (lane == 7 || lane == 8) ? en : val;
+      val = lane == 9 ? (en > p.repr_thresh ? f_add(tar, dt) : 0.0f) : val;
+      val = lane == 10 ? (en < p.die_thresh ? f_add(tbd, dt) : 0.0f) : val;
+      val = lane == 11 ? f_add(age0, dt) : val;
+      if (lane < 12) const_cast<float*>(my_leaf)[a] = val;
     }
     __syncwarp();  // all lanes are done with slot s before the copies of a later agent land in it
     if (slots == 1) {

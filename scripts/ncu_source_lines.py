@@ -16,8 +16,9 @@ for r in rows:
     elif r and r[0] == "Line No":
         hdr = {h: i for i, h in enumerate(r)}
     elif hdr and len(r) > 8 and r[0].isdigit():
-        lines.append((cur, int(r[0]), r[1].strip()[:90], int(r[hdr["Instructions Executed"]] or 0),
-                      int(r[hdr["# Samples"]] or 0), float(r[hdr["Avg. Threads Executed"]] or 0)))
+        num = lambda v: float(v) if v not in ("", "-") else 0.0  # noqa: E731
+        lines.append((cur, int(r[0]), r[1].strip()[:90], int(num(r[hdr["Instructions Executed"]])),
+                      int(num(r[hdr["# Samples"]])), num(r[hdr["Avg. Threads Executed"]])))
 tot_i = sum(x[3] for x in lines) or 1
 tot_s = sum(x[4] for x in lines) or 1
 print(f"total warp instructions {tot_i:,}; stall samples {tot_s:,}")
