@@ -460,7 +460,23 @@ def run_ours(args):
                 "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
                 "share_of_step": k2_ms / (k1_ms + k2_ms),
                 "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
-        roof_rc = {"kernel": "wall_count / wall_scan / wall_fill + raycast_walls_grid_kernel", "kernel_ms": k1_ms,
+        # the culled ray cast is instruction-issue bound: warp instructions (ncu, committed under profiles/) against
+        # the issue rate of 4 schedulers per SM
+        rc_prof = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            rc_prof = json.load(open(tp)).get("raycast_walls_grid_kernel")
+        rc_roof = None
+        if rc_prof:
+            winst = rc_prof["warp_instructions_per_launch"] * n_local / rc_prof["agents"]
+            issue_peak = sms * 4 * sm_max * 1e6
+            rc_roof = {"bound": "issue", "achieved": winst / (k1_ms * 1e-3) / 1e9, "peak": issue_peak / 1e9,
+                       "unit": "G warp-instructions/s", "frac": winst / (k1_ms * 1e-3) / issue_peak,
+                       "traffic": rc_prof["dram_bytes_per_launch"] * n_local / rc_prof["agents"],
+                       "peak_basis": f"{sms} SMs x 4 warp schedulers x {sm_max:.0f} MHz; instruction count from "
+                                     "profiles/r01_traffic.json (ncu smsp__inst_executed.sum of this workload)"}
+        roof_rc = {"kernel": "raycast_walls_grid_kernel (wall lists built once, cached)", "kernel_ms": k1_ms,
+                   "roofline": rc_roof,
                    "share_of_step": k1_ms / (k1_ms + k2_ms),
                    "algorithmic_tests_per_sec": float(n_local) * N_RAYS * N_WALLS / (k1_ms * 1e-3),
                    "speedup_vs_all_pairs_kernel": ap_k1_ms / k1_ms,
