@@ -118,6 +118,48 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxRaycastWalls, RaycastWallsImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::S32>>());
 
+// ---- the same reduction through per-cell wall lists (fgx_raycast_walls_grid: bit-identical, ~30x faster at 1,000
+// walls).  XLA owns the scratch, so the wall lists are rebuilt per call (reuse_grid = 0); a caller that keeps the
+// walls fixed can carry the scratch as an explicit operand instead and pass reuse_grid = 1.
+static ffi::Error RaycastWallsGridImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> y,
+                                       ffi::Buffer<ffi::F32> ang, ffi::Buffer<ffi::F32> active,
+                                       ffi::Buffer<ffi::F32> wx1, ffi::Buffer<ffi::F32> wy1, ffi::Buffer<ffi::F32> wx2,
+                                       ffi::Buffer<ffi::F32> wy2, ffi::ScratchAllocator scratch, int32_t n_rays,
+                                       float ray_span, float ray_length, float x_min, float x_max, float y_min,
+                                       float y_max, ffi::Result<ffi::Buffer<ffi::F32>> dist,
+                                       ffi::Result<ffi::Buffer<ffi::S32>> hit) {
+  const int64_t n_walls = static_cast<int64_t>(wx1.element_count());
+  const size_t bytes = fgx_raycast_walls_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
+  auto buf = scratch.Allocate(bytes, 256);
+  if (!buf.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "fgx_raycast_walls_grid: scratch");
+  return Status(fgx_raycast_walls_grid(x.typed_data(), y.typed_data(), ang.typed_data(), active.typed_data(),
+                                       static_cast<int64_t>(x.element_count()), n_rays, ray_span, ray_length,
+                                       wx1.typed_data(), wy1.typed_data(), wx2.typed_data(), wy2.typed_data(), n_walls,
+                                       x_min, x_max, y_min, y_max, dist->typed_data(), hit->typed_data(), *buf, bytes,
+                                       /*reuse_grid=*/0, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxRaycastWallsGrid, RaycastWallsGridImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Attr<int32_t>("n_rays")
+                                  .Attr<float>("ray_span")
+                                  .Attr<float>("ray_length")
+                                  .Attr<float>("x_min")
+                                  .Attr<float>("x_max")
+                                  .Attr<float>("y_min")
+                                  .Attr<float>("y_max")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>());
+
 // ---- jax.random.split on a key batch (the K4 entry the others follow)
 static ffi::Error SplitImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> keys, int32_t num,
                             ffi::Result<ffi::Buffer<ffi::U32>> out) {
