@@ -48,7 +48,12 @@ K2_BYTES_ACTIVE = 4 * (N_NEURONS * N_NEURONS + N_NEURONS * N_OBS + N_ACT * N_NEU
                        + N_RAYS + 8                                                                  # obs, state in
                        + N_NEURONS + 12) + 4                                                         # Z, state out
 METRIC = "ray-wall tests/sec"
-UNIT = "tests/s"
+# `value` counts ALGORITHMIC pairs (agents x rays x walls per tick, inactive slots included: the reference's vmap
+# evaluates every slot and every pair) whether or not the kernel culls them; the unit says so, and the
+# line also carries the executed figure (`executed_tests_per_sec`) and the un-culled tick (`all_pairs`).
+UNIT = "all-pairs-equivalent tests/s"
+PARITY_TICKS = 3
+PARITY_GOLDEN = os.path.join(ROOT, "tests", "golden", "bench_parity_digest.json")
 WORKLOAD = ("C4: 1M agents x 32 rays x 1000 walls, 4096^2 arena, WilsonCowan forager 40 neurons / 33 obs "
             "(SURVEY.md 8d)")
 
@@ -90,7 +95,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -175,22 +180,40 @@ class CpuTick:
         t = time.perf_counter()
         dist, _ = self.c.raycast_walls(st["X"], st["Y"], st["ang"], self.fg["active_state"], N_RAYS, RAY_SPAN,
                                        RAY_LEN, *self.walls)
+        self.raycast_sec = time.perf_counter() - t
         self.c.forager_step(self.cfg, dist, self.zero, self.fg)
         return time.perf_counter() - t
 
 
 def cpu_baseline(work, n_sample):
+    use_all_host_cores()
     tick = CpuTick(work, n_sample)
     sec = tick.step()
     return {"value": tick.tests / sec, "unit": UNIT, "cores": tick.c.threads(), "kind": "port",
+            "raycast_only_tests_per_sec": tick.tests / tick.raycast_sec,
             "sample": f"one tick (ray cast + forager step) over the first {n_sample} agents x {N_RAYS} rays x "
                       f"{N_WALLS} walls of the same workload ({sec:.2f} s); C restatement of the reference path "
                       "with OpenMP (jax is not installed, so the reference itself cannot run)"}
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core at every N, so the
+    variable is reset BEFORE the OpenMP runtime of the C oracle loads and the pool size is set explicitly."""
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0)) or cores
+    except (AttributeError, OSError):
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    from oracle import c_oracle
+    c_oracle.set_threads(cores)
+    return cores
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    use_all_host_cores()
     work = make_workload()
     n_sample = 20_000
     tick = CpuTick(work, n_sample)
@@ -215,7 +238,7 @@ def run_reference(args):
     }))
 
 
-def build_foragers(work, rank, world, dev):
+def build_foragers(work, rank, world, dev, n_agents=None):
     """The local shard (slots rank, rank+world, ...: round-robin, so that active and inactive slots are
     spread evenly over the ranks) of the 1M-forager set: native create (threefry weights, PRNGKey(0)),
     then positions / headings of the synthetic workload.  Every rank builds exactly its rows of the
@@ -227,11 +250,12 @@ def build_foragers(work, rank, world, dev):
     from foragax_b200.base.agent_methods import create_agents
     from foragax_b200.base.space_methods import create_space
     from foragax_b200.examples.foraging import Forager
+    n_agents = N_AGENTS if n_agents is None else int(n_agents)
     space = create_space(0.0, ARENA, 0.0, ARENA, False, wall_array(work))
-    fset = Agent_Set(agent=Forager, num_total_agents=N_AGENTS, num_active_agents=int(0.9 * N_AGENTS), agent_type=1)
+    fset = Agent_Set(agent=Forager, num_total_agents=n_agents, num_active_agents=int(0.9 * n_agents), agent_type=1)
     cp = Params(content={'policy_params': {'num_neurons': N_NEURONS, 'num_obs': N_OBS, 'num_actions': N_ACT, 'dt': DT,
                                            'action_scale': 1.0, 'deterministic': True}, 'dt': DT, 'space': space})
-    n_local = len(range(rank, N_AGENTS, world))
+    n_local = len(range(rank, n_agents, world))
     fset.agents = create_agents(cp, fset, fgx_random.PRNGKey(0), shard=(rank, n_local, world))
     st = fset.agents.state.content
     for k, src in (("X", "x"), ("Y", "y"), ("ang", "ang")):
@@ -239,7 +263,141 @@ def build_foragers(work, rank, world, dev):
     return fset, space
 
 
+def np_forager_rows(F, rows):
+    """Oracle-layout dict (oracle/foraging.py) of the first `rows` local rows of a Forager pytree."""
+    from oracle import foraging as ofo
+    c, pc = F.state.content, F.policy.params.content
+    cp = lambda t: t[:rows].cpu().numpy()  # noqa: E731
+    return {"state": {k: cp(c[k]) for k in ofo.FSTATE},
+            "policy": {**{k: cp(pc[k]) for k in ("J", "tau", "E", "B", "D")}, "Z": cp(F.policy.state.content["Z"])},
+            "unique_id": cp(F.unique_id), "agent_type": cp(F.agent_type), "active_state": cp(F.active_state),
+            "age": cp(F.age)}
+
+
+def oracle_slice_check(work, F, space, dist_out, hit_out, tick, rows, dev):
+    """Rank 0, BEFORE the parity ticks: one tick over this rank's first `rows` agents on the oracle -- ray cast
+    bit-exact (the oracle is fed the device's ray directions, as in the parity tests), forager step within the
+    1e-5 relative tolerance of north_star -- against the tick the device runs on the full shard."""
+    import torch
+
+    import foragax_b200.base.space_methods as sm
+    from oracle import foraging as ofo
+    from oracle import space_methods as osm
+    st = F.state.content
+    before = np_forager_rows(F, rows)
+    old_res = sm.RESOLUTION
+    sm.RESOLUTION = N_RAYS
+    try:
+        rays = sm.ray_generator((st["X"][:rows], st["Y"][:rows], st["ang"][:rows]), RAY_SPAN, RAY_LEN)
+    finally:
+        sm.RESOLUTION = old_res
+    dx, dy = rays.ray_direction.x.cpu().numpy(), rays.ray_direction.y.cpu().numpy()
+    x0, y0 = before["state"]["X"].reshape(-1), before["state"]["Y"].reshape(-1)
+    w = work["walls"]
+    ref_d = np.empty((rows, N_RAYS), np.float32)
+    ref_h = np.empty((rows, N_RAYS), np.int32)
+    for lo in range(0, rows, 500):  # chunks bound the [agents, rays, walls] temporaries of the NumPy oracle
+        hi = min(rows, lo + 500)
+        d = osm.ray_wall_sensor(x0[lo:hi, None, None], y0[lo:hi, None, None], dx[lo:hi, :, None], dy[lo:hi, :, None],
+                                RAY_LEN, *[a[None, None, :] for a in w])
+        ref_d[lo:hi] = d.min(-1)
+        ref_h[lo:hi] = np.where(ref_d[lo:hi] < np.float32(RAY_LEN), d.argmin(-1), -1)
+    inactive = before["active_state"] == 0
+    ref_d[inactive] = 0
+    ref_h[inactive] = -1
+    tick()  # the device tick over the whole shard (first of the PARITY_TICKS)
+    got_d, got_h = dist_out[:rows].cpu().numpy(), hit_out[:rows].cpu().numpy()
+    cfg = ofo.Config("sim", n_neurons=N_NEURONS, n_obs=N_OBS, n_act=N_ACT, x_max=ARENA, y_max=ARENA)
+    ref = ofo.forager_step(cfg, got_d, np.zeros(rows, np.float32), before)
+    after = np_forager_rows(F, rows)
+
+    def rel(name, a, b):
+        scale = max(1.0, float(np.abs(b).max()))
+        return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / scale)
+
+    errs = {k: rel(k, after["state"][k], ref["state"][k]) for k in ("X", "Y", "X_vel", "Y_vel", "ang", "energy")}
+    errs["Z"] = rel("Z", after["policy"]["Z"], ref["policy"]["Z"])
+    return {"agents": rows, "raycast_dist_bit_exact": bool(np.array_equal(got_d, ref_d)),
+            "raycast_hit_bit_exact": bool(np.array_equal(got_h, ref_h)),
+            "rays_hitting_a_wall": float((ref_h >= 0).mean()),
+            "step_max_rel_err": errs, "step_within_1e-5": bool(max(errs.values()) <= 1e-5),
+            "age_bit_exact": bool(np.array_equal(after["age"], ref["age"])),
+            "oracle": "oracle/space_methods.py ray_wall_sensor (device ray directions) + oracle/foraging.py forager_step"}
+
+
+def c5_churn_leg(args, rank, world, dev):
+    """BASELINE config 5 (10 M Dice slots, D20: ~5 % + 5 % turnover per tick) -- per-op CUDA-event times,
+    algorithmic bytes and fraction of measured HBM (N = 1); with N > 1 the set is block-sharded and the tick runs
+    through the peer-memory exchange (foragax_b200/peer.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from foragax_b200.examples import churn
+    n, ticks = args.c5_slots, args.c5_ticks
+    peaks, peak_src = measured_peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    if world == 1:
+        w = churn.ChurnWorld(n)
+        tick_ms, ops, n_act = churn.time_ticks(w, ticks)
+        alg = churn.algorithmic_bytes(n, n_act, 0.05 * n_act)
+        rows = {}
+        for name in churn.OPS:
+            gbs = alg[name] / (ops[name] * 1e-3) / 1e9
+            rows[name] = {"ms": ops[name], "algorithmic_bytes": float(alg[name]), "gbs": gbs, "frac_of_hbm": gbs / hbm}
+        tot = float(sum(alg.values()))
+        out = {"workload": f"C5: {n} Dice slots (28 B rows), D20, ~{n_act:.0f} active, ~5% + 5% turnover per tick; tick = "
+                           "step -> select -> remove -> sort(active_state, desc) -> select -> clip -> add "
+                           "(hello_world.ipynb:104-144)",
+               "n_gpus": 1, "ms_per_tick": tick_ms, "slot_steps_per_sec": n / (tick_ms * 1e-3),
+               "active_agent_steps_per_sec": n_act / (tick_ms * 1e-3), "ops": rows,
+               "algorithmic_bytes_per_tick": tot, "tick_gbs": tot / (tick_ms * 1e-3) / 1e9,
+               "tick_frac_of_hbm": tot / (tick_ms * 1e-3) / 1e9 / hbm, "hbm_peak_gbs": hbm, "peak_basis": peak_src,
+               "launches_per_tick": 13, "final_active": int(churn.fgx_methods.count_active(w.agents))}
+        del w
+        torch.cuda.empty_cache()
+        return out
+    from foragax_b200.examples import churn_sharded
+    w = churn_sharded.ShardedChurnWorld(n)
+    res = w.time_ticks(ticks)
+    t = torch.tensor([res["ms_per_tick"], res["eager_ms_per_tick"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([res["final_active_local"], res["rows_sent_remote_per_tick"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(cnt)
+    out = {"workload": f"C5: {n} Dice slots (28 B rows) in contiguous blocks over {world} GPUs, D20; tick = local step / "
+                       "select / remove -> GLOBAL pack of the actives (one kernel: compaction + peer-memory stores over "
+                       "NVLink, device-side flag barriers, no NCCL call in the tick) -> local select -> global add range "
+                       "-> local add",
+           "n_gpus": world, "ms_per_tick": float(t[0]), "eager_ms_per_tick": float(t[1]),
+           "slot_steps_per_sec": n / (float(t[0]) * 1e-3), "final_active": int(cnt[0]),
+           "nvlink_row_bytes_per_tick": float(cnt[1]) * churn.ROW_BYTES, "mode": res["mode"]}
+    del w
+    torch.cuda.empty_cache()
+    return out
+
+
+def d2h_ceiling(n_local, dev, barrier, max_over_ranks):
+    """Pinned device->host copy bandwidth with every rank copying at once (what bounds the e2e leg): one 35 MB-class
+    buffer per rank, 10 copies, GB/s summed over ranks."""
+    import torch
+    nbytes = (2 * 4 * N_RAYS + 8) * n_local
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / 10
+    return nbytes, ms
+
+
 def run_ours(args):
+    import hashlib
+
     import torch
     import torch.distributed as dist
 
@@ -254,6 +412,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import foragax_b200.base.space_methods as sm
+    from foragax_b200 import distributed as fd
     from foragax_b200.base.agent_classes import Params, Signal
     from foragax_b200.base.agent_methods import step_agents
 
@@ -289,6 +448,14 @@ def run_ours(args):
         k1()
         k2()
 
+    def sense():
+        # agent-agent ray sensing: NCCL all-gather of the float4 positions IN SLOT ORDER (round-robin shards are
+        # un-interleaved), uniform-grid build, ray_agent_sensor, merge with the wall result; hit = global entity id
+        k1()
+        tg = fd.all_gather_positions(st["X"], st["Y"], st["rad"], F.active_state, layout="round_robin")
+        sm.raycast_agents((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, tg, BOUNDS, 15.0,
+                          active_state=F.active_state, n_rays=N_RAYS, merge_walls=True, out=(dist_out, hit_out))
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -299,6 +466,58 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def slot_order(t):
+        """The local rows of every rank reassembled in GLOBAL slot order (slot i = row i // world of rank i % world)."""
+        t = t.contiguous()
+        if world == 1:
+            return t
+        assert N_AGENTS % world == 0
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return out.transpose(0, 1).reshape((N_AGENTS,) + tuple(t.shape[1:]))
+
+    def digest(t):
+        g = slot_order(t)
+        h = hashlib.sha256(g.cpu().numpy().tobytes()).hexdigest() if rank == 0 else None
+        del g
+        return h
+
+    # ---- parity block: PARITY_TICKS ticks from the fixed seed, BEFORE any timing.  Digests of the outputs in global
+    # slot order are independent of N (every agent is stepped by the same kernel on the same operands), so the
+    # N-GPU line must carry the digests committed from the 1-GPU run; rank 0 also checks a slice against the oracle.
+    parity = None
+    if not args.no_parity:
+        oracle_slice = None
+        ticks_left = PARITY_TICKS
+        if rank == 0:
+            oracle_slice = oracle_slice_check(work, F, space, dist_out, hit_out, tick, args.parity_rows, dev)
+        else:
+            tick()
+        ticks_left -= 1
+        for _ in range(ticks_left):
+            tick()
+        dg = {"dist": digest(dist_out), "hit": digest(hit_out), "X": digest(st["X"]),
+              "Z": digest(F.policy.state.content["Z"])}
+        if not args.no_agent_sensing:
+            sense()
+            dg["agent_sensing_dist"] = digest(dist_out)
+            dg["agent_sensing_hit"] = digest(hit_out)
+        if rank == 0:
+            golden = json.load(open(PARITY_GOLDEN)) if os.path.exists(PARITY_GOLDEN) else None
+            same = None
+            if golden:
+                same = {k: (golden["sha256"].get(k) == v) for k, v in dg.items()}
+            parity = {"ticks": PARITY_TICKS, "order": "global slot order (round-robin shards un-interleaved)",
+                      "sha256": dg, "golden": "tests/golden/bench_parity_digest.json (1-GPU run)" if golden else None,
+                      "equals_1gpu_golden": same, "all_equal": (all(same.values()) if same else None),
+                      "oracle_slice": oracle_slice}
+            if args.write_parity_golden:
+                os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                with open(os.path.join(ROOT, "gpurun_out", "bench_parity_digest.json"), "w") as f:
+                    json.dump({"sha256": dg, "ticks": PARITY_TICKS, "n_gpus": world,
+                               "made_by": "python bench.py --write-parity-golden (see DESIGN.md, Measurement)"}, f,
+                              indent=1)
 
     stream = torch.cuda.current_stream()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -319,7 +538,7 @@ def run_ours(args):
     # per-kernel durations, live, with CUDA events on the launching stream
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     k1_ms, k2_ms = [], []
-    for _ in range(args.steps):
+    for _ in range(max(args.steps, 20)):
         ev[0].record(stream)
         k1()
         ev[1].record(stream)
@@ -329,6 +548,7 @@ def run_ours(args):
         k1_ms.append(ev[0].elapsed_time(ev[1]))
         k2_ms.append(ev[1].elapsed_time(ev[2]))
     k1_ms, k2_ms = float(np.mean(k1_ms)), float(np.mean(k2_ms))
+    listed = sm.wall_grid_listed((st["X"], st["Y"]), space.walls, BOUNDS, RAY_LEN, active_state=F.active_state)
 
     # the same tick with the all-pairs ray cast (every (ray, wall) pair evaluates all four determinants): the
     # FP32-bound kernel whose roofline fraction is reported next to the culled default
@@ -403,19 +623,12 @@ def run_ours(args):
     h2d = 4 * 4 * N_AGENTS
     d2h = (2 * 4 * N_RAYS + 2 * 4) * N_AGENTS
     clocks = sampler.stop() if sampler else None
+    # the ceiling of that leg: every rank's pinned read-back running at once, nothing else on the GPUs
+    ceil_bytes, ceil_ms = d2h_ceiling(n_local, dev, barrier, max_over_ranks)
 
-    # extra stage (not part of `value`): agent-agent ray sensing -- NCCL all-gather of float4 positions
-    # (N > 1), uniform-grid build, ray_agent_sensor over the 3x3 neighbourhood, merge with the wall result
+    # extra stage (not part of `value`): agent-agent ray sensing
     agent_sensing = None
     if not args.no_agent_sensing:
-        from foragax_b200 import distributed as fd
-
-        def sense():
-            k1()
-            tg = fd.all_gather_positions(st["X"], st["Y"], st["rad"], F.active_state)
-            sm.raycast_agents((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, tg, (0.0, ARENA, 0.0, ARENA), 15.0,
-                              active_state=F.active_state, n_rays=N_RAYS, merge_walls=True, out=(dist_out, hit_out))
-
         sense()
         barrier()
         reps = max(2, min(5, args.steps))
@@ -428,8 +641,17 @@ def run_ours(args):
         frac_agent = float(((hit_out >= 0) & (hit_out < N_AGENTS)).float().mean())
         agent_sensing = {"ms_per_tick_walls_plus_agents": sense_ms, "ms_agents_only": sense_ms - k1_ms,
                          "rays_hitting_an_agent": frac_agent,
-                         "note": "fgx_raycast_walls + all_gather_positions + fgx_raycast_agents (grid, exact "
-                                 "vs all-pairs); 1M agents sensing 1M targets, not included in `value`"}
+                         "note": "fgx_raycast_walls + all_gather_positions (slot order) + fgx_raycast_agents (grid, exact "
+                                 "vs all-pairs); 1M agents sensing 1M targets, not included in `value`; hit indices "
+                                 "are global slot ids (digest in `parity`)"}
+
+    # free the 12.5 GB forager set before the other configs run
+    listed_host = [int(v) for v in listed.cpu().tolist()]
+    c5 = None
+    if not args.no_c5:
+        del fset, F, st, outs, step_input
+        torch.cuda.empty_cache()
+        c5 = c5_churn_leg(args, rank, world, dev)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -437,8 +659,13 @@ def run_ours(args):
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_tflops = sms * 128 * sm_max * 1e6 / 1e12  # non-FMA FP32 lanes x clock
         # all-pairs ray cast: FP32 / issue bound, 20 algorithmic FLOP per (ray, wall) test
-        ach = FLOP_PER_TEST * (float(n_local) * N_RAYS * N_WALLS) / (ap_k1_ms * 1e-3) / 1e12
+        ap_tests = float(n_local) * N_RAYS * N_WALLS
+        ach = FLOP_PER_TEST * ap_tests / (ap_k1_ms * 1e-3) / 1e12
+        ach_exec = 16 * ap_tests / (ap_k1_ms * 1e-3) / 1e12
         roof_ap = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                   "executed": {"flop_per_test": 16, "achieved": ach_exec, "frac": ach_exec / peak_tflops,
+                                "note": "o4 reuses the two differences of o2 and o3 is hoisted per (thread, wall): 16 "
+                                        "FP32 ops execute per test against the 20 of SURVEY.md 8d"},
                    "traffic": measured_traffic("raycast_walls_kernel", n_local),
                    "algorithmic_bytes": float(n_local) * (16 + 8 * N_RAYS),
                    "kernel": "raycast_walls_kernel<16,1>", "kernel_ms": ap_k1_ms,
@@ -459,29 +686,30 @@ def run_ours(args):
                 "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
                 "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
                 "share_of_step": k2_ms / (k1_ms + k2_ms),
+                "frac_of_nominal_8tbs": k2_gbs / 8000.0,
                 "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
-        # the culled ray cast is instruction-issue bound: warp instructions (ncu, committed under profiles/) against
-        # the issue rate of 4 schedulers per SM
-        rc_prof = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            rc_prof = json.load(open(tp)).get("raycast_walls_grid_kernel")
-        rc_roof = None
-        if rc_prof:
-            winst = rc_prof["warp_instructions_per_launch"] * n_local / rc_prof["agents"]
-            issue_peak = sms * 4 * sm_max * 1e6
-            rc_roof = {"bound": "issue", "achieved": winst / (k1_ms * 1e-3) / 1e9, "peak": issue_peak / 1e9,
-                       "unit": "G warp-instructions/s", "frac": winst / (k1_ms * 1e-3) / issue_peak,
-                       "traffic": rc_prof["dram_bytes_per_launch"] * n_local / rc_prof["agents"],
-                       "peak_basis": f"{sms} SMs x 4 warp schedulers x {sm_max:.0f} MHz; instruction count from "
-                                     "profiles/r01_traffic.json (ncu smsp__inst_executed.sum of this workload)"}
+        # the culled ray cast against its two floors: bytes (pose in, dist + hit out) and instructions (the walls the
+        # grid lists for the agents' cells x 16 executed FP32 ops per (ray, wall) + the output), not against its own
+        # instruction count
+        rc_bytes = float(n_local) * 16 + float(n_local) * N_RAYS * 8
+        listed_pairs = float(listed_host[0]) * N_RAYS            # (ray, wall) tests the kernel has to evaluate
+        floor_bytes_ms = rc_bytes / (hbm * 1e9) * 1e3
+        floor_inst_ms = listed_pairs * 16 / (peak_tflops * 1e12) * 1e3
         roof_rc = {"kernel": "raycast_walls_grid_kernel (wall lists built once, cached)", "kernel_ms": k1_ms,
-                   "roofline": rc_roof,
                    "share_of_step": k1_ms / (k1_ms + k2_ms),
+                   "algorithmic_bytes": rc_bytes, "gbs": rc_bytes / (k1_ms * 1e-3) / 1e9,
+                   "frac_of_hbm": rc_bytes / (k1_ms * 1e-3) / 1e9 / hbm,
+                   "listed_walls_per_active_agent": listed_host[0] / max(listed_host[1], 1),
+                   "floors_ms": {"bytes": floor_bytes_ms, "fp32_of_listed_tests": floor_inst_ms},
+                   "frac_of_larger_floor": max(floor_bytes_ms, floor_inst_ms) / k1_ms,
+                   "executed_tests_per_sec": listed_pairs / (k1_ms * 1e-3),
                    "algorithmic_tests_per_sec": float(n_local) * N_RAYS * N_WALLS / (k1_ms * 1e-3),
                    "speedup_vs_all_pairs_kernel": ap_k1_ms / k1_ms,
-                   "note": "spatial cull: per grid cell only the walls that can matter are tested (~14 of 1000 here); "
-                           "bit-identical to the all-pairs kernel, so a FLOP roofline no longer describes it"}
+                   "note": "spatial cull: per grid cell only the walls that can matter are tested; bit-identical to the "
+                           "all-pairs kernel. Floors: algorithmic bytes / measured HBM, and listed (ray, wall) tests x "
+                           "16 FP32 ops / non-FMA FP32 peak"}
+        ceil_gbs = ceil_bytes * world / (ceil_ms * 1e-3) / 1e9
+        e2e_floor_ms = (h2d + d2h) / world / (ceil_bytes / (ceil_ms * 1e-3)) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -491,22 +719,56 @@ def run_ours(args):
                        "tick": ["fgx_raycast_walls_grid (ray_generator + ray_wall_sensor + min/argmin over the walls a "
                                 "uniform grid lists for the agent's cell; results bit-identical to all-pairs)",
                                 "fgx_forager_step (WilsonCowan policy + physics)"],
+                       "value_counts": "agents x rays x walls per tick = algorithmic pairs (SURVEY.md 8d), all slots, "
+                                       "whether or not the kernel culls them; see executed_tests_per_sec and all_pairs",
                        "l2": "per-step working set 11.6 GB of per-agent weights + 272 MB ray I/O >> 126 MB L2"},
             "agent_steps_per_sec": N_AGENTS / (ms_step * 1e-3),
+            "executed_tests_per_sec": listed_pairs * world / (ms_step * 1e-3),
             "roofline": roof, "raycast_stage": roof_rc, "all_pairs": all_pairs,
             "e2e": {"value": tests_per_step / (e2e_ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step,
-                    "agent_steps_per_sec": N_AGENTS / (e2e_ms_step * 1e-3)},
+                    "agent_steps_per_sec": N_AGENTS / (e2e_ms_step * 1e-3),
+                    "copy_ceiling": {"pinned_d2h_gbs_all_ranks": ceil_gbs, "bytes_per_rank": ceil_bytes,
+                                     "ms_for_this_steps_bytes": e2e_floor_ms,
+                                     "e2e_ms_over_ceiling_ms": e2e_ms_step / e2e_floor_ms,
+                                     "note": "measured here: every rank copies its result-sized buffer device -> "
+                                             "pinned host at once, nothing else running; (H2D + D2H bytes of a step) "
+                                             "/ that rate is the floor of the e2e leg"}},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if parity:
+            line["parity"] = parity
         if agent_sensing:
             line["agent_sensing"] = agent_sensing
+        if c5:
+            line["c5_churn"] = c5
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(work, args.cpu_sample)
+            cb = line["cpu_baseline"]
+            line["all_pairs_vs_cpu"] = {"gpu_all_pairs_tests_per_sec": all_pairs["value"],
+                                        "cpu_tests_per_sec": cb["value"], "ratio": all_pairs["value"] / cb["value"],
+                                        "note": "like for like: neither side culls (the CPU port is all-pairs)"}
+        if world == 1 and not args.no_extra:
+            line["other_configs"] = other_configs()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs():
+    """BASELINE configs 2 and 3 (scripts/bench_foraging.py, scripts/bench_wolf_sheep.py), each in its own process on
+    the same GPU after the main measurement; their last stdout line is a JSON record."""
+    out = {}
+    for name, script in (("c2_foraging_world", "bench_foraging.py"), ("c3_wolf_sheep_grass", "bench_wolf_sheep.py")):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script)], capture_output=True, text=True,
+                               timeout=240, cwd=ROOT)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out[name] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": r.stderr[-300:]}
+        except (subprocess.TimeoutExpired, ValueError) as e:
+            out[name] = {"error": str(e)[:300]}
+    return out
 
 
 def main():
@@ -518,6 +780,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=40_000, help="agents in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-agent-sensing", action="store_true", help="skip the extra agent-agent sensing stage")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (digests + oracle slice)")
+    ap.add_argument("--parity-rows", type=int, default=2000, help="agents of the oracle slice of the parity block")
+    ap.add_argument("--write-parity-golden", action="store_true",
+                    help="also write gpurun_out/bench_parity_digest.json (copy it to tests/golden/ from a 1-GPU run)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 churn leg")
+    ap.add_argument("--c5-slots", type=int, default=10_000_000)
+    ap.add_argument("--c5-ticks", type=int, default=20)
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-2 / config-3 subprocess legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

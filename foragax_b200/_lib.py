@@ -69,6 +69,7 @@ _decl("fgx_select_scratch_bytes", sz, i64)
 _decl("fgx_select", C.c_int, C.POINTER(Predicate), i64, vp, vp, vp, sz, vp)
 _decl("fgx_argsort_scratch_bytes", sz, i64)
 _decl("fgx_argsort", C.c_int, vp, i32, i64, i32, vp, vp, sz, vp)
+_decl("fgx_sort_rows", C.c_int, vp, i32, i64, i32, vp, C.POINTER(Leaf), i32, vp, sz, vp)
 _decl("fgx_gather_rows", C.c_int, C.POINTER(Leaf), i32, vp, i64, vp)
 _decl("fgx_gather_rows_from", C.c_int, C.POINTER(Leaf), i32, vp, i64, i64, vp)
 _decl("fgx_pack_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, vp, i64, vp, C.POINTER(i64), i32, i32, vp)
@@ -76,12 +77,15 @@ _decl("fgx_key_chain_advance", C.c_int, i32, vp, vp, vp, vp)
 _decl("fgx_sort_key_images", C.c_int, vp, i32, i64, i32, vp, vp, vp)
 _decl("fgx_sort_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, i64, vp, i64, C.POINTER(i64), i32, i32, vp, vp)
 _decl("fgx_count_active", C.c_int, vp, i64, vp, vp)
+_decl("fgx_count_active_clip", C.c_int, vp, i64, vp, vp, vp)
 _decl("fgx_create_base", C.c_int, C.POINTER(u32), i64, i64, i32, vp, vp, vp, vp, vp)
 _decl("fgx_create_base_shard", C.c_int, C.POINTER(u32), i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, vp)
 _decl("fgx_raycast_walls", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, vp, vp, vp)
 _decl("fgx_raycast_walls_grid_scratch_bytes", sz, i64, f32, f32, f32, f32, f32)
 _decl("fgx_raycast_walls_grid", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, f32, f32, f32, f32,
       vp, vp, vp, sz, i32, vp)
+_decl("fgx_raycast_walls_grid_listed", C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, sz, i32,
+      vp, vp)
 _decl("fgx_raycast_agents_scratch_bytes", sz, i64, i64, f32, f32, f32, f32, f32, f32)
 _decl("fgx_raycast_agents", C.c_int, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, i64, i64, f32, f32, f32, f32,
       f32, i32, vp, vp, vp, sz, vp)

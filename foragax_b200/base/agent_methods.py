@@ -83,10 +83,24 @@ def count_active(agents):
     return out
 
 
+def count_active_clip(agents, num_agents_add):
+    """``(n_active, min(num_agents_add, N - n_active))`` as int32[1] device tensors in ONE launch: the count of
+    ``add_agents`` (agent_methods.py:27) and the caller's clip to the free slots (README.md:124-125,
+    hello_world.ipynb:138-139, sim.py:520-521)."""
+    a = agents.active_state
+    out = torch.empty(3, dtype=torch.int32, device=a.device)
+    k = L.device_i32(num_agents_add)
+    L.check(L.lib.fgx_count_active_clip(L.ptr(a), a.shape[0], L.ptr(k), L.ptr(out), L.stream()))
+    return out[0:1], out[1:2]
+
+
 # agent_methods.py:26-38
-def add_agents(add_func, num_agents_add, add_params, agents, key):
+def add_agents(add_func, num_agents_add, add_params, agents, key, num_active=None):
+    """``num_active`` (optional, not in the reference signature): ``jnp.sum(agents.active_state)`` as an int32
+    device scalar when the caller already holds it (the clip before an add computes it, README.md:124-125);
+    otherwise it is counted here as the reference does (agent_methods.py:27)."""
     require_native(add_func, "add_func")
-    id_last_active = count_active(agents)
+    id_last_active = count_active(agents) if num_active is None else L.device_i32(num_active)
     rows = RowRange(id_last_active, L.device_i32(num_agents_add))
     new_agents, key = add_func(add_params, agents, rows, key)
     return new_agents, key
@@ -157,37 +171,65 @@ def argsort(quantity, ascend=True):
     return perm
 
 
-def take_rows(agents, ids):
-    """``tree_map(lambda x: jnp.take(x, ids, axis=0), agents)`` in one launch per 32 leaves; ``ids`` may be shorter
-    (or longer) than the slot axis: the result has ``len(ids)`` rows."""
-    n = ids.shape[0]
+def _leaf_table(agents, n_out):
+    """(leaves, fresh destination buffers of n_out rows, [(src, dst, row_bytes)]) of an agent pytree."""
     leaves = struct.tree_leaves(agents)
     n_src = leaves[0].shape[0] if leaves else 0
-    outs = []
-    table = []
+    outs, table = [], []
     for x in leaves:
         if x.shape[0] != n_src:
             raise L.FgxError("every agent leaf must have the slot axis first")
         src = x if x.is_contiguous() else x.contiguous()
-        dst = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        dst = torch.empty((n_out,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
         outs.append(dst)
         row_bytes = src.element_size() * (src.numel() // n_src) if n_src else 0
         table.append((src, dst, row_bytes))
+    return n_src, outs, table
+
+
+def _leaf_array(part):
+    arr = (L.Leaf * len(part))()
+    for k, (src, dst, rb) in enumerate(part):
+        arr[k].src, arr[k].dst, arr[k].row_bytes = L.ptr(src), L.ptr(dst), rb
+    return arr
+
+
+def take_rows(agents, ids):
+    """``tree_map(lambda x: jnp.take(x, ids, axis=0), agents)`` in one launch per 32 leaves; ``ids`` may be shorter
+    (or longer) than the slot axis: the result has ``len(ids)`` rows."""
+    n = ids.shape[0]
+    n_src, outs, table = _leaf_table(agents, n)
     if n and n_src:
         for s in range(0, len(table), L.MAX_LEAVES):
             part = table[s:s + L.MAX_LEAVES]
-            arr = (L.Leaf * len(part))()
-            for k, (src, dst, rb) in enumerate(part):
-                arr[k].src, arr[k].dst, arr[k].row_bytes = L.ptr(src), L.ptr(dst), rb
-            L.check(L.lib.fgx_gather_rows_from(arr, len(part), L.ptr(ids), n, n_src, L.stream()))
+            L.check(L.lib.fgx_gather_rows_from(_leaf_array(part), len(part), L.ptr(ids), n, n_src, L.stream()))
     it = iter(outs)
     return struct.tree_map(lambda x: next(it), agents)
 
 
 # agent_methods.py:74-79
 def sort_agents(quantity, ascend, agents):
-    sorted_ids = argsort(quantity, ascend)
-    return take_rows(agents, sorted_ids), sorted_ids
+    """argsort + ``take`` of every leaf as ONE native call (``fgx_sort_rows``): a two-valued key (the sort on
+    ``active_state``) is partitioned and its rows are moved by a single kernel that reads the key once."""
+    q = quantity.reshape(-1)
+    if q.dtype == torch.bool:
+        q = q.to(torch.int32)
+    if not q.is_contiguous():
+        q = q.contiguous()
+    n = q.shape[0]
+    n_src, outs, table = _leaf_table(agents, n)
+    if len(table) > L.MAX_LEAVES or n_src != n:
+        sorted_ids = argsort(quantity, ascend)
+        return take_rows(agents, sorted_ids), sorted_ids
+    if isinstance(ascend, torch.Tensor):
+        ascend = bool(ascend.item())
+    perm = torch.empty(n, dtype=torch.int32, device=q.device)
+    nbytes = L.lib.fgx_argsort_scratch_bytes(n)
+    scr = L.scratch(nbytes)
+    L.check(L.lib.fgx_sort_rows(L.ptr(q), L.dtype_code(q), n, 0 if ascend else 1, L.ptr(perm), _leaf_array(table),
+                                len(table), L.ptr(scr), nbytes, L.stream()))
+    it = iter(outs)
+    return struct.tree_map(lambda x: next(it), agents), perm
 
 
 jit_sort_agents = sort_agents

@@ -127,18 +127,39 @@ GRID_MIN_WALLS = 32  # below this the all-pairs kernel is as fast as building th
 _wall_grids = weakref.WeakKeyDictionary()  # Wall -> (key, scratch holding its grid): walls are static (create_space)
 
 
+class _GridTicket:
+    """One use of a wall grid: ``reuse`` tells the native call whether the scratch already holds the lists;
+    :meth:`done` is called AFTER the native call returned FGX_OK -- only then does the cache learn that the grid
+    exists (a call that raised, e.g. on a bad argument before the build, must not leave a cache entry pointing
+    at uninitialised scratch) -- and records the build on the launching stream so that a later call on another
+    stream waits for it."""
+    __slots__ = ("bounds", "scratch", "reuse", "_walls", "_key")
+
+    def __init__(self, bounds, scratch, reuse, walls, key):
+        self.bounds, self.scratch, self.reuse, self._walls, self._key = bounds, scratch, reuse, walls, key
+
+    def done(self):
+        if not self.reuse:
+            ev = None
+            if not torch.cuda.is_current_stream_capturing():  # a captured build is ordered by the graph itself
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+            _wall_grids[self._walls] = (self._key, self.scratch, ev, L.stream())
+
+
 def wall_grid(walls, bounds, ray_length):
-    """``(bounds as floats, scratch tensor, reuse flag)`` of the wall lists for ``fgx_raycast_walls_grid`` /
-    ``fgx_forager_sense_step``: built by the first call that passes ``reuse == 0`` and cached per Wall object."""
+    """A :class:`_GridTicket` for ``fgx_raycast_walls_grid`` / ``fgx_forager_sense_step``: the wall lists are built
+    by the first successful call (``reuse == 0``) and cached per Wall object."""
     w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
     b = [float(v) for v in bounds]
     key = (tuple(b), float(ray_length), nw, w1, w2, w3, w4, keep[0].device.index if keep else None)
     ent = _wall_grids.get(walls)
     if ent is not None and ent[0] == key:
-        return b, ent[1], 1
+        if ent[2] is not None and ent[3] != L.stream() and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream().wait_event(ent[2])  # built on another stream: order this one after it
+        return _GridTicket(b, ent[1], 1, walls, key)
     scr = L.scratch(L.lib.fgx_raycast_walls_grid_scratch_bytes(nw, b[0], b[1], b[2], b[3], float(ray_length)))
-    _wall_grids[walls] = (key, scr)
-    return b, scr, 0
+    return _GridTicket(b, scr, 0, walls, key)
 
 
 def invalidate_wall_grid(walls):
@@ -170,14 +191,32 @@ def raycast_walls(agent_pos, ray_span, ray_length, walls, active_state=None, n_r
         dist, hit = out
     w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
     if bounds is not None and nw >= GRID_MIN_WALLS:
-        b, scr, reuse = wall_grid(walls, bounds, ray_length)
+        tk = wall_grid(walls, bounds, ray_length)
+        b, scr = tk.bounds, tk.scratch
         L.check(L.lib.fgx_raycast_walls_grid(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                              float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2], b[3],
-                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), scr.numel(), reuse, L.stream()))
+                                             L.ptr(dist), L.ptr(hit), L.ptr(scr), scr.numel(), tk.reuse, L.stream()))
+        tk.done()
         return dist, hit
     L.check(L.lib.fgx_raycast_walls(L.ptr(x), L.ptr(y), L.ptr(ang), L.ptr(act), n, r, float(ray_span),
                                     float(ray_length), w1, w2, w3, w4, nw, L.ptr(dist), L.ptr(hit), L.stream()))
     return dist, hit
+
+
+def wall_grid_listed(agent_pos, walls, bounds, ray_length, active_state=None):
+    """``(listed, active)`` int64[2] device tensor: the number of (agent, wall) pairs the culled kernel evaluates
+    per ray for these agents (sum of the agents' cell lists) and the number of active agents."""
+    x, y = _f32(agent_pos[0]), _f32(agent_pos[1])
+    act = None if active_state is None else _f32(active_state)
+    w1, w2, w3, w4, nw, keep = _wall_ptrs(walls)
+    tk = wall_grid(walls, bounds, ray_length)
+    b, scr = tk.bounds, tk.scratch
+    out = torch.empty(2, dtype=torch.int64, device=x.device)
+    L.check(L.lib.fgx_raycast_walls_grid_listed(L.ptr(x), L.ptr(y), L.ptr(act), x.shape[0], w1, w2, w3, w4, nw, b[0],
+                                                b[1], b[2], b[3], float(ray_length), L.ptr(scr), scr.numel(), tk.reuse,
+                                                L.ptr(out), L.stream()))
+    tk.done()
+    return out
 
 
 def raycast_agents(agent_pos, ray_span, ray_length, targets, bounds, max_rad, active_state=None, n_rays=None,

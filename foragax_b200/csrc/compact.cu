@@ -4,17 +4,24 @@
 // argsort(-mask) -> (count, permutation).  The permutation is "selected slots
 // ascending, then unselected slots ascending", so the O(N log N) comparison
 // sort of the reference is a 1-bit stable partition here:
-//   pass A  selected count of each CTA's contiguous tile range (warp ballots + popc)
-//   pass B  every CTA sums the counts of the CTAs before it (its offset) and of all CTAs
-//           (the total), re-evaluates the predicate (the leaves are L2-resident after
-//           pass A), ranks each slot with ballot/popc prefix sums and writes
-//           perm[rank] or perm[total + i - rank]
+//   one pass (default, up to ~77 M slots): ONE cooperative launch.  Every warp owns a contiguous run
+//           of 256-slot groups: it evaluates the predicate ONCE (leaves read once), keeps the
+//           ballots in shared memory and publishes its CTA's count; after a grid-wide sync every
+//           CTA sums the counts before it (its offset) and all of them (the total -- the position
+//           of an unselected slot depends on it, which is why a chained look-back scan alone
+//           cannot finish the job) and scatters perm[rank] / perm[total + i - rank] from the
+//           saved ballots.  HBM traffic = leaves once + 4 B/slot.
+//   two pass (larger sets): pass A counts per CTA, pass B re-evaluates the predicate and scatters.
 //   small   up to 16,384 slots: ONE 1024-thread CTA holds every flag in registers
 //           (one round of loads, one block scan, one scatter).
 // The predicate is evaluated in-kernel from the agent leaves (up to four
 // comparisons combined by a truth table), so no mask array is materialised.
 // Algorithmic HBM bytes: predicate leaves read once + 4 B/slot written.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace fgx {
 
@@ -182,6 +189,79 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_scatter_kernel(const __grid_
   for (int64_t tile = t0; tile < t1; ++tile) off += tile_scatter(p, tile, n, off, total, perm, warp_sums);
 }
 
+// ---- one pass: cooperative launch, predicate evaluated once, ballots parked in shared memory ----------
+constexpr int OP_GROUP = 32 * SEL_ITEMS;  // 256 slots: lane l holds rows r = 0..7 (slot g*256 + r*32 + l)
+constexpr int OP_MAX_GPW = 32;            // groups per warp the ballots of which fit (8 KB of shared memory)
+
+__global__ void __launch_bounds__(SEL_BLOCK) select_onepass_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
+                                                                  int64_t groups, int gpw,
+                                                                  int32_t* __restrict__ cta_count,
+                                                                  int32_t* __restrict__ perm,
+                                                                  int32_t* __restrict__ count_out) {
+  __shared__ unsigned balls[SEL_WARPS][OP_MAX_GPW][SEL_ITEMS];
+  __shared__ int wcount[SEL_WARPS];
+  __shared__ int warp_sums[SEL_WARPS];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int64_t g0 = ((int64_t)blockIdx.x * SEL_WARPS + w) * gpw;
+  const int mine = (int)max((int64_t)0, min((int64_t)gpw, groups - g0));  // groups of this warp (warp-uniform)
+  int c = 0;
+  int k = 0;
+  for (; k + 2 <= mine; k += 2) {  // two groups per trip: 16 independent loads per term in flight
+    const unsigned f0 = flags_at<SEL_ITEMS>(p, (g0 + k) * OP_GROUP, n, l);
+    const unsigned f1 = flags_at<SEL_ITEMS>(p, (g0 + k + 1) * OP_GROUP, n, l);
+#pragma unroll
+    for (int r = 0; r < SEL_ITEMS; ++r) {
+      const unsigned b0 = __ballot_sync(0xffffffffu, (f0 >> r) & 1u), b1 = __ballot_sync(0xffffffffu, (f1 >> r) & 1u);
+      if (l == r) { balls[w][k][r] = b0; balls[w][k + 1][r] = b1; }
+      c += __popc(b0) + __popc(b1);
+    }
+  }
+  if (k < mine) {
+    const unsigned f0 = flags_at<SEL_ITEMS>(p, (g0 + k) * OP_GROUP, n, l);
+#pragma unroll
+    for (int r = 0; r < SEL_ITEMS; ++r) {
+      const unsigned b0 = __ballot_sync(0xffffffffu, (f0 >> r) & 1u);
+      if (l == r) balls[w][k][r] = b0;
+      c += __popc(b0);
+    }
+  }
+  if (l == 0) wcount[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int q = 0; q < SEL_WARPS; ++q) t += wcount[q];
+    __stcg(cta_count + blockIdx.x, t);
+  }
+  cg::this_grid().sync();
+  int before = 0, all = 0;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += SEL_BLOCK) {
+    const int v = __ldcg(cta_count + q);
+    all += v;
+    if (q < (int)blockIdx.x) before += v;
+  }
+  const int total = block_sum(all, warp_sums);
+  int off = block_sum(before, warp_sums);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = total;
+#pragma unroll
+  for (int q = 0; q < SEL_WARPS; ++q)
+    if (q < w) off += wcount[q];
+  const unsigned lt = lanemask_lt();
+  for (k = 0; k < mine; ++k) {
+    const int64_t base = (g0 + k) * OP_GROUP;
+#pragma unroll
+    for (int r = 0; r < SEL_ITEMS; ++r) {
+      const unsigned b = balls[w][k][r];
+      const int64_t i = base + r * 32 + l;
+      if (i < n) {
+        const int rank = off + __popc(b & lt);
+        perm[(b >> l) & 1u ? (int64_t)rank : (int64_t)total + (i - rank)] = (int32_t)i;
+      }
+      off += __popc(b);
+    }
+  }
+}
+
 // small sets (<= 16384 slots): ONE CTA of 1024 threads holds every slot's flag in registers -- one round
 // of loads, one block scan, one scatter (config C2's select calls are latency-bound, not bandwidth-bound)
 constexpr int SEL_SMALL_BLOCK = 1024;
@@ -264,6 +344,29 @@ int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32
   FGX_REQUIRE(scratch && scratch_bytes >= fgx_select_scratch_bytes(n), "fgx_select: scratch too small");
   FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 3) == 0, "fgx_select: scratch must be 4-byte aligned");
   int32_t* cta_count = reinterpret_cast<int32_t*>(scratch);
+  {  // one cooperative pass whenever the ballots of a warp's groups fit in shared memory
+    static const bool two_pass = [] { const char* v = getenv("FGX_SELECT_TWO_PASS"); return v && atoi(v) == 1; }();
+    static int per_sm = -1;
+    if (per_sm < 0) {
+      int q = 0;
+      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, select_onepass_kernel, SEL_BLOCK, 0);
+      per_sm = (oe == cudaSuccess && q >= 1) ? q : 0;
+    }
+    int64_t coop = (int64_t)sm_count() * per_sm;
+    if (coop > SEL_MAX_GRID) coop = SEL_MAX_GRID;
+    const int64_t groups = ceil_div(n, OP_GROUP);
+    if (!two_pass && coop >= 1 && ceil_div(groups, coop * SEL_WARPS) <= OP_MAX_GPW) {
+      int gpw = (int)ceil_div(groups, coop * SEL_WARPS);
+      const int grid = (int)ceil_div(groups, (int64_t)gpw * SEL_WARPS);
+      fgx_predicate_t pred = *pred_host;
+      int64_t n_arg = n, groups_arg = groups;
+      void* args[] = {&pred, &n_arg, &groups_arg, &gpw, &cta_count, &perm, &count};
+      cudaError_t e = cudaLaunchCooperativeKernel((const void*)select_onepass_kernel, dim3((unsigned)grid),
+                                                  dim3(SEL_BLOCK), args, 0, s);
+      if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_select: cooperative launch: %s", cudaGetErrorString(e));
+      return check_launch("fgx_select(one pass)");
+    }
+  }
   int64_t cap = (int64_t)sm_count() * 8;
   if (cap > SEL_MAX_GRID) cap = SEL_MAX_GRID;
   const int64_t per = ceil_div(tiles, tiles < cap ? tiles : cap);

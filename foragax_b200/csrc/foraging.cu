@@ -609,13 +609,14 @@ int fgx_forager_sense_step(const fgx_forager_params_t* p, int64_t n, const float
   FGX_REQUIRE(p->n_neurons > 0 && p->n_obs > 0 && p->n_act >= 2, "fgx_forager_sense_step: bad policy shape");
   FGX_REQUIRE(n_rays > 0 && n_rays == p->n_obs - 1,
               "fgx_forager_sense_step: the policy observes the ray distances and its own energy: n_rays must be n_obs - 1");
-  if (n == 0) return FGX_OK;
-  FGX_REQUIRE(active_state && energy_in && age && dist, "fgx_forager_sense_step: null pointer");
   cudaStream_t s = as_stream(stream);
   SenseArgs sense{};
+  // built (reuse_grid == 0) even for an empty agent set: the caller caches the scratch as "built" after this call
   const int rc = wall_grid_prepare("fgx_forager_sense_step", wx1, wy1, wx2, wy2, n_walls, x_min, x_max, y_min, y_max,
                                    ray_length, wall_scratch, wall_scratch_bytes, reuse_grid, s, &sense.v);
   if (rc != FGX_OK) return rc;
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(active_state && energy_in && age && dist, "fgx_forager_sense_step: null pointer");
   sense.enabled = 1;
   sense.n_rays = n_rays;
   sense.span = ray_span;

@@ -178,6 +178,35 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
   }
 }
 
+// statistics of the cull for a set of agents: out[0] = sum over active agents of the walls their rays are tested
+// against (the cell's list; n_walls for agents that take the all-walls loop), out[1] = active agents
+__global__ void __launch_bounds__(256) walls_grid_listed_kernel(WallsGridView v, const float* __restrict__ ax,
+                                                                const float* __restrict__ ay,
+                                                                const float* __restrict__ aactive, int64_t n,
+                                                                unsigned long long* __restrict__ out) {
+  unsigned long long listed = 0, act = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (aactive != nullptr && aactive[i] == 0.0f) continue;
+    ++act;
+    const float fx = (ax[i] - v.g.x0) * v.g.inv_cs, fy = (ay[i] - v.g.y0) * v.g.inv_cs;
+    const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
+    if (inside && v.st->fallback == 0) {
+      const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
+      listed += v.start[cell + 1] - v.start[cell];
+    } else {
+      listed += (unsigned long long)v.n_walls;
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    listed += __shfl_xor_sync(0xffffffffu, listed, d);
+    act += __shfl_xor_sync(0xffffffffu, act, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, listed);
+    atomicAdd(out + 1, act);
+  }
+}
+
 static inline size_t wg_al(size_t x) { return (x + 255) / 256 * 256; }
 
 static int wgrid_dims(float x_min, float x_max, float y_min, float y_max, float L, WGrid* g) {
@@ -277,17 +306,38 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
   using namespace fgx;
   FGX_REQUIRE(n_agents >= 0, "fgx_raycast_walls_grid: bad sizes");
   FGX_REQUIRE(n_rays > 0, "fgx_raycast_walls_grid: n_rays must be > 0");
-  if (n_agents == 0) return FGX_OK;
-  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls_grid: null pointer");
   cudaStream_t s = as_stream(stream);
   WallsGridArgs a{};
+  // the grid is built (reuse_grid == 0) even for an empty agent set: the caller caches the scratch as "built"
   const int rc = wall_grid_prepare("fgx_raycast_walls_grid", wx1, wy1, wx2, wy2, n_walls, x_min, x_max, y_min, y_max,
                                    ray_length, scratch, scratch_bytes, reuse_grid, s, &a.v);
   if (rc != FGX_OK) return rc;
+  if (n_agents == 0) return FGX_OK;
+  FGX_REQUIRE(x && y && ang && dist, "fgx_raycast_walls_grid: null pointer");
   a.ax = x; a.ay = y; a.aang = ang; a.aactive = active;
   a.n = n_agents; a.n_rays = n_rays; a.span = ray_span; a.L = ray_length;
   a.dist = dist; a.hit = hit;
   raycast_walls_grid_kernel<<<grid_for(n_agents * n_rays, 256, 8), 256, 0, s>>>(a);
   return check_launch("fgx_raycast_walls_grid");
+}
+
+int fgx_raycast_walls_grid_listed(const float* x, const float* y, const float* active, int64_t n_agents, const float* wx1,
+                                  const float* wy1, const float* wx2, const float* wy2, int64_t n_walls, float x_min,
+                                  float x_max, float y_min, float y_max, float ray_length, void* scratch,
+                                  size_t scratch_bytes, int32_t reuse_grid, int64_t* out2, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n_agents >= 0 && out2, "fgx_raycast_walls_grid_listed: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(int64_t), s);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_walls_grid_listed: %s", cudaGetErrorString(e));
+  WallsGridView v{};
+  const int rc = wall_grid_prepare("fgx_raycast_walls_grid_listed", wx1, wy1, wx2, wy2, n_walls, x_min, x_max, y_min,
+                                   y_max, ray_length, scratch, scratch_bytes, reuse_grid, s, &v);
+  if (rc != FGX_OK) return rc;
+  if (n_agents == 0) return FGX_OK;
+  FGX_REQUIRE(x && y, "fgx_raycast_walls_grid_listed: null pointer");
+  walls_grid_listed_kernel<<<grid_for(n_agents, 256, 8), 256, 0, s>>>(v, x, y, active, n_agents,
+                                                                      reinterpret_cast<unsigned long long*>(out2));
+  return check_launch("fgx_raycast_walls_grid_listed");
 }
 }

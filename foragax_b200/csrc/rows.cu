@@ -7,66 +7,61 @@
 // of a warp copy consecutive chunks of one row (wide leaves: the per-agent RNN
 // weights, 6.4 KB rows) or consecutive rows (scalar leaves).  HBM-bound:
 // 2 * row_bytes per slot + 4 B of index.
-#include "common.cuh"
+#include "rows.cuh"
 #include "threefry.cuh"
 
 namespace fgx {
 
-struct LeafTable {
-  fgx_leaf_t leaf[FGX_MAX_LEAVES];
-  int32_t vec[FGX_MAX_LEAVES];  // bytes per copy chunk: 16 / 8 / 4 / 2 / 1
-};
-
-// Narrow leaves (row <= 8 vector chunks of T): one thread per row, FOUR rows per thread with all index
-// loads, then all gathers, then all stores -- four independent gathers in flight per thread.
-// Wide leaves (per-agent weight matrices): one warp per row, lanes stride the 16-byte chunks
-// (coalesced 512 B per step).  grid.y = leaf in both kernels.
+// Narrow leaves (row <= 8 vector chunks of T): one thread per row, FOUR rows per thread.  The index of a row is
+// loaded ONCE and reused for every leaf (an earlier version ran one grid.y slice per leaf and re-read the
+// 4 B/slot permutation for each of them: 7x the index traffic on a Dice set); per leaf all four gathers are in
+// flight before the first store.  Wide leaves (per-agent weight matrices): one warp per row, lanes stride the
+// 16-byte chunks (coalesced 512 B per step), grid.y = leaf.
 __device__ __forceinline__ int64_t clamp_index(int64_t s, int64_t n) { return s < 0 ? 0 : (s >= n ? n - 1 : s); }
 
 template <typename T>
-__device__ __forceinline__ void gather_narrow(const fgx_leaf_t& lf, const int32_t* __restrict__ perm, int64_t n,
-                                              int64_t n_src) {
+__device__ __forceinline__ void gather_narrow4(const fgx_leaf_t& lf, const int64_t (&s)[4], const int64_t (&r)[4],
+                                               int64_t n) {
   const int64_t chunks = lf.row_bytes / (int64_t)sizeof(T);
   const T* __restrict__ src = reinterpret_cast<const T*>(lf.src);
   T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n; row += 4 * nthreads) {
-    int64_t s[4];
+  if (chunks == 1) {
+    T v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t r = row + u * nthreads;
-      s[u] = r < n ? clamp_index(__ldg(perm + r), n_src) : 0;  // jnp.take clamps
-    }
-    if (chunks == 1) {
-      T v[4];
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + s[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + s[u]);
+    for (int u = 0; u < 4; ++u)
+      if (r[u] < n) dst[r[u]] = v[u];
+  } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t r = row + u * nthreads;
-        if (r < n) dst[r] = v[u];
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t r = row + u * nthreads;
-        if (r < n)
-          for (int64_t c = 0; c < chunks; ++c) dst[r * chunks + c] = __ldg(src + s[u] * chunks + c);
-      }
-    }
+    for (int u = 0; u < 4; ++u)
+      if (r[u] < n)
+        for (int64_t c = 0; c < chunks; ++c) dst[r[u] * chunks + c] = __ldg(src + s[u] * chunks + c);
   }
 }
 
-__global__ void __launch_bounds__(256) gather_narrow_kernel(const __grid_constant__ LeafTable tab,
+__global__ void __launch_bounds__(256) gather_narrow_kernel(const __grid_constant__ LeafTable tab, int n_leaves,
                                                             const int32_t* __restrict__ perm, int64_t n,
-                                                            int64_t n_src) {
-  const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
-  switch (tab.vec[blockIdx.y]) {
-    case 16: gather_narrow<uint4>(lf, perm, n, n_src); break;
-    case 8: gather_narrow<uint2>(lf, perm, n, n_src); break;
-    case 4: gather_narrow<uint32_t>(lf, perm, n, n_src); break;
-    case 2: gather_narrow<uint16_t>(lf, perm, n, n_src); break;
-    default: gather_narrow<uint8_t>(lf, perm, n, n_src); break;
+                                                            int64_t n_src, const int32_t* __restrict__ skip) {
+  if (skip != nullptr && __ldcg(skip) != 0) return;  // uniform over the grid: written by an earlier launch
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n; row += 4 * nthreads) {
+    int64_t s[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      r[u] = row + u * nthreads;
+      s[u] = r[u] < n ? clamp_index(__ldg(perm + r[u]), n_src) : 0;  // jnp.take clamps
+    }
+    for (int t = 0; t < n_leaves; ++t) {
+      const fgx_leaf_t& lf = tab.leaf[t];
+      switch (tab.vec[t]) {
+        case 16: gather_narrow4<uint4>(lf, s, r, n); break;
+        case 8: gather_narrow4<uint2>(lf, s, r, n); break;
+        case 4: gather_narrow4<uint32_t>(lf, s, r, n); break;
+        case 2: gather_narrow4<uint16_t>(lf, s, r, n); break;
+        default: gather_narrow4<uint8_t>(lf, s, r, n); break;
+      }
+    }
   }
 }
 
@@ -96,11 +91,21 @@ __global__ void __launch_bounds__(256) gather_wide_kernel(const __grid_constant_
   }
 }
 
+// out[0] += this CTA's count; clip_in != nullptr: the LAST CTA to finish (ticket in out[2]) also writes
+// out[1] = min(*clip_in, n - out[0]) -- the caller's "at most as many new agents as free slots" clip
+// (README.md:124-125) without a second launch.  All loads of a thread are issued before the adds.
 __global__ void __launch_bounds__(256) count_active_kernel(const float* __restrict__ active, int64_t n,
-                                                           int32_t* __restrict__ out) {
+                                                           int32_t* __restrict__ out,
+                                                           const int32_t* __restrict__ clip_in) {
   int c = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    c += (int)active[i];  // sum(x, dtype=int32) converts each element first
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const float a0 = __ldg(active + i), a1 = __ldg(active + i + stride), a2 = __ldg(active + i + 2 * stride),
+                a3 = __ldg(active + i + 3 * stride);
+    c += (int)a0 + (int)a1 + (int)a2 + (int)a3;  // sum(x, dtype=int32) converts each element first
+  }
+  for (; i < n; i += stride) c += (int)__ldg(active + i);
   c = __reduce_add_sync(0xffffffffu, c);
   __shared__ int ws[8];
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
@@ -109,6 +114,15 @@ __global__ void __launch_bounds__(256) count_active_kernel(const float* __restri
     int t = 0;
     for (int k = 0; k < 8; ++k) t += ws[k];
     if (t) atomicAdd(out, t);
+    if (clip_in != nullptr) {
+      __threadfence();
+      if (atomicAdd(out + 2, 1) == (int)gridDim.x - 1) {
+        __threadfence();
+        const int64_t free_slots = n - (int64_t)__ldcg(out);
+        const int64_t want = *clip_in;
+        out[1] = (int32_t)(want < free_slots ? want : free_slots);
+      }
+    }
   }
 }
 
@@ -127,6 +141,35 @@ __global__ void __launch_bounds__(256) create_base_kernel(Key root, int64_t n_to
     active[j] = i < n_active ? 1.0f : 0.0f;
     atype[j] = type;
   }
+}
+
+int classify_leaves(const char* what, const fgx_leaf_t* leaves_host, int32_t n_leaves, LeafTable* narrow, int* nn,
+                    LeafTable* wide, int* nw) {
+  *nn = *nw = 0;
+  for (int k = 0; k < n_leaves; ++k) {
+    const fgx_leaf_t& lf = leaves_host[k];
+    FGX_REQUIRE(lf.src && lf.dst && lf.row_bytes > 0, "%s: leaf %d is malformed", what, k);
+    FGX_REQUIRE(lf.src != lf.dst, "%s: leaf %d aliases its destination", what, k);
+    const int v = leaf_vec(lf);
+    if (lf.row_bytes / v <= 8) {
+      narrow->leaf[*nn] = lf;
+      narrow->vec[(*nn)++] = v;
+    } else {
+      wide->leaf[*nw] = lf;
+      wide->vec[(*nw)++] = v;
+    }
+  }
+  return FGX_OK;
+}
+
+int launch_gather(const LeafTable& narrow, int nn, const LeafTable& wide, int nw, const int32_t* perm, int64_t n,
+                  int64_t n_src, const int32_t* skip_narrow, cudaStream_t s) {
+  if (nn) gather_narrow_kernel<<<grid_for(ceil_div(n, 4), 256, 8), 256, 0, s>>>(narrow, nn, perm, n, n_src, skip_narrow);
+  if (nw) {
+    dim3 grid(grid_for(n * 32, 256, 8), nw);
+    gather_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n, n_src);
+  }
+  return check_launch("fgx_gather_rows");
 }
 
 }  // namespace fgx
@@ -148,32 +191,9 @@ int fgx_gather_rows_from(const fgx_leaf_t* leaves_host, int32_t n_leaves, const 
   FGX_REQUIRE(leaves_host && perm, "fgx_gather_rows: null pointer");
   LeafTable narrow, wide;
   int nn = 0, nw = 0;
-  for (int k = 0; k < n_leaves; ++k) {
-    const fgx_leaf_t& lf = leaves_host[k];
-    FGX_REQUIRE(lf.src && lf.dst && lf.row_bytes > 0, "fgx_gather_rows: leaf %d is malformed", k);
-    FGX_REQUIRE(lf.src != lf.dst, "fgx_gather_rows: leaf %d aliases its destination", k);
-    const uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | reinterpret_cast<uintptr_t>(lf.dst) |
-                           (uintptr_t)lf.row_bytes;
-    int v = 16;
-    while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
-    if (lf.row_bytes / v <= 8) {
-      narrow.leaf[nn] = lf;
-      narrow.vec[nn++] = v;
-    } else {
-      wide.leaf[nw] = lf;
-      wide.vec[nw++] = v;
-    }
-  }
-  cudaStream_t s = as_stream(stream);
-  if (nn) {
-    dim3 grid(grid_for(ceil_div(n, 4), 256, 8), nn);
-    gather_narrow_kernel<<<grid, 256, 0, s>>>(narrow, perm, n, n_src);
-  }
-  if (nw) {
-    dim3 grid(grid_for(n * 32, 256, 8), nw);
-    gather_wide_kernel<<<grid, 256, 0, s>>>(wide, perm, n, n_src);
-  }
-  return check_launch("fgx_gather_rows");
+  const int rc = classify_leaves("fgx_gather_rows", leaves_host, n_leaves, &narrow, &nn, &wide, &nw);
+  if (rc != FGX_OK) return rc;
+  return launch_gather(narrow, nn, wide, nw, perm, n, n_src, nullptr, as_stream(stream));
 }
 
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream) {
@@ -184,8 +204,21 @@ int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_str
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_count_active: %s", cudaGetErrorString(e));
   if (n == 0) return FGX_OK;
   FGX_REQUIRE(active_state, "fgx_count_active: null pointer");
-  count_active_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(active_state, n, out);
+  count_active_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(active_state, n, out, nullptr);
   return check_launch("fgx_count_active");
+}
+
+int fgx_count_active_clip(const float* active_state, int64_t n, const int32_t* n_add, int32_t* out3,
+                          fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && out3 && n_add, "fgx_count_active_clip: bad arguments");
+  FGX_REQUIRE(n == 0 || active_state, "fgx_count_active_clip: null pointer");
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(out3, 0, 3 * sizeof(int32_t), s);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_count_active_clip: %s", cudaGetErrorString(e));
+  // n == 0: one CTA with nothing to count still writes the clip (min(n_add, 0) = 0)
+  count_active_kernel<<<n ? grid_for(n, 256, 8) : 1, 256, 0, s>>>(active_state, n, out3, n_add);
+  return check_launch("fgx_count_active_clip");
 }
 
 int fgx_create_base_shard(const uint32_t key_host[2], int64_t n_total, int64_t n_active, int64_t first,

@@ -5,9 +5,15 @@
 // last).  Here: keys are mapped to order-preserving uint32 images, then
 //   1. stats    per-CTA (min, #min, max, #max) of the images in ONE read of the keys;
 //   2. two-valued fast path (the common sort on active_state or a 0/1 flag): if every
-//      key is the global min or max the sort IS a stable 2-way partition -- one
-//      ballot/popc scatter pass writes the permutation and the general path below is
-//      skipped on device;
+//      key is the global min or max the sort IS a stable 2-way partition.  Up to ~77 M slots
+//      steps 1 + 2 are ONE cooperative launch that reads the keys once: per 256-slot group a
+//      warp keeps the ballots of "key == group minimum" in shared memory and publishes the
+//      (min, #min, max, #max) record of its CTA; after a grid-wide sync every CTA derives the
+//      global extrema and its offset, and scatters -- the permutation AND, for
+//      fgx_sort_rows (= sort_agents, agent_methods.py:74-79), the narrow payload rows of every
+//      leaf: rows are read coalesced at slot i and written once at their sorted position, so
+//      the permutation never makes a round trip through memory and no gather pass runs.  The
+//      general path below is skipped on device;
 //   3. general path: stable LSD radix sort of (image, slot index), 8-bit digits:
 //      prep (images + 4 digit histograms), plan (digit bases, trivial passes),
 //      per pass: tile histogram -> per-digit scan over tiles -> stable scatter with
@@ -19,6 +25,7 @@
 
 #include "common.cuh"
 #include "key_image.cuh"
+#include "rows.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -183,6 +190,156 @@ __global__ void __launch_bounds__(RS_BLOCK)
       rank0 += __popc(ball[r]);
     }
     off += tile_total;
+  }
+}
+
+// ---- 1 + 2 fused: keys read once, narrow payload rows moved in the same pass -----------------
+constexpr int TO_MAX_GPW = 32;  // 256-slot groups per warp the ballots of which fit (8 KB + 1 KB of shared memory)
+
+// rows of one leaf for the 8 slots of a lane (one base pointer, immediate offsets): BATCH loads in flight,
+// then BATCH stores (16-byte rows go four at a time to stay inside the register budget).  Only leaves whose
+// row is ONE 4 / 8 / 16-byte word ride in the fused kernel; anything else is gathered afterwards.
+template <typename T, int BATCH>
+__device__ __forceinline__ void scatter_full8(const fgx_leaf_t& lf, int64_t first, const int (&pos)[TV_ITEMS]) {
+  const T* __restrict__ sp = reinterpret_cast<const T*>(lf.src) + first;
+  T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
+#pragma unroll
+  for (int r0 = 0; r0 < TV_ITEMS; r0 += BATCH) {
+    T v[BATCH];
+#pragma unroll
+    for (int r = 0; r < BATCH; ++r) v[r] = __ldg(sp + (r0 + r) * 32);
+#pragma unroll
+    for (int r = 0; r < BATCH; ++r) dst[pos[r0 + r]] = v[r];
+  }
+}
+// the one partial group at the end of the array
+template <typename T>
+__device__ __forceinline__ void scatter_tail8(const fgx_leaf_t& lf, int64_t first, int64_t n,
+                                              const int (&pos)[TV_ITEMS]) {
+  const T* __restrict__ sp = reinterpret_cast<const T*>(lf.src) + first;
+  T* __restrict__ dst = reinterpret_cast<T*>(lf.dst);
+#pragma unroll
+  for (int r = 0; r < TV_ITEMS; ++r)
+    if (first + r * 32 < n) dst[pos[r]] = __ldg(sp + r * 32);
+}
+
+__global__ void __launch_bounds__(RS_BLOCK, 4)
+    sort_two_onepass_kernel(const void* __restrict__ keys, int dtype, int descending, int64_t n, int64_t groups, int gpw,
+                            TvStat* __restrict__ cta_stat, SortState* __restrict__ st, int32_t* __restrict__ perm,
+                            const __grid_constant__ LeafTable tab, int n_leaves) {
+  __shared__ unsigned balls[RS_WARPS][TO_MAX_GPW][TV_ITEMS];
+  __shared__ uint32_t gmin[RS_WARPS][TO_MAX_GPW];
+  __shared__ TvStat ws[RS_WARPS];
+  __shared__ TvStat gs[RS_WARPS];
+  __shared__ int wbefore[RS_WARPS];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int64_t g0 = ((int64_t)blockIdx.x * RS_WARPS + w) * gpw;
+  const int mine = (int)max((int64_t)0, min((int64_t)gpw, groups - g0));  // warp-uniform
+  const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(keys);
+  TvStat a{0xFFFFFFFFu, 0u, 0u, 0u};
+#pragma unroll 1
+  for (int k = 0; k < mine; ++k) {
+    const int64_t base = (g0 + k) * (32 * TV_ITEMS);
+    uint32_t v[TV_ITEMS];  // all loads first, then the images
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) v[r] = __ldg(kw + min(base + r * 32 + l, n - 1));
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    unsigned valid = 0;
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      v[r] = image_of(v[r], dtype, descending);
+      if (base + r * 32 + l < n) {
+        valid |= 1u << r;
+        lo = min(lo, v[r]);
+        hi = max(hi, v[r]);
+      }
+    }
+    const uint32_t mn = __reduce_min_sync(0xffffffffu, lo), mx = __reduce_max_sync(0xffffffffu, hi);
+    uint32_t cmn = 0, cmx = 0;
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      const unsigned b = __ballot_sync(0xffffffffu, ((valid >> r) & 1u) && v[r] == mn);
+      if (l == r) balls[w][k][r] = b;
+      cmn += __popc(b);
+    }
+    if (mx != mn) {
+#pragma unroll
+      for (int r = 0; r < TV_ITEMS; ++r) cmx += __popc(__ballot_sync(0xffffffffu, ((valid >> r) & 1u) && v[r] == mx));
+    } else {
+      cmx = cmn;
+    }
+    if (l == 0) gmin[w][k] = mn;
+    tv_merge(a, mn, cmn, mx, cmx);
+  }
+  if (l == 0) ws[w] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < RS_WARPS; ++q) tv_merge(a, ws[q].mn, ws[q].cmn, ws[q].mx, ws[q].cmx);
+    uint4 rec = make_uint4(a.mn, a.cmn, a.mx, a.cmx);
+    __stcg(reinterpret_cast<uint4*>(cta_stat) + blockIdx.x, rec);
+  }
+  cg::this_grid().sync();
+  // global extrema and their multiplicities from the per-CTA records (every CTA recomputes them)
+  TvStat g{0xFFFFFFFFu, 0u, 0u, 0u};
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += RS_BLOCK) {
+    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(cta_stat) + q);
+    tv_merge(g, c.x, c.y, c.z, c.w);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    tv_merge(g, __shfl_xor_sync(0xffffffffu, g.mn, d), __shfl_xor_sync(0xffffffffu, g.cmn, d),
+             __shfl_xor_sync(0xffffffffu, g.mx, d), __shfl_xor_sync(0xffffffffu, g.cmx, d));
+  if (l == 0) gs[w] = g;
+  __syncthreads();
+  g = gs[0];
+  for (int q = 1; q < RS_WARPS; ++q) tv_merge(g, gs[q].mn, gs[q].cmn, gs[q].mx, gs[q].cmx);
+  const uint32_t kmin = g.mn;
+  const uint64_t covered = g.mn == g.mx ? (uint64_t)g.cmn : (uint64_t)g.cmn + g.cmx;
+  if (covered != (uint64_t)n) return;  // more than two values: general path (uniform over the grid)
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->done = 1;
+  const int total = (int)g.cmn;
+  // keys equal to the minimum in the CTAs before this one, then in this CTA's warps before this one
+  int before = 0;
+  for (int q = threadIdx.x; q < (int)blockIdx.x; q += RS_BLOCK) {
+    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(cta_stat) + q);
+    before += c.x == kmin ? (int)c.y : 0;
+  }
+  before = __reduce_add_sync(0xffffffffu, before);
+  if (l == 0) wbefore[w] = before;
+  __syncthreads();
+  int off = 0;
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) off += wbefore[q] + (q < w && ws[q].mn == kmin ? (int)ws[q].cmn : 0);
+  const unsigned lt = lanemask_lt();
+#pragma unroll 1
+  for (int k = 0; k < mine; ++k) {
+    const int64_t base = (g0 + k) * (32 * TV_ITEMS);
+    const bool sel = gmin[w][k] == kmin;
+    int pos[TV_ITEMS];
+#pragma unroll
+    for (int r = 0; r < TV_ITEMS; ++r) {
+      const unsigned b = sel ? balls[w][k][r] : 0u;
+      const int64_t i = base + r * 32 + l;
+      const int rank = off + __popc(b & lt);
+      pos[r] = (b >> l) & 1u ? rank : total + (int)(i - rank);
+      if (i < n) perm[pos[r]] = (int32_t)i;
+      off += __popc(b);
+    }
+    const bool full = base + 32 * TV_ITEMS <= n;  // warp-uniform
+#pragma unroll 1
+    for (int t = 0; t < n_leaves; ++t) {
+      const fgx_leaf_t& lf = tab.leaf[t];
+      const int vec = tab.vec[t];
+      if (full) {
+        if (vec == 4) scatter_full8<uint32_t, 8>(lf, base + l, pos);
+        else if (vec == 8) scatter_full8<uint2, 8>(lf, base + l, pos);
+        else scatter_full8<uint4, 4>(lf, base + l, pos);
+      } else {
+        if (vec == 4) scatter_tail8<uint32_t>(lf, base + l, n, pos);
+        else if (vec == 8) scatter_tail8<uint2>(lf, base + l, n, pos);
+        else scatter_tail8<uint4>(lf, base + l, n, pos);
+      }
+    }
   }
 }
 
@@ -519,21 +676,29 @@ size_t fgx_argsort_scratch_bytes(int64_t n) {
   return b;
 }
 
-int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, int32_t* perm, void* scratch,
-                size_t scratch_bytes, fgx_stream_t stream) {
+// argsort (+ optional payload move).  `narrow`/`wide`: the leaves of fgx_sort_rows (nn = nw = 0 for a bare argsort).
+static int sort_impl(const char* what, const void* keys, int32_t key_dtype, int64_t n, int32_t descending,
+                     int32_t* perm, void* scratch, size_t scratch_bytes, const fgx::LeafTable& narrow, int nn,
+                     const fgx::LeafTable& wide, int nw, cudaStream_t s) {
   using namespace fgx;
-  FGX_REQUIRE(n >= 0 && n < (1ll << 31), "fgx_argsort: n out of range");
-  FGX_REQUIRE(key_dtype == FGX_F32 || key_dtype == FGX_I32, "fgx_argsort: key dtype must be FGX_F32 or FGX_I32");
-  if (n == 0) return FGX_OK;
-  FGX_REQUIRE(keys && perm, "fgx_argsort: null pointer");
-  cudaStream_t s = as_stream(stream);
   const int desc = descending ? 1 : 0;
+  // leaves the fused two-valued kernel can move (a row = one 4 / 8 / 16-byte word) and the other narrow ones
+  LeafTable fused{}, rest{};
+  int nf = 0, nr = 0;
+  for (int k = 0; k < nn; ++k) {
+    const bool one_word = narrow.leaf[k].row_bytes == narrow.vec[k] && narrow.vec[k] >= 4;
+    LeafTable& t = one_word ? fused : rest;
+    int& c = one_word ? nf : nr;
+    t.leaf[c] = narrow.leaf[k];
+    t.vec[c++] = narrow.vec[k];
+  }
   if (n <= SORT_SMALL_N) {
     sort_small_kernel<<<1, 128, 0, s>>>(keys, key_dtype, desc, (int)n, perm);
-    return check_launch("fgx_argsort(small)");
+    if (nn || nw) return launch_gather(narrow, nn, wide, nw, perm, n, n, nullptr, s);
+    return check_launch(what);
   }
-  FGX_REQUIRE(scratch && scratch_bytes >= fgx_argsort_scratch_bytes(n), "fgx_argsort: scratch too small");
-  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "fgx_argsort: scratch must be 256-byte aligned");
+  FGX_REQUIRE(scratch && scratch_bytes >= fgx_argsort_scratch_bytes(n), "%s: scratch too small", what);
+  FGX_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "%s: scratch must be 256-byte aligned", what);
   if (n <= SORT_RANK_N) {
     const int itiles = (int)ceil_div(n, RK_ITILE);
     int64_t js = ceil_div((int64_t)2 * sm_count(), itiles);
@@ -544,10 +709,11 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
     js = ceil_div(n, jchunk);
     int32_t* rank = reinterpret_cast<int32_t*>(scratch);  // rank[n] then one ticket per i-tile
     cudaError_t e = cudaMemsetAsync(rank, 0, sizeof(int32_t) * (size_t)(n + itiles), s);
-    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     sort_rank_kernel<<<dim3(itiles, (unsigned)js), RK_BLOCK, 0, s>>>(keys, key_dtype, desc, (int)n, jchunk, rank,
                                                                     rank + n, perm);
-    return check_launch("fgx_argsort(rank)");
+    if (nn || nw) return launch_gather(narrow, nn, wide, nw, perm, n, n, nullptr, s);
+    return check_launch(what);
   }
   const int64_t tiles = ceil_div(n, RS_TILE);
   char* p = reinterpret_cast<char*>(scratch);
@@ -565,23 +731,49 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
   int32_t* idx0 = perm;
 
   cudaError_t e = cudaMemsetAsync(st, 0, sizeof(SortState), s);
-  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
-  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   const int g = grid_for(n, 256, 8);
-  // two-valued fast path (contiguous tile range per CTA)
-  const int64_t tv_tiles = ceil_div(n, TV_TILE);
-  int64_t cap = (int64_t)sm_count() * 8;
-  if (cap > TV_MAX_GRID) cap = TV_MAX_GRID;
-  const int64_t per = ceil_div(tv_tiles, tv_tiles < cap ? tv_tiles : cap);
-  const int tv_grid = (int)ceil_div(tv_tiles, per);
-  sort_two_stats_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, cta_stat);
-  sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_stat, perm);
+  // two-valued fast path
+  static const bool two_pass = [] { const char* v = getenv("FGX_SORT_TWO_PASS"); return v && atoi(v) == 1; }();
+  static int tv_per_sm = -1;
+  if (tv_per_sm < 0) {
+    int q = 0;
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sort_two_onepass_kernel, RS_BLOCK, 0);
+    tv_per_sm = (oe == cudaSuccess && q >= 1) ? q : 0;
+  }
+  int64_t tv_coop = (int64_t)sm_count() * tv_per_sm;
+  if (tv_coop > TV_MAX_GRID) tv_coop = TV_MAX_GRID;
+  const int64_t groups = ceil_div(n, 32 * TV_ITEMS);
+  bool fused_rows = false;
+  if (!two_pass && tv_coop >= 1 && ceil_div(groups, tv_coop * RS_WARPS) <= TO_MAX_GPW) {
+    // ONE cooperative launch: stats + partition (+ the narrow payload rows) with the keys read once
+    int gpw = (int)ceil_div(groups, tv_coop * RS_WARPS);
+    const int tv_grid = (int)ceil_div(groups, (int64_t)gpw * RS_WARPS);
+    const void* keys_arg = keys;
+    int dtype_arg = key_dtype, desc_arg = desc, nn_arg = nf;
+    int64_t n_arg = n, groups_arg = groups;
+    LeafTable tab = fused;
+    void* args[] = {&keys_arg, &dtype_arg, &desc_arg, &n_arg, &groups_arg, &gpw, &cta_stat, &st, &perm, &tab, &nn_arg};
+    e = cudaLaunchCooperativeKernel((const void*)sort_two_onepass_kernel, dim3((unsigned)tv_grid), dim3(RS_BLOCK), args,
+                                    0, s);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: cooperative launch: %s", what, cudaGetErrorString(e));
+    fused_rows = true;
+  } else {
+    // contiguous tile range per CTA: a statistics pass, then the scatter pass
+    const int64_t tv_tiles = ceil_div(n, TV_TILE);
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (cap > TV_MAX_GRID) cap = TV_MAX_GRID;
+    const int64_t per = ceil_div(tv_tiles, tv_tiles < cap ? tv_tiles : cap);
+    const int tv_grid = (int)ceil_div(tv_tiles, per);
+    sort_two_stats_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, cta_stat);
+    sort_two_scatter_kernel<<<tv_grid, RS_BLOCK, 0, s>>>(keys, key_dtype, desc, n, tv_tiles, per, st, cta_stat, perm);
+  }
   // general path (returns at once when st->done)
   static const bool multi = [] { const char* v = getenv("FGX_SORT_MULTI"); return v && atoi(v) == 1; }();
   if (!multi) {
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_general_kernel, RS_BLOCK, 0);
-    if (e != cudaSuccess || per_sm < 1) return fail(FGX_ERR_CUDA, "fgx_argsort: occupancy query failed");
+    if (e != cudaSuccess || per_sm < 1) return fail(FGX_ERR_CUDA, "%s: occupancy query failed", what);
     int64_t coop = (int64_t)sm_count() * per_sm;  // all CTAs must be co-resident for the grid-wide syncs
     const int64_t useful = ceil_div(n, RS_BLOCK * 4);
     if (coop > useful) coop = useful < 1 ? 1 : useful;
@@ -590,18 +782,53 @@ int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descendi
     int64_t n_arg = n, tiles_arg = tiles;
     void* args[] = {&keys_arg, &dtype_arg, &desc_arg, &n_arg, &tiles_arg, &img0, &img1, &idx0, &idx1, &block_hist, &st};
     e = cudaLaunchCooperativeKernel((const void*)sort_general_kernel, dim3((unsigned)coop), dim3(RS_BLOCK), args, 0, s);
-    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_argsort: cooperative launch: %s", cudaGetErrorString(e));
-    return check_launch("fgx_argsort");
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: cooperative launch: %s", what, cudaGetErrorString(e));
+  } else {
+    sort_prep_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, img0, st);
+    sort_plan_kernel<<<1, 256, 0, s>>>(n, st);
+    const int gt = (int)(tiles < (int64_t)sm_count() * 4 ? tiles : (int64_t)sm_count() * 4);
+    for (int pass = 0; pass < 4; ++pass) {
+      sort_hist_kernel<<<gt, RS_BLOCK, 0, s>>>(img0, img1, n, tiles, pass, st, block_hist);
+      sort_scan_kernel<<<256, 256, 0, s>>>(tiles, pass, st, block_hist);
+      sort_scatter_kernel<<<gt, RS_BLOCK, 0, s>>>(img0, img1, idx0, idx1, n, tiles, pass, st, block_hist);
+    }
+    sort_finish_kernel<<<g, 256, 0, s>>>(idx1, perm, n, st);
   }
-  sort_prep_kernel<<<g, 256, 0, s>>>(keys, key_dtype, desc, n, img0, st);
-  sort_plan_kernel<<<1, 256, 0, s>>>(n, st);
-  const int gt = (int)(tiles < (int64_t)sm_count() * 4 ? tiles : (int64_t)sm_count() * 4);
-  for (int pass = 0; pass < 4; ++pass) {
-    sort_hist_kernel<<<gt, RS_BLOCK, 0, s>>>(img0, img1, n, tiles, pass, st, block_hist);
-    sort_scan_kernel<<<256, 256, 0, s>>>(tiles, pass, st, block_hist);
-    sort_scatter_kernel<<<gt, RS_BLOCK, 0, s>>>(img0, img1, idx0, idx1, n, tiles, pass, st, block_hist);
+  // payload: the fused launch moved the one-word rows iff it finished the sort (st->done); all other rows gather
+  if (nf) {
+    const int rc = launch_gather(fused, nf, wide, 0, perm, n, n, fused_rows ? &st->done : nullptr, s);
+    if (rc != FGX_OK) return rc;
   }
-  sort_finish_kernel<<<g, 256, 0, s>>>(idx1, perm, n, st);
-  return check_launch("fgx_argsort");
+  if (nr || nw) return launch_gather(rest, nr, wide, nw, perm, n, n, nullptr, s);
+  return check_launch(what);
+}
+
+int fgx_argsort(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, int32_t* perm, void* scratch,
+                size_t scratch_bytes, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31), "fgx_argsort: n out of range");
+  FGX_REQUIRE(key_dtype == FGX_F32 || key_dtype == FGX_I32, "fgx_argsort: key dtype must be FGX_F32 or FGX_I32");
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(keys && perm, "fgx_argsort: null pointer");
+  static const LeafTable none{};
+  return sort_impl("fgx_argsort", keys, key_dtype, n, descending, perm, scratch, scratch_bytes, none, 0, none, 0,
+                   as_stream(stream));
+}
+
+int fgx_sort_rows(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, int32_t* perm,
+                  const fgx_leaf_t* leaves_host, int32_t n_leaves, void* scratch, size_t scratch_bytes,
+                  fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31), "fgx_sort_rows: n out of range");
+  FGX_REQUIRE(key_dtype == FGX_F32 || key_dtype == FGX_I32, "fgx_sort_rows: key dtype must be FGX_F32 or FGX_I32");
+  FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_LEAVES, "fgx_sort_rows: at most %d leaves per call", FGX_MAX_LEAVES);
+  if (n == 0) return FGX_OK;
+  FGX_REQUIRE(keys && perm && (n_leaves == 0 || leaves_host), "fgx_sort_rows: null pointer");
+  LeafTable narrow{}, wide{};
+  int nn = 0, nw = 0;
+  const int rc = classify_leaves("fgx_sort_rows", leaves_host, n_leaves, &narrow, &nn, &wide, &nw);
+  if (rc != FGX_OK) return rc;
+  return sort_impl("fgx_sort_rows", keys, key_dtype, n, descending, perm, scratch, scratch_bytes, narrow, nn, wide, nw,
+                   as_stream(stream));
 }
 }

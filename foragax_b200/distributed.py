@@ -85,23 +85,41 @@ def global_partition(local_perm, local_selected, lo, n_total):
     return total.to(torch.int32), gperm
 
 
-def all_gather_positions(x, y, rad, active):
-    """``float4 (x, y, rad, active)`` of all agents, rank order = slot order: float32[n_total, 4]."""
+def all_gather_positions(x, y, rad, active, layout="block"):
+    """``float4 (x, y, rad, active)`` of all agents IN GLOBAL SLOT ORDER: float32[n_total, 4] -- row ``i`` is slot
+    ``i`` of the unsharded set, so the hit indices ``fgx_raycast_agents`` returns against this table are global
+    slot ids (entity order of ``sim.py:402-408``).
+
+    ``layout`` names how the slots are dealt to the ranks: ``"block"`` = contiguous blocks (rank order = slot
+    order, :func:`shard_bounds`), ``"round_robin"`` = slot ``i`` on rank ``i % world`` at local row ``i // world``
+    (what ``fgx_create_base_shard(first=rank, stride=world)`` builds and ``bench.py`` uses): the gathered blocks
+    are then un-interleaved back to slot order."""
+    if layout not in ("block", "round_robin"):
+        raise ValueError(f"unknown shard layout {layout!r}")
     r, w = world()
     local = torch.stack([x.reshape(-1), y.reshape(-1), rad.reshape(-1), active.reshape(-1)], dim=1).contiguous()
     if w == 1:
         return local
     counts = all_gather_counts(torch.as_tensor(local.shape[0], device=local.device))
-    if int(counts.min()) == int(counts.max()):
-        out = torch.empty((w * local.shape[0], 4), dtype=torch.float32, device=local.device)
-        dist.all_gather_into_tensor(out, local)
-        return out
-    # ragged shards: pad to the largest one, gather, drop the padding
     m = int(counts.max())
-    padded = torch.zeros((m, 4), dtype=torch.float32, device=local.device)
-    padded[: local.shape[0]] = local
-    out = torch.empty((w * m, 4), dtype=torch.float32, device=local.device)
-    dist.all_gather_into_tensor(out, padded)
+    n_total = int(counts.sum())
+    if int(counts.min()) == m:
+        out = torch.empty((w * m, 4), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+    else:
+        # ragged shards: pad to the largest one, gather (the padding is dropped below)
+        padded = torch.zeros((m, 4), dtype=torch.float32, device=local.device)
+        padded[: local.shape[0]] = local
+        out = torch.empty((w * m, 4), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(out, padded)
+    if layout == "round_robin":
+        # rank q holds slots q, q + w, ...: row j of rank q is slot j * w + q.  Ranks q < n_total % w hold one row
+        # more, so the padded rows are exactly the slots >= n_total of the interleaved table.
+        if any(int(c) != len(range(q, n_total, w)) for q, c in enumerate(counts)):
+            raise ValueError("round_robin layout: shard sizes do not match slot i -> rank i % world")
+        return out.view(w, m, 4).transpose(0, 1).reshape(w * m, 4)[:n_total].contiguous()
+    if int(counts.min()) == m:
+        return out
     return torch.cat([out[i * m: i * m + int(c)] for i, c in enumerate(counts)], dim=0)
 
 

@@ -163,11 +163,14 @@ class Forager(Agent):
         else:
             dist, hit = out
         w1, w2, w3, w4, nw, keep = sm._wall_ptrs(walls)
-        b, scr, reuse = sm.wall_grid(walls, bounds, ray_length)
+        tk = sm.wall_grid(walls, bounds, ray_length)
+        b, scr = tk.bounds, tk.scratch
         L.check(L.lib.fgx_forager_sense_step(p, n, L.ptr(forager.active_state), L.ptr(energy_in.reshape(n).contiguous()),
                                              _fstate(forager), wc_struct(forager.policy), L.ptr(forager.age), r,
                                              float(ray_span), float(ray_length), w1, w2, w3, w4, nw, b[0], b[1], b[2],
-                                             b[3], L.ptr(scr), scr.numel(), reuse, L.ptr(dist), L.ptr(hit), L.stream()))
+                                             b[3], L.ptr(scr), scr.numel(), tk.reuse, L.ptr(dist), L.ptr(hit),
+                                             L.stream()))
+        tk.done()
         return forager, dist, hit
 
     # sim.py:139-151

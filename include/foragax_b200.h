@@ -106,6 +106,14 @@ int fgx_gather_rows(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32
 /* the same with n output rows taken from leaves of n_src rows (x[ids] for a shorter id list) */
 int fgx_gather_rows_from(const fgx_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n,
                          int64_t n_src, fgx_stream_t stream);
+/* sort_agents (agent_methods.py:74-79) as ONE call: perm = the stable argsort of fgx_argsort AND
+ * dst[i] = src[perm[i]] for every leaf (agent_methods.py:77).  When the key is two-valued (the sort on
+ * active_state, or on a 0/1 flag) the keys are read once and the narrow payload rows are scattered to their
+ * sorted positions by the same cooperative kernel -- no permutation round trip, no gather pass; otherwise the
+ * radix sort runs and the rows are gathered by it.  scratch: fgx_argsort_scratch_bytes(n), 256-byte aligned. */
+int fgx_sort_rows(const void* keys, int32_t key_dtype, int64_t n, int32_t descending, int32_t* perm,
+                  const fgx_leaf_t* leaves_host, int32_t n_leaves, void* scratch, size_t scratch_bytes,
+                  fgx_stream_t stream);
 /* sort_agents(active_state, descending) (agent_methods.py:74-79) over a set sharded in contiguous blocks
  * across the GPUs of one node, compaction and exchange in ONE kernel: every rank scatters its rows into
  * the peers' destination buffers (peer-mapped device memory, stores over NVLink) at their slots of the
@@ -135,6 +143,10 @@ int fgx_sort_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, con
                        int32_t world, int64_t* gpos_scratch, fgx_stream_t stream);
 /* jnp.sum(active_state, dtype=int32) (agent_methods.py:27): out int32[1] */
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream);
+/* the same count plus the caller's clip of hello_world.ipynb:138-139 / README.md:124-125 in one launch:
+ * out3[0] = sum(active_state), out3[1] = min(*n_add, n - out3[0]) (new agents that still fit), out3[2] = scratch */
+int fgx_count_active_clip(const float* active_state, int64_t n, const int32_t* n_add, int32_t* out3,
+                          fgx_stream_t stream);
 /* the argument construction of create_agents (agent_methods.py:10-15), fused:
  * unique_id = arange(n); create_keys = split(key, n+1)[1:]; active_state =
  * concat(ones(n_active), zeros(n-n_active)) float32; agent_types = tile(agent_type, n).
@@ -178,6 +190,13 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
                            const float* wx2, const float* wy2, int64_t n_walls, float x_min, float x_max, float y_min,
                            float y_max, float* dist, int32_t* hit, void* scratch, size_t scratch_bytes,
                            int32_t reuse_grid, fgx_stream_t stream);
+/* Statistics of that cull (measurement aid for the instruction floor of the kernel): out2[0] = sum over the
+ * ACTIVE agents of the number of walls listed for their cell (n_walls for agents that take the all-walls
+ * loop), out2[1] = number of active agents.  Same grid arguments / scratch / reuse_grid as above.         */
+int fgx_raycast_walls_grid_listed(const float* x, const float* y, const float* active, int64_t n_agents, const float* wx1,
+                                  const float* wy1, const float* wx2, const float* wy2, int64_t n_walls, float x_min,
+                                  float x_max, float y_min, float y_max, float ray_length, void* scratch,
+                                  size_t scratch_bytes, int32_t reuse_grid, int64_t* out2, fgx_stream_t stream);
 /* The agents x rays x agent-targets loop: ray_generator + ray_agent_sensor (space_methods.py:71-94)
  * for every ray of every sensing agent against every target circle (tx, ty, trad, tactive:
  * float32, element i at [i*target_stride] -- stride 4 for the interleaved float4 rows of a position

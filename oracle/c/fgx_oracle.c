@@ -154,6 +154,14 @@ void fgx_oracle_dice_step(int64_t n, int sides, const float* active, int32_t* dr
   }
 }
 
+void fgx_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int fgx_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -55,6 +55,11 @@ def threads():
     return load().fgx_oracle_threads()
 
 
+def set_threads(n):
+    """Size of the OpenMP pool (torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py's CPU arm sets it back)."""
+    load().fgx_oracle_set_threads(C.c_int(int(n)))
+
+
 def forager_step(cfg, obs, energy_in, fg):
     """In place on the oracle's forager dict (oracle/foraging.py layout); sim.py variant only."""
     lib = load()

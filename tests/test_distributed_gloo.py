@@ -209,3 +209,49 @@ def test_distributed_add_range_and_parent_rows():
                 assert j0 == want_lo - a
             for got, want in zip(leaves, ref_leaves):
                 np.testing.assert_array_equal(got, want[want_lo - a:want_hi - a] if local_count else want[:0])
+
+
+def _rr_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from foragax_b200 import distributed as fd
+    x = np.arange(n, dtype=np.float32)
+    mine = slice(rank, None, world)  # round-robin: slot i lives on rank i % world (bench.py's sharding)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    pos = fd.all_gather_positions(t(x[mine]), t(x[mine] * 2), t(x[mine] + 0.5), t((x[mine] % 3 == 0).astype(np.float32)),
+                                  layout="round_robin")
+    bad = None
+    try:  # a block-sharded set passed off as round-robin must be refused when the shard sizes give it away
+        if n % world:
+            lo, hi = fd.shard_bounds(n)
+            fd.all_gather_positions(t(x[lo:hi]), t(x[lo:hi]), t(x[lo:hi]), t(x[lo:hi]), layout="round_robin")
+            bad = "ragged block shards were accepted as round_robin"
+    except ValueError:
+        pass
+    q.put((rank, pos.numpy(), bad))
+    dist.destroy_process_group()
+
+
+def test_round_robin_positions_come_back_in_slot_order():
+    """with slots dealt round-robin the gathered table must be un-interleaved, otherwise
+    the hit indices of agent-agent sensing index the gathered order instead of the global slot ids."""
+    ctx = mp.get_context("spawn")
+    for world, n in ((2, 1000), (2, 1001), (3, 1000)):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_rr_worker, args=(r, world, port, n, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out = [q.get(timeout=120) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        x = np.arange(n, dtype=np.float32)
+        for rank, pos, bad in out:
+            assert bad is None, bad
+            assert pos.shape == (n, 4)
+            np.testing.assert_array_equal(pos[:, 0], x)
+            np.testing.assert_array_equal(pos[:, 1], x * 2)
+            np.testing.assert_array_equal(pos[:, 2], x + 0.5)
+            np.testing.assert_array_equal(pos[:, 3], (x % 3 == 0).astype(np.float32))

@@ -99,7 +99,7 @@ def test_churn_ticks_match_oracle(cuda, n, n_active, sides, ticks):
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 1024, 1025, 2047, 2048, 2049, 6000, 8193, 16384, 16385, 100003,
-                               1 << 20])
+                               1 << 20, 3_000_017, 10_000_019])  # the last two: several 256-slot groups per warp
 @pytest.mark.parametrize("frac", [0.0, 0.3, 1.0])
 def test_select_partition(cuda, n, frac):
     import foragax_b200.base.agent_methods as fgx_methods
@@ -140,7 +140,7 @@ def test_select_fused_predicates(cuda):
         np.testing.assert_array_equal(perm.cpu().numpy(), rp)
 
 
-@pytest.mark.parametrize("n", [1, 2, 100, 256, 257, 1000, 1025, 4096, 6000, 16384, 16385, 50000, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 100, 256, 257, 1000, 1025, 4096, 6000, 16384, 16385, 50000, 1 << 20, 3_000_017])
 @pytest.mark.parametrize("kind", ["flag", "float", "float_special", "int", "int_small", "const"])
 @pytest.mark.parametrize("ascend", [True, False])
 def test_argsort(cuda, n, kind, ascend):
@@ -245,3 +245,94 @@ def test_argsort_one_launch_per_phase_variant(cuda):
     env = dict(os.environ, FGX_SORT_MULTI="1", PYTHONPATH=os.path.dirname(os.path.dirname(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [16385, 100003, 2_500_037])
+@pytest.mark.parametrize("key_kind", ["active", "flag_int", "three_valued", "all_equal"])
+@pytest.mark.parametrize("ascend", [True, False])
+def test_sort_agents_fused_rows(cuda, n, key_kind, ascend):
+    """jit_sort_agents = fgx_sort_rows: on a two-valued key the cooperative kernel partitions AND moves the
+    one-word rows (4 / 8 / 16 bytes) in one pass; other leaves (bytes, 12-byte rows, wide rows) and keys with
+    more values take the gather.  Every leaf must equal leaf[argsort] (agent_methods.py:74-79)."""
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200.base.agent_classes import Agent, Params, Policy, State
+    rng = np.random.default_rng(n)
+    act = (rng.random(n) < 0.6).astype(np.float32)
+    leaves = {
+        "draw": rng.integers(0, 21, (n, 1)).astype(np.int32),            # 4-byte rows
+        "key": rng.integers(0, 2**32, (n, 2), dtype=np.uint32),          # 8-byte rows
+        "quad": rng.standard_normal((n, 4)).astype(np.float32),          # 16-byte rows
+        "tri": rng.standard_normal((n, 3)).astype(np.float32),           # 12-byte rows (3 chunks)
+        "b": rng.random(n) < 0.5,                                        # 1-byte rows
+        "w": rng.standard_normal((n, 40)).astype(np.float32),            # 160-byte rows (wide)
+    }
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in leaves.items()}
+    uid = np.arange(n, dtype=np.int32)
+    ag = Agent(params=Params(content={"w": d["w"], "quad": d["quad"]}),
+               state=State(content={"draw": d["draw"], "key": d["key"], "tri": d["tri"], "b": d["b"]}),
+               unique_id=torch.from_numpy(uid).to(cuda), agent_type=torch.full((n,), 3, dtype=torch.int32, device=cuda),
+               active_state=torch.from_numpy(act).to(cuda), age=torch.arange(n, dtype=torch.float32, device=cuda),
+               policy=None)
+    if key_kind == "active":
+        q, qt = act, ag.active_state
+    elif key_kind == "flag_int":
+        q = (leaves["draw"][:, 0] > 10).astype(np.int32)
+        qt = torch.from_numpy(q).to(cuda)
+    elif key_kind == "three_valued":
+        q = (leaves["draw"][:, 0] % 3).astype(np.float32)
+        qt = torch.from_numpy(q).to(cuda).reshape(n, 1)
+    else:
+        q = np.full(n, 1.0, np.float32)
+        qt = torch.from_numpy(q).to(cuda)
+    new, ids = fgx_methods.jit_sort_agents(qt, ascend, ag)
+    ref_ids = oam.sort_ids(q, ascend)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids)
+    np.testing.assert_array_equal(new.unique_id.cpu().numpy(), uid[ref_ids])
+    np.testing.assert_array_equal(new.active_state.cpu().numpy(), act[ref_ids])
+    np.testing.assert_array_equal(new.age.cpu().numpy(), np.arange(n, dtype=np.float32)[ref_ids])
+    np.testing.assert_array_equal(new.agent_type.cpu().numpy(), np.full(n, 3, np.int32))
+    for name, tree in (("draw", new.state.content), ("key", new.state.content), ("tri", new.state.content),
+                       ("b", new.state.content), ("w", new.params.content), ("quad", new.params.content)):
+        np.testing.assert_array_equal(tree[name].cpu().numpy(), leaves[name][ref_ids], err_msg=name)
+    # the input set is untouched (sort_agents gathers into fresh buffers)
+    np.testing.assert_array_equal(ag.state.content["draw"].cpu().numpy(), leaves["draw"])
+
+
+def test_two_pass_variants_of_select_and_sort(cuda):
+    """FGX_SELECT_TWO_PASS=1 / FGX_SORT_TWO_PASS=1 (count pass + scatter pass instead of the cooperative
+    single pass; also what sets beyond ~77 M slots use) give the same permutations; the switches are read
+    once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = ("import torch, foragax_b200.base.agent_methods as am\n"
+            "g = torch.Generator(device='cuda').manual_seed(2)\n"
+            "for n in (20000, 300001, 2000003):\n"
+            "    f = (torch.rand(n, device='cuda', generator=g) < 0.4)\n"
+            "    cnt, perm = am.select_agents(lambda a, p: f, None, None)\n"
+            "    ref = torch.sort((~f).to(torch.int32), stable=True).indices.to(torch.int32)\n"
+            "    assert int(cnt) == int(f.sum()) and torch.equal(perm, ref)\n"
+            "    k = f.float()\n"
+            "    for asc in (True, False):\n"
+            "        ref = torch.sort(k if asc else -k, stable=True).indices.to(torch.int32)\n"
+            "        assert torch.equal(am.argsort(k, ascend=asc), ref)\n"
+            "print('ok')\n")
+    env = dict(os.environ, FGX_SELECT_TWO_PASS="1", FGX_SORT_TWO_PASS="1",
+               PYTHONPATH=os.path.dirname(os.path.dirname(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [40_000, 300_017])
+def test_churn_world_matches_oracle(cuda, n):
+    """examples/churn.py (the C5 tick bench.py times: one-pass select, fused sort + row move, count + clip in one
+    launch, add with the count passed in) against the oracle's hello-world tick, leaf by leaf, every tick."""
+    import functools
+    from foragax_b200.examples.churn import ChurnWorld
+    w = ChurnWorld(n, sides=20, n_active=n // 2, key=None)
+    ref = oam.create_agents(functools.partial(odice.create_agent, sides=20), None, n, n // 2, 0, jr.PRNGKey(0))
+    assert_same(w.agents, ref)
+    for _ in range(4):
+        n_act = w.tick()
+        ref = odice.churn_tick(ref, n, 20)
+        assert_same(w.agents, ref)
+    assert 0 < int(n_act) <= n  # the count before the add of the last tick

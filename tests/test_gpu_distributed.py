@@ -357,3 +357,58 @@ def test_two_gpu_forager_add_with_parents_equals_single_gpu():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res) and res[0][2] > 100
+
+
+def _sense_worker(rank, world, port, n, layout, q):
+    """Agent-agent sensing over a sharded set: all-gather of the float4 positions in SLOT order, then every
+    rank senses its own agents; the hit indices must be the global slot ids the single-GPU call returns."""
+    import numpy as np
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200 import distributed as fd
+    rng = np.random.default_rng(11)
+    arena, L, R = 600.0, 40.0, 16
+    x = rng.uniform(1, arena - 1, n).astype(np.float32)
+    y = rng.uniform(1, arena - 1, n).astype(np.float32)
+    ang = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    rad = rng.uniform(2, 6, n).astype(np.float32)
+    act = (rng.random(n) < 0.8).astype(np.float32)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    bounds = (0.0, arena, 0.0, arena)
+    full_d, full_h = sm.raycast_agents((up(x), up(y), up(ang)), 0.7, L, (up(x), up(y), up(rad), up(act)), bounds, 6.0,
+                                       active_state=up(act), n_rays=R)
+    if layout == "round_robin":
+        mine = slice(rank, None, world)
+    else:
+        lo, hi = fd.shard_bounds(n)
+        mine = slice(lo, hi)
+    tg = fd.all_gather_positions(up(x[mine]), up(y[mine]), up(rad[mine]), up(act[mine]), layout=layout)
+    d, h = sm.raycast_agents((up(x[mine]), up(y[mine]), up(ang[mine])), 0.7, L, tg, bounds, 6.0,
+                             active_state=up(act[mine]), n_rays=R)
+    ok = torch.equal(d, full_d[mine]) and torch.equal(h, full_h[mine])
+    q.put((rank, bool(ok), float((full_h >= 0).float().mean())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("layout,n", [("round_robin", 30_001), ("block", 30_001)])
+def test_two_gpu_agent_sensing_hit_indices_are_global_slots(layout, n):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sense_worker, args=(r, world, port, n, layout, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = _collect(procs, q, world)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, frac in out:
+        assert ok, f"rank {rank}: sharded sensing differs from the single-GPU result ({layout})"
+        assert frac > 0.05

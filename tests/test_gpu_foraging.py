@@ -116,7 +116,9 @@ def test_wilson_cowan_step_policy(cuda):
     from foragax_b200 import random as fgx_random
     from foragax_b200.base.agent_classes import Params, Signal
     from foragax_b200.policy.wilson_cowan import WilsonCowan
-    for nn, nobs, nact in ((40, 28, 2), (30, 28, 2), (17, 5, 3), (64, 97, 4)):
+    # (40, 33, 2) is the instantiation bench.py times (odd-length E rows: the `len & 1` tail of row_dot2<33>);
+    # (22, 18, 2) is even but not a multiple of 4 (generic path, float2 rows without a float4 body)
+    for nn, nobs, nact in ((40, 28, 2), (30, 28, 2), (40, 33, 2), (22, 18, 2), (17, 5, 3), (64, 97, 4)):
         cfg = ofo.Config("sim", n_neurons=nn, n_obs=nobs, n_act=nact)
         keys = jr.split(jr.PRNGKey(nn), 300)
         dk = torch.from_numpy(keys).to(cuda)
@@ -206,14 +208,9 @@ def test_fused_sense_step_equals_raycast_then_step(cuda):
     from foragax_b200 import struct
     from foragax_b200.examples.foraging import Forager
     n = 30_000
-    old = bench.N_AGENTS
-    bench.N_AGENTS = n
-    try:
-        work = bench.make_workload(n)
-        fa, space = bench.build_foragers(work, 0, 1, cuda)
-        fb, _ = bench.build_foragers(work, 0, 1, cuda)
-    finally:
-        bench.N_AGENTS = old
+    work = bench.make_workload(n)
+    fa, space = bench.build_foragers(work, 0, 1, cuda, n_agents=n)
+    fb, _ = bench.build_foragers(work, 0, 1, cuda, n_agents=n)
     for f in (fa, fb):   # some agents outside the arena (all-walls loop) and on the boundary
         f.agents.state.content["X"][:50] -= 300.0
         f.agents.state.content["Y"][50:100] = 0.0
@@ -231,3 +228,33 @@ def test_fused_sense_step_equals_raycast_then_step(cuda):
         for x, y in zip(struct.tree_leaves(fa.agents), struct.tree_leaves(fb.agents)):
             assert torch.equal(x, y)
     assert float((h0 >= 0).float().mean()) > 0.01
+
+
+def test_bench_instantiation_forager_step_matches_oracle(cuda):
+    """The kernel instantiation bench.py times -- forager_step_kernel<40,33,2> on the C4 workload (32 ray
+    distances + own energy = 33 observations) -- against oracle.foraging.forager_step (Forager.step_agent,
+    sim.py:74-136, with WilsonCowan.step_policy, wilson_cowan.py:34-51) on 50,000 agents of the bench workload,
+    three ticks: ray cast on the device, the same distances fed to both sides."""
+    import bench
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200.base.agent_classes import Params, Signal
+    from foragax_b200.base.agent_methods import step_agents
+    n = 50_000
+    work = bench.make_workload(n)
+    fs, space = bench.build_foragers(work, 0, 1, cuda, n_agents=n)
+    cfg = ofo.Config("sim", n_neurons=bench.N_NEURONS, n_obs=bench.N_OBS, n_act=bench.N_ACT, x_max=bench.ARENA,
+                     y_max=bench.ARENA)
+    params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0,
+                             'energy_max': 15.0})
+    bounds = (0.0, bench.ARENA, 0.0, bench.ARENA)
+    rng = np.random.default_rng(5)
+    for tick in range(3):
+        A = fs.agents
+        st = A.state.content
+        dist, _ = sm.raycast_walls((st["X"], st["Y"], st["ang"]), bench.RAY_SPAN, bench.RAY_LEN, space.walls,
+                                   active_state=A.active_state, n_rays=bench.N_RAYS, bounds=bounds)
+        e_in = (rng.random(n) * 0.2).astype(np.float32)
+        ref = ofo.forager_step(cfg, dist.cpu().numpy(), e_in, np_forager(A))
+        fs.agents = step_agents(params, Signal(content={'obs': dist, 'energy_in': torch.from_numpy(e_in).to(cuda)}), fs)
+        assert_tree(np_forager(fs.agents), ref)
+    assert float((dist < bench.RAY_LEN).float().mean()) > 0.01  # the observations are not all "no hit"
