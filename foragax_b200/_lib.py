@@ -73,6 +73,15 @@ _decl("fgx_sort_rows", C.c_int, vp, i32, i64, i32, vp, C.POINTER(Leaf), i32, vp,
 _decl("fgx_gather_rows", C.c_int, C.POINTER(Leaf), i32, vp, i64, vp)
 _decl("fgx_gather_rows_from", C.c_int, C.POINTER(Leaf), i32, vp, i64, i64, vp)
 _decl("fgx_pack_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, vp, i64, vp, C.POINTER(i64), i32, i32, vp)
+
+
+class PeerSync(C.Structure):
+    _fields_ = [("mailbox", vp * MAX_PEERS), ("epoch", vp), ("error", vp), ("rank", i32), ("world", i32)]
+
+
+_decl("fgx_peer_mailbox_bytes", sz)
+_decl("fgx_peer_exchange", C.c_int, C.POINTER(PeerSync), vp, vp, vp, vp)
+_decl("fgx_peer_add_range", C.c_int, C.POINTER(PeerSync), vp, vp, i64, i64, i64, vp, vp)
 _decl("fgx_key_chain_advance", C.c_int, i32, vp, vp, vp, vp)
 _decl("fgx_sort_key_images", C.c_int, vp, i32, i64, i32, vp, vp, vp)
 _decl("fgx_sort_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, i64, vp, i64, C.POINTER(i64), i32, i32, vp, vp)

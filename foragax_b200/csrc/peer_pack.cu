@@ -188,6 +188,159 @@ int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, con
 }
 }
 
+// ---- counts between ranks without the host or NCCL: mailboxes in peer-mapped memory ------------------------
+namespace fgx {
+
+struct Mailbox {
+  unsigned long long flag[FGX_MAX_PEERS];        // flag[s] = last epoch rank s has released here
+  long long payload[2][FGX_MAX_PEERS][2];        // [epoch parity][source rank][value]
+};
+
+struct PeerSync {
+  Mailbox* box[FGX_MAX_PEERS];
+  unsigned long long* epoch;
+  int32_t* error;
+  int32_t rank, world;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
+  asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One warp: lane d publishes to rank d, lane s waits for rank s.  Returns (in every lane) the values of all ranks
+// through vals[j][s] in shared memory.  Payload slots alternate with the epoch parity: a rank can run at most one
+// epoch ahead of a peer (it cannot pass epoch e + 1 before the peer has released e + 1, which the peer does only
+// after it has read epoch e), so the slot written for e + 1 is never the one a peer still reads for e.
+__device__ __forceinline__ void peer_exchange_warp(const PeerSync& sy, long long v0, long long v1,
+                                                   long long (*vals)[FGX_MAX_PEERS]) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long e = *sy.epoch + 1ull;
+  const int par = (int)(e & 1ull);
+  if (lane < sy.world) {
+    Mailbox* peer = sy.box[lane];
+    st_relaxed_sys(&peer->payload[par][sy.rank][0], v0);
+    st_relaxed_sys(&peer->payload[par][sy.rank][1], v1);
+    __threadfence_system();  // also orders the peer stores of every earlier kernel of this stream before the flag
+    st_release_sys(&peer->flag[sy.rank], e);
+    const Mailbox* mine = sy.box[sy.rank];
+    const unsigned long long t0 = globaltimer_ns();
+    bool ok = true;
+    while (ld_acquire_sys(&mine->flag[lane]) < e) {
+      if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer is gone -- report, never hang
+        ok = false;
+        break;
+      }
+      __nanosleep(64);
+    }
+    if (!ok) atomicExch(sy.error, 1 + lane);
+    vals[0][lane] = ld_relaxed_sys(&mine->payload[par][lane][0]);
+    vals[1][lane] = ld_relaxed_sys(&mine->payload[par][lane][1]);
+  } else if (lane < FGX_MAX_PEERS) {
+    vals[0][lane] = 0;
+    vals[1][lane] = 0;
+  }
+  __syncwarp();
+  if (lane == 0) *sy.epoch = e;
+}
+
+__global__ void __launch_bounds__(32) peer_exchange_kernel(const PeerSync sy, const int32_t* __restrict__ v0,
+                                                           const int32_t* __restrict__ v1,
+                                                           long long* __restrict__ out_all) {
+  __shared__ long long vals[2][FGX_MAX_PEERS];
+  peer_exchange_warp(sy, v0 ? (long long)*v0 : 0ll, v1 ? (long long)*v1 : 0ll, vals);
+  const int lane = threadIdx.x & 31;
+  if (out_all != nullptr && lane < FGX_MAX_PEERS) {
+    out_all[lane] = vals[0][lane];
+    out_all[FGX_MAX_PEERS + lane] = vals[1][lane];
+  }
+}
+
+__global__ void __launch_bounds__(32) peer_add_range_kernel(const PeerSync sy, const int32_t* __restrict__ n_sel,
+                                                            const int32_t* __restrict__ n_act, long long n_local,
+                                                            long long lo, long long n_total,
+                                                            int32_t* __restrict__ out3) {
+  __shared__ long long vals[2][FGX_MAX_PEERS];
+  peer_exchange_warp(sy, (long long)*n_sel, (long long)*n_act, vals);
+  if ((threadIdx.x & 31) == 0) {
+    long long sel = 0, act = 0;
+    for (int s = 0; s < sy.world; ++s) {
+      sel += vals[0][s];
+      act += vals[1][s];
+    }
+    const long long k = sel < n_total - act ? sel : n_total - act;
+    auto clampll = [](long long v, long long a, long long b) { return v < a ? a : (v > b ? b : v); };
+    const long long start = clampll(act - lo, 0, n_local), end = clampll(act + k - lo, 0, n_local);
+    out3[0] = (int32_t)k;
+    out3[1] = (int32_t)(end - start);
+    out3[2] = (int32_t)(start + lo - act);
+  }
+}
+
+static int make_sync(const char* what, const fgx_peer_sync_t* sync, PeerSync* out) {
+  FGX_REQUIRE(sync, "%s: null sync", what);
+  FGX_REQUIRE(sync->world >= 1 && sync->world <= FGX_MAX_PEERS && sync->rank >= 0 && sync->rank < sync->world,
+              "%s: bad rank / world", what);
+  FGX_REQUIRE(sync->epoch && sync->error, "%s: null epoch / error", what);
+  for (int d = 0; d < sync->world; ++d) {
+    FGX_REQUIRE(sync->mailbox[d], "%s: rank %d has no mailbox", what, d);
+    FGX_REQUIRE((reinterpret_cast<uintptr_t>(sync->mailbox[d]) & 15) == 0, "%s: mailbox %d must be 16-byte aligned", what, d);
+    out->box[d] = reinterpret_cast<Mailbox*>(sync->mailbox[d]);
+  }
+  out->epoch = reinterpret_cast<unsigned long long*>(sync->epoch);
+  out->error = sync->error;
+  out->rank = sync->rank;
+  out->world = sync->world;
+  return FGX_OK;
+}
+
+}  // namespace fgx
+
+extern "C" {
+
+size_t fgx_peer_mailbox_bytes(void) { return (sizeof(fgx::Mailbox) + 255) / 256 * 256; }
+
+int fgx_peer_exchange(const fgx_peer_sync_t* sync, const int32_t* v0, const int32_t* v1, int64_t* out_all,
+                      fgx_stream_t stream) {
+  using namespace fgx;
+  PeerSync sy{};
+  const int rc = make_sync("fgx_peer_exchange", sync, &sy);
+  if (rc != FGX_OK) return rc;
+  peer_exchange_kernel<<<1, 32, 0, as_stream(stream)>>>(sy, v0, v1, reinterpret_cast<long long*>(out_all));
+  return check_launch("fgx_peer_exchange");
+}
+
+int fgx_peer_add_range(const fgx_peer_sync_t* sync, const int32_t* n_selected_local, const int32_t* n_active_local,
+                       int64_t n_local, int64_t lo, int64_t n_total, int32_t* out3, fgx_stream_t stream) {
+  using namespace fgx;
+  PeerSync sy{};
+  const int rc = make_sync("fgx_peer_add_range", sync, &sy);
+  if (rc != FGX_OK) return rc;
+  FGX_REQUIRE(n_selected_local && n_active_local && out3, "fgx_peer_add_range: null pointer");
+  FGX_REQUIRE(n_local >= 0 && lo >= 0 && n_total >= lo + n_local, "fgx_peer_add_range: bad block");
+  peer_add_range_kernel<<<1, 32, 0, as_stream(stream)>>>(sy, n_selected_local, n_active_local, n_local, lo, n_total,
+                                                         out3);
+  return check_launch("fgx_peer_add_range");
+}
+}
+
 // ---- general keys: the global stable sort of a block-sharded set ("general float keys") ----
 // Every rank sorts its keys locally (fgx_argsort), publishes the SORTED key images of its block (an
 // all-gather: 4 B per slot), and finds the global position of each of its rows without any exchange of

@@ -73,11 +73,16 @@ __global__ void __launch_bounds__(128) wall_count_kernel(WGrid g, const float* _
                                                          const float* __restrict__ wy1, const float* __restrict__ wx2,
                                                          const float* __restrict__ wy2, int n_walls,
                                                          uint32_t* __restrict__ count, float4* __restrict__ wall4,
+                                                         float4* __restrict__ wallb, float* __restrict__ wallt,
                                                          WState* __restrict__ st) {
   const int cu = blockIdx.x * blockDim.x + threadIdx.x;
   for (int w = blockIdx.y; w < n_walls; w += gridDim.y) {
     const float ax = wx1[w], ay = wy1[w], bx = wx2[w], by = wy2[w];
-    if (cu == 0) wall4[w] = make_float4(ax, ay, bx, by);
+    if (cu == 0) {  // the records the sensing side reads: endpoints, bounding box, |o3| threshold of the line band
+      wall4[w] = make_float4(ax, ay, bx, by);
+      wallb[w] = make_float4(fminf(ax, bx), fminf(ay, by), fmaxf(ax, bx), fmaxf(ay, by));
+      wallt[w] = g.tol_line * norm2(f_sub(bx, ax), f_sub(by, ay));
+    }
     if (!wall_in_scale(g, ax, ay, bx, by)) {
       if (cu == 0) st->fallback = 1;
       continue;
@@ -154,14 +159,59 @@ struct WallsGridArgs {
   int32_t* hit;
 };
 
-__global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a) {
+// NR > 0: rays per agent known at compile time (index split by shifts / constant division); NR == 0: run time.
+// 32-bit flat (agent, ray) index; linspace steps j / (n_rays - 1) come from a per-CTA shared-memory table (the
+// IEEE division -- whose j = 0 lane takes the slow path of the software divide -- runs once per CTA, not per ray).
+constexpr int WG_STEP_TABLE = 256;
+
+template <int NR>
+__global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a, uint32_t total) {
+  __shared__ float s_step[WG_STEP_TABLE];
+  const uint32_t nr = NR > 0 ? (uint32_t)NR : (uint32_t)a.n_rays;
+  const bool table = nr <= (uint32_t)WG_STEP_TABLE;
+  if (table) {
+    for (uint32_t j = threadIdx.x; j < nr; j += blockDim.x)
+      s_step[j] = nr > 1 ? __fdiv_rn((float)j, (float)(nr - 1)) : 0.0f;
+    __syncthreads();
+  }
+  const float L = a.L, span = a.span;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t agent = t / nr;
+    const uint32_t j = t - agent * nr;
+    if (a.aactive != nullptr && __ldg(a.aactive + agent) == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
+      a.dist[t] = 0.0f;
+      if (a.hit) a.hit[t] = -1;
+      continue;
+    }
+    const float p1x = __ldg(a.ax + agent), p1y = __ldg(a.ay + agent), ang = __ldg(a.aang + agent);
+    // ray_generator (space_methods.py:56-69): linspace(ang - span, ang + span, n)[j] = lo*(1-s) + hi*s, last = hi
+    const float lo = f_sub(ang, span), hi = f_add(ang, span);
+    float th;
+    if (!table) th = linspace_elem(lo, hi, (int)nr, (int)j);
+    else if (nr == 1) th = lo;
+    else if (j == nr - 1) th = hi;
+    else {
+      const float sj = s_step[j];
+      th = f_add(f_mul(lo, f_sub(1.0f, sj)), f_mul(hi, sj));
+    }
+    float sn, cs;
+    sincosf(th, &sn, &cs);
+    const float q1x = f_add(p1x, f_mul(cs, L)), q1y = f_add(p1y, f_mul(sn, L));
+    float best = L;
+    int bidx = -1;
+    walls_grid_cast(a.v, p1x, p1y, q1x, q1y, L, best, bidx);
+    a.dist[t] = best;
+    if (a.hit) a.hit[t] = bidx;
+  }
+}
+
+// the same for flat indices beyond 2^31 (64-bit index arithmetic)
+__global__ void __launch_bounds__(256) raycast_walls_grid_kernel_big(const WallsGridArgs a) {
   const int64_t total = a.n * a.n_rays;
-  const bool small = total < (1ll << 31);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    // (agent, ray) of flat index t: 32-bit division whenever the index fits (the 64-bit one is ~40 instructions)
-    const int64_t agent = small ? (int64_t)((uint32_t)t / (uint32_t)a.n_rays) : t / a.n_rays;
+    const int64_t agent = t / a.n_rays;
     const int j = (int)(t - agent * a.n_rays);
-    if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
+    if (a.aactive != nullptr && a.aactive[agent] == 0.0f) {
       a.dist[t] = 0.0f;
       if (a.hit) a.hit[t] = -1;
       continue;
@@ -224,6 +274,10 @@ static int wgrid_dims(float x_min, float x_max, float y_min, float y_max, float 
   g->scale = scale;
   g->eps = 1e-4f * scale + 1e-6f;
   g->thick = L * 1.0001f + 5e-4f * scale + 1e-6f;
+  g->margin = g->thick - L;
+  // run-time line band (walls_pretest_skip): 8 x (2 L / margin + 1) x the determinant noise of 4e-7 * scale, at least eps
+  const float noise = 4e-7f * scale;
+  g->tol_line = fmaxf(g->eps, 8.0f * (2.0f * L / g->margin + 1.0f) * noise);
   return 0;
 }
 
@@ -244,8 +298,8 @@ size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float 
   WGrid g;
   if (n_walls < 0 || wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((size_t)n_walls * 16 + 16) +
-         wg_al(wgrid_capacity(g, n_walls) * 4);
+  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + 2 * wg_al((size_t)n_walls * 16 + 16) +
+         wg_al((size_t)n_walls * 4 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
 }
 
 int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
@@ -269,6 +323,10 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
   p += wg_al(((size_t)n_cells + 1) * 4);
   float4* wall4 = reinterpret_cast<float4*>(p);
   p += wg_al((size_t)n_walls * 16 + 16);
+  float4* wallb = reinterpret_cast<float4*>(p);
+  p += wg_al((size_t)n_walls * 16 + 16);
+  float* wallt = reinterpret_cast<float*>(p);
+  p += wg_al((size_t)n_walls * 4 + 16);
   int32_t* entries = reinterpret_cast<int32_t*>(p);
   cudaError_t e = cudaSuccess;
   if (reuse_grid) {
@@ -278,14 +336,14 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     const int nmaj = g.gx > g.gy ? g.gx : g.gy;
     const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
-    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, st);
+    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, wallb, wallt, st);
     wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
   } else {
     e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4), s);
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
-  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, st};
+  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, wallb, wallt, st};
   return FGX_OK;
 }
 
@@ -317,7 +375,20 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
   a.ax = x; a.ay = y; a.aang = ang; a.aactive = active;
   a.n = n_agents; a.n_rays = n_rays; a.span = ray_span; a.L = ray_length;
   a.dist = dist; a.hit = hit;
-  raycast_walls_grid_kernel<<<grid_for(n_agents * n_rays, 256, 8), 256, 0, s>>>(a);
+  const int64_t total = n_agents * (int64_t)n_rays;
+  const int grid = grid_for(total, 256, 8);
+  if (total >= (1ll << 31)) {
+    raycast_walls_grid_kernel_big<<<grid, 256, 0, s>>>(a);
+  } else {
+    const uint32_t t32 = (uint32_t)total;
+    switch (n_rays) {
+      case 32: raycast_walls_grid_kernel<32><<<grid, 256, 0, s>>>(a, t32); break;
+      case 16: raycast_walls_grid_kernel<16><<<grid, 256, 0, s>>>(a, t32); break;
+      case 9: raycast_walls_grid_kernel<9><<<grid, 256, 0, s>>>(a, t32); break;
+      case 8: raycast_walls_grid_kernel<8><<<grid, 256, 0, s>>>(a, t32); break;
+      default: raycast_walls_grid_kernel<0><<<grid, 256, 0, s>>>(a, t32); break;
+    }
+  }
   return check_launch("fgx_raycast_walls_grid");
 }
 

@@ -11,6 +11,8 @@ struct WGrid {
   float x0, y0, cs, inv_cs;
   int gx, gy;
   float thick, eps, scale;  // band half-widths (perpendicular) and the coordinate scale they assume
+  float margin;             // thick - ray_length: how far beyond a ray's bounding box a wall can still matter
+  float tol_line;           // per-(agent, wall) line band of the run-time pre-test (>= eps; see walls_pretest)
 };
 
 struct WState {
@@ -26,23 +28,81 @@ struct WallsGridView {
   const uint32_t* start;
   const int32_t* entries;
   const float4* wall4;  // (p2x, p2y, q2x, q2y) per wall, packed by the grid build
+  const float4* wallb;  // (min x, min y, max x, max y) of the wall
+  const float* wallt;   // tol_line * |q2 - p2|: |o3| above it <=> the agent is farther than tol_line from the wall's line
   const WState* st;
 };
+
+// ray_wall_sensor (space_methods.py:96-143) given the four orientation determinants the caller already holds.
+// When none of them is zero the collinear cases c2..c5 (each needs an o == 0) cannot apply, so only the
+// proper-crossing candidate d1 is evaluated: the same bits as ray_wall_exact, without its three extra norms.
+static __device__ __noinline__ float ray_wall_exact_o(float p1x, float p1y, float q1x, float q1y, float L, float p2x,
+                                                      float p2y, float q2x, float q2y, float v1, float v2, float v3,
+                                                      float v4) {
+  const int o1 = orient_cls(v1), o2 = orient_cls(v2), o3 = orient_cls(v3), o4 = orient_cls(v4);
+  float d1 = L;
+  if (o1 != o2 && o3 != o4) {
+    // line_intercept (space_methods.py:98-103)
+    const float ax = f_sub(q1x, p1x), ay = f_sub(q1y, p1y);
+    const float c1 = f_sub(f_mul(ax, f_sub(p2y, p1y)), f_mul(ay, f_sub(p2x, p1x)));
+    const float c2 = f_sub(f_mul(ax, f_sub(q2y, p1y)), f_mul(ay, f_sub(q2x, p1x)));
+    const float r = __fdiv_rn(c1, f_add(f_sub(c1, c2), 1e-6f));
+    const float ix = f_add(p2x, f_mul(r, f_sub(q2x, p2x)));
+    const float iy = f_add(p2y, f_mul(r, f_sub(q2y, p2y)));
+    d1 = norm2(f_sub(ix, p1x), f_sub(iy, p1y));
+  }
+  if (o1 != 0 && o2 != 0 && o3 != 0 && o4 != 0) return min_nan(d1, L);
+  float d2 = L, d3 = L, d4 = L, d5 = L;
+  if (o1 == 0 && on_segment(p1x, p1y, p2x, p2y, q1x, q1y)) d2 = norm2(f_sub(p1x, p2x), f_sub(p1y, p2y));
+  if (o2 == 0 && on_segment(p1x, p1y, q2x, q2y, q1x, q1y)) d3 = norm2(f_sub(p1x, q2x), f_sub(p1y, q2y));
+  if (o3 == 0 && on_segment(p2x, p2y, p1x, p1y, q2x, q2y)) d4 = 0.0f;
+  if (o4 == 0 && on_segment(p2x, p2y, q1x, q1y, q2x, q2y)) d5 = norm2(f_sub(p1x, q1x), f_sub(p1y, q1y));
+  return min_nan(d1, min_nan(d2, min_nan(d3, min_nan(d4, d5))));
+}
 
 // one (ray, wall) pair, exactly as the all-pairs kernel decides it: sure miss <=> no candidate distance of
 // ray_wall_sensor can apply (max(o1*o2, o3*o4) > 0 and all four determinants nonzero); otherwise the op-for-op
 // restatement.  (distance, wall) minima are lexicographic = argmin's first-index rule for any visiting order.
-__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
-                                          float q2x, float q2y, int w, float& best, int& bidx) {
+// o3 = orient_val(p2, q2, p1) is passed in (the pre-test computed it).
+__device__ __forceinline__ void test_wall_o3(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
+                                             float q2x, float q2y, float o3, int w, float& best, int& bidx) {
   const float o1 = orient_val(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_val(p1x, p1y, q1x, q1y, q2x, q2y);
-  const float o3 = orient_val(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
+  const float o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
   const float A = f_mul(o1, o2), B = f_mul(o3, o4);
   if (fmaxf(A, B) > 0.0f && fabsf(f_mul(A, B)) > 0.0f) return;
-  const float d = ray_wall_exact(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y);
+  const float d = ray_wall_exact_o(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, o1, o2, o3, o4);
   if (d < best || (d == best && bidx >= 0 && w < bidx)) {
     best = d;
     bidx = w;
   }
+}
+__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
+                                          float q2x, float q2y, int w, float& best, int& bidx) {
+  test_wall_o3(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, orient_val(p2x, p2y, q2x, q2y, p1x, p1y), w, best, bidx);
+}
+
+// The ray's bounding box widened by g.margin (what the per-ray pre-test compares wall boxes with).
+struct RayBox {
+  float x0, y0, x1, y1;
+};
+__device__ __forceinline__ RayBox ray_box(float p1x, float p1y, float q1x, float q1y, float margin) {
+  return RayBox{fminf(p1x, q1x) - margin, fminf(p1y, q1y) - margin, fmaxf(p1x, q1x) + margin, fmaxf(p1y, q1y) + margin};
+}
+
+// Run-time pre-test of a LISTED wall for one ray -- the list-building rule of raycast_walls_grid.cu evaluated per
+// (ray, wall) instead of per (cell, wall).  A wall can give d < L for the ray p1 -> q1 only if
+//   (a) a wall point lies in the ray's bounding box: c2 / c3 / c5 (space_methods.py:130-140) test exactly that with
+//       on_segment, and a proper crossing (c1) of two segments lies in both boxes -- the boxes are compared with a
+//       margin of 5e-4 * S (S = coordinate scale), hundreds of times the rounding of the determinants; or
+//   (b) rounding can fake a crossing: c1 with a wrong sign class needs a determinant within the noise (~4e-7 * S in
+//       distance units) of zero, i.e. the wall's line passes within that noise of a ray endpoint or the ray's line
+//       of a wall endpoint, with the true crossing of the two LINES outside the widened box -- the lines are then
+//       parallel to within noise / margin and p1 sits within (2 L / margin + 1) * noise of the wall's line;
+//       tol_line is 8x that (and never below the list builder's eps); c4 (d = 0) needs o3 == 0 exactly.
+// So: skip <=> boxes disjoint AND |o3| > tol_line * |q2 - p2|.  NaN operands fail every comparison -> not skipped.
+__device__ __forceinline__ bool walls_pretest_skip(const RayBox& rb, const float4& bb, float o3, float tolw) {
+  const bool disjoint = bb.z < rb.x0 || bb.x > rb.x1 || bb.w < rb.y0 || bb.y > rb.y1;
+  return disjoint && fabsf(o3) > tolw;
 }
 
 // min / first-argmin over the walls for the ray p1 -> q1 (best = L, bidx = -1 on entry)
@@ -51,23 +111,37 @@ __device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, float p1
   // strictly inside the grid (NaN positions fail and take the all-walls loop)
   const float fx = (p1x - v.g.x0) * v.g.inv_cs, fy = (p1y - v.g.y0) * v.g.inv_cs;
   const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
+  const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
   if (inside && v.st->fallback == 0) {
     const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
     const uint32_t e0 = v.start[cell], e1 = v.start[cell + 1];
-    for (uint32_t e = e0; e < e1; e += 4) {  // four independent (index -> wall record) load chains in flight
-      int w[4];
-      float4 wl[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = v.entries[min(e + u, e1 - 1)];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) wl[u] = v.wall4[w[u]];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (e + u < e1) test_wall(p1x, p1y, q1x, q1y, L, wl[u].x, wl[u].y, wl[u].z, wl[u].w, w[u], best, bidx);
+    if (e0 >= e1) return;
+    // records one entry ahead of the tests: (index -> endpoints, box, tolerance) of entry e + 1 load while e is tested
+    int w = v.entries[e0];
+    float4 wl = v.wall4[w], bb = v.wallb[w];
+    float tw = v.wallt[w];
+    for (uint32_t e = e0; e < e1; ++e) {
+      const int wc = w;
+      const float4 wlc = wl, bbc = bb;
+      const float twc = tw;
+      if (e + 1 < e1) {
+        w = v.entries[e + 1];
+        wl = v.wall4[w];
+        bb = v.wallb[w];
+        tw = v.wallt[w];
+      }
+      const float o3 = orient_val(wlc.x, wlc.y, wlc.z, wlc.w, p1x, p1y);
+      if (walls_pretest_skip(rb, bbc, o3, twc)) continue;
+      test_wall_o3(p1x, p1y, q1x, q1y, L, wlc.x, wlc.y, wlc.z, wlc.w, o3, wc, best, bidx);
     }
   } else {
-    for (int w = 0; w < v.n_walls; ++w)
-      test_wall(p1x, p1y, q1x, q1y, L, v.wx1[w], v.wy1[w], v.wx2[w], v.wy2[w], w, best, bidx);
+    for (int w = 0; w < v.n_walls; ++w) {
+      const float4 wl = make_float4(v.wx1[w], v.wy1[w], v.wx2[w], v.wy2[w]);
+      const float4 bb = make_float4(fminf(wl.x, wl.z), fminf(wl.y, wl.w), fmaxf(wl.x, wl.z), fmaxf(wl.y, wl.w));
+      const float o3 = orient_val(wl.x, wl.y, wl.z, wl.w, p1x, p1y);
+      if (walls_pretest_skip(rb, bb, o3, v.g.tol_line * norm2(f_sub(wl.z, wl.x), f_sub(wl.w, wl.y)))) continue;
+      test_wall_o3(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, o3, w, best, bidx);
+    }
   }
 }
 

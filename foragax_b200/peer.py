@@ -69,7 +69,21 @@ class PeerPackedSet:
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         self._counts = torch.empty(self.world, dtype=torch.int64, device=dev)
         self._bounds_c = (C.c_int64 * (self.world + 1))(*self.bounds)
-        dist.all_reduce(self._token, group=self.group)  # every rank's buffers exist before anyone writes to them
+        # device-side exchange state (fgx_peer_exchange): one zeroed mailbox per rank in symmetric memory, the epoch
+        # counter and the error flag in local memory.  After this constructor no NCCL call is needed by a tick.
+        self._mailbox = symm.empty(int(L.lib.fgx_peer_mailbox_bytes()), dtype=torch.uint8, device=dev)
+        self._mailbox.zero_()
+        self._mailbox_hdl = symm.rendezvous(self._mailbox, self.group)
+        self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._gathered = torch.zeros(2 * L.MAX_PEERS, dtype=torch.int64, device=dev)
+        self._sync = L.PeerSync()
+        for d in range(self.world):
+            self._sync.mailbox[d] = int(self._mailbox_hdl.buffer_ptrs[d])
+        self._sync.epoch, self._sync.error = self._epoch.data_ptr(), self._error.data_ptr()
+        self._sync.rank, self._sync.world = self.rank, self.world
+        torch.cuda.synchronize()
+        dist.all_reduce(self._token, group=self.group)  # every rank's buffers exist (and mailboxes are zero) before anyone writes to them
 
     def _make_views(self, buf, leaves):
         out = []
@@ -128,12 +142,41 @@ class PeerPackedSet:
         self.cur = dst
         return self.agents
 
-    def pack_active(self):
-        """``sort_agents(active_state, descending)`` over the whole sharded set; returns the new local block."""
+    def exchange(self, v0=None, v1=None):
+        """All-gather of up to two int32 device scalars per rank through the mailboxes (``fgx_peer_exchange``: one
+        one-warp kernel, peer stores + flags, no host, no NCCL); with no values a barrier between the ranks' streams
+        that also publishes every peer store enqueued before it.  Returns int64[2, MAX_PEERS] (rows = values)."""
+        L.check(L.lib.fgx_peer_exchange(C.byref(self._sync), L.ptr(v0), L.ptr(v1), L.ptr(self._gathered), L.stream()))
+        return self._gathered.view(2, L.MAX_PEERS)
+
+    def add_range(self, n_selected_local, n_active_local, n_total):
+        """``distributed.global_add_range`` without NCCL or torch arithmetic: one launch (``fgx_peer_add_range``).
+        Returns int32 device scalars ``(k, local_count, j0)``."""
+        out = torch.empty(3, dtype=torch.int32, device=self._epoch.device)
+        L.check(L.lib.fgx_peer_add_range(C.byref(self._sync), L.ptr(L.device_i32(n_selected_local)),
+                                         L.ptr(L.device_i32(n_active_local)), self.n_local, self.bounds[self.rank],
+                                         int(n_total), L.ptr(out), L.stream()))
+        return out[0:1], out[1:2], out[2:3]
+
+    def check(self):
+        """Raises if a device-side exchange timed out (a peer never arrived); synchronises the stream."""
+        e = int(self._error.item())
+        if e:
+            raise L.FgxError(f"peer exchange timed out waiting for rank {e - 1}")
+
+    def pack_active(self, sync="peer"):
+        """``sort_agents(active_state, descending)`` over the whole sharded set; returns the new local block.
+        ``sync="peer"`` (default): the counts travel and the ranks are ordered by ``fgx_peer_exchange`` -- no NCCL
+        call, so the tick can be captured in a CUDA graph on every rank; ``sync="nccl"``: the round-1 path
+        (all-gather of the counts + an all-reduce as the barrier)."""
         from .base.agent_methods import select_agents
         agents = self.agents
         count, perm = select_agents(lambda a, p: P(a.active_state).nonzero(), None, agents)
-        dist.all_gather_into_tensor(self._counts, count.reshape(1).to(torch.int64), group=self.group)
+        if sync == "nccl":
+            dist.all_gather_into_tensor(self._counts, count.reshape(1).to(torch.int64), group=self.group)
+            counts = self._counts
+        else:
+            counts = self.exchange(count.reshape(1))[0]
         src, dst = self._views[self.cur], 1 - self.cur
         rows = [(v, off, rb) for v, off, rb, row in zip(src, self._offsets, self._row_bytes, self._is_row) if row]
         for s in range(0, len(rows), L.MAX_PEER_LEAVES):
@@ -145,7 +188,10 @@ class PeerPackedSet:
                 for d in range(self.world):
                     arr[k].dst[d] = self._ptrs[dst][d] + off
             L.check(L.lib.fgx_pack_rows_peer(arr, len(part), L.ptr(perm), L.ptr(count), self.n_local,
-                                             L.ptr(self._counts), self._bounds_c, self.rank, self.world, L.stream()))
-        dist.all_reduce(self._token, group=self.group)  # orders the ranks: every scatter has landed
+                                             L.ptr(counts), self._bounds_c, self.rank, self.world, L.stream()))
+        if sync == "nccl":
+            dist.all_reduce(self._token, group=self.group)  # orders the ranks: every scatter has landed
+        else:
+            self.exchange()  # system fence + flags: every rank's scatter has landed before anyone reads set `dst`
         self.cur = dst
         return self.agents

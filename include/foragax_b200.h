@@ -131,6 +131,34 @@ typedef struct {
 int fgx_pack_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm,
                        const int32_t* n_front, int64_t n_local, const int64_t* front_counts,
                        const int64_t* bounds_host, int32_t rank, int32_t world, fgx_stream_t stream);
+/* Device-side exchange of a few counts between the ranks of one node, with NO host involvement and no NCCL
+ * call: SURVEY.md 8e(2) ("all-gather of one int32 count per rank -> exclusive prefix") as a one-warp kernel over
+ * peer-mapped memory.  Every rank owns a MAILBOX (fgx_peer_mailbox_bytes() of symmetric memory, zeroed once);
+ * mailbox[d] is rank d's mailbox as mapped into this process.  One call = one epoch: the kernel stores this
+ * rank's values into its row of every peer's mailbox, releases a flag there (st.release.sys after a system
+ * fence -- which also publishes the peer stores of every kernel enqueued earlier on this stream, e.g. the row
+ * scatter of fgx_pack_rows_peer), spins on the flags the peers set in its own mailbox (bounded: on a timeout of
+ * ~5 s it raises *error and returns, it never hangs) and copies the gathered values out.  Every rank must call
+ * the same sequence of exchanges.  epoch: device uint64 (zeroed once), error: device int32 (zeroed once).
+ * With v0 == v1 == NULL the call is a pure barrier between the ranks' streams.
+ * out_all (may be NULL): int64[2][FGX_MAX_PEERS], out_all[j][s] = value j of rank s (0 when not supplied).      */
+typedef struct {
+  void* mailbox[FGX_MAX_PEERS];
+  uint64_t* epoch;
+  int32_t* error;
+  int32_t rank, world;
+} fgx_peer_sync_t;
+size_t fgx_peer_mailbox_bytes(void);
+int fgx_peer_exchange(const fgx_peer_sync_t* sync, const int32_t* v0, const int32_t* v1, int64_t* out_all,
+                      fgx_stream_t stream);
+/* add_agents over a globally packed, block-sharded set (agent_methods.py:26-38 + the caller's clip
+ * min(n_selected, N - n_active), README.md:124-125) in one launch: exchanges (n_selected_local, n_active_local)
+ * as above and writes out3 = { k = min(sum selected, n_total - sum active),
+ *                              local_count = rows of the global new range [A, A + k) inside this rank's block
+ *                                            [lo, lo + n_local),
+ *                              j0 = global add index of this rank's first new row }.                       */
+int fgx_peer_add_range(const fgx_peer_sync_t* sync, const int32_t* n_selected_local, const int32_t* n_active_local,
+                       int64_t n_local, int64_t lo, int64_t n_total, int32_t* out3, fgx_stream_t stream);
 /* sort_agents on a GENERAL key over the same block-sharded set: images[p] = order-preserving uint32 image of
  * keys[perm[p]] (perm = this rank's fgx_argsort); after an all-gather of every rank's sorted images
  * (images_all: [world][n_pad], rows padded), fgx_sort_rows_peer finds each local row's position in the

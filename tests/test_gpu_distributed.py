@@ -412,3 +412,65 @@ def test_two_gpu_agent_sensing_hit_indices_are_global_slots(layout, n):
     for rank, ok, frac in out:
         assert ok, f"rank {rank}: sharded sensing differs from the single-GPU result ({layout})"
         assert frac > 0.05
+
+
+def _sharded_world_worker(rank, world, port, n, q):
+    """examples/churn_sharded.py (no NCCL call inside the tick: counts and ordering through peer-memory mailboxes)
+    against examples/churn.py on the whole set: eager ticks, then the SAME ticks replayed from a CUDA graph."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from foragax_b200 import struct
+    from foragax_b200.examples.churn import ChurnWorld
+    from foragax_b200.examples.churn_sharded import ShardedChurnWorld
+    whole = ChurnWorld(n)
+    sh = ShardedChurnWorld(n)
+    lo, hi = sh.lo, sh.hi
+
+    def same():
+        return all(torch.equal(g, r[lo:hi]) for g, r in zip(struct.tree_leaves(sh.agents), struct.tree_leaves(whole.agents))
+                   if r.dim() and r.shape[0] == n)
+
+    ok_eager = same()
+    for _ in range(4):
+        whole.tick()
+        sh.tick()
+        ok_eager = ok_eager and same()
+    sh.packed.check()
+    graph = sh.capture_two_ticks()          # warm-up runs 2 ticks, the capture itself runs none
+    captured = graph is not None
+    ok_graph = True
+    if captured:
+        for _ in range(2):
+            whole.tick()
+        for _ in range(3):
+            graph.replay()                  # 6 ticks
+            for _ in range(2):
+                whole.tick()
+            torch.cuda.synchronize()
+            ok_graph = ok_graph and same()
+        sh.packed.check()
+    q.put((rank, bool(ok_eager), captured, bool(ok_graph)))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_churn_world_eager_and_graph():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n = 2, 400_003
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_world_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = _collect(procs, q, world)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_eager, captured, ok_graph in res:
+        assert ok_eager, f"rank {rank}: sharded eager ticks differ from the single-GPU set"
+        assert captured, f"rank {rank}: the two-tick CUDA graph could not be captured"
+        assert ok_graph, f"rank {rank}: graph-replayed ticks differ from the single-GPU set"
