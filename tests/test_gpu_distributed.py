@@ -474,3 +474,20 @@ def test_two_gpu_sharded_churn_world_eager_and_graph():
         assert ok_eager, f"rank {rank}: sharded eager ticks differ from the single-GPU set"
         assert captured, f"rank {rank}: the two-tick CUDA graph could not be captured"
         assert ok_graph, f"rank {rank}: graph-replayed ticks differ from the single-GPU set"
+
+
+def test_one_rank_sharded_churn_world_eager_and_graph():
+    """The same world with ONE rank (runs on a 1-GPU box): symmetric-memory state, mailbox exchange with itself,
+    two-tick CUDA graph -- equal to the plain single-GPU ChurnWorld."""
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_world_worker, args=(0, 1, port, 250_001, q))]
+    procs[0].start()
+    res = _collect(procs, q, 1)
+    procs[0].join(timeout=60)
+    assert procs[0].exitcode == 0
+    rank, ok_eager, captured, ok_graph = res[0]
+    assert ok_eager and captured and ok_graph
