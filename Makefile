@@ -26,10 +26,16 @@ oracle/_build/libfgx_oracle.so: oracle/c/fgx_oracle.c
 	@mkdir -p oracle/_build
 	gcc -O3 -mavx2 -mno-fma -fPIC -shared -fopenmp -ffp-contract=off -fno-fast-math -o $@ $< -lm
 
+# compile-only check of the XLA-FFI shim against a stand-in for jaxlib's xla/ffi/api/ffi.h (jaxlib is absent from
+# this image): every handler's parameter list is static_assert-ed against its binding and every launcher call
+# against include/foragax_b200.h
+xla-ffi-check:
+	g++ -std=c++17 -fsyntax-only -I$(CSRC)/xla_ffi/stub -Iinclude -I/usr/local/cuda/include $(CSRC)/xla_ffi/xla_ffi_shim.cc
+
 ptxas-info:
 	@for f in $(SRCS); do echo "== $$f"; $(NVCC) $(NVFLAGS) -Xptxas -v -c $$f -o /dev/null 2>&1 | grep -E "Compiling|registers|spill" ; done
 
 clean:
 	rm -rf build $(LIB) oracle/_build
 
-.PHONY: all oracle clean ptxas-info
+.PHONY: all oracle clean ptxas-info xla-ffi-check

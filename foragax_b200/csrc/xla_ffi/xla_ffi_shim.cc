@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 
 #include "foragax_b200.h"
+#include <string>
+
 #include "xla/ffi/api/ffi.h"
 
 namespace ffi = xla::ffi;
@@ -197,3 +199,341 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxDiceStep, DiceStepImpl,
                                   .Ret<ffi::Buffer<ffi::S32>>()
                                   .Ret<ffi::Buffer<ffi::U32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>());
+
+// =====================================================================================================
+// Round 2: the rest of the per-tick path.  In-place launchers are exposed the XLA way: every updated leaf is a
+// result that must ALIAS its operand (ffi_call(..., input_output_aliases={operand index: result index})); the
+// handlers verify the aliasing instead of copying.  Leaf lists ride in RemainingArgs / RemainingRets.
+// =====================================================================================================
+
+template <typename T>
+static T* ArgPtr(ffi::RemainingArgs& a, size_t i) {
+  auto b = a.get<ffi::AnyBuffer>(i);
+  return b.has_value() ? static_cast<T*>(b->untyped_data()) : nullptr;
+}
+static void* RetPtr(ffi::RemainingRets& r, size_t i) {
+  auto b = r.get<ffi::AnyBuffer>(i);
+  return b.has_value() ? (*b)->untyped_data() : nullptr;
+}
+static ffi::Error NotAliased(const char* op) {
+  return ffi::Error(ffi::ErrorCode::kInvalidArgument,
+                    std::string(op) + " updates in place: pass input_output_aliases for every result");
+}
+
+// ---- jax.random.uniform / randint on a key batch
+static ffi::Error UniformImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> keys, int32_t n, float minval, float maxval,
+                              ffi::Result<ffi::Buffer<ffi::F32>> out) {
+  return Status(fgx_threefry_uniform(keys.typed_data(), static_cast<int64_t>(keys.element_count() / 2), n, minval,
+                                     maxval, out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxThreefryUniform, UniformImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>()
+                                  .Attr<int32_t>("n")
+                                  .Attr<float>("minval")
+                                  .Attr<float>("maxval")
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+static ffi::Error RandintImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> keys, int32_t n, int32_t minval,
+                              int32_t maxval, ffi::Result<ffi::Buffer<ffi::S32>> out) {
+  return Status(fgx_threefry_randint(keys.typed_data(), static_cast<int64_t>(keys.element_count() / 2), n, minval,
+                                     maxval, out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxThreefryRandint, RandintImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>()
+                                  .Attr<int32_t>("n")
+                                  .Attr<int32_t>("minval")
+                                  .Attr<int32_t>("maxval")
+                                  .Ret<ffi::Buffer<ffi::S32>>());
+
+// ---- jnp.sum(active_state, dtype=int32) (agent_methods.py:27)
+static ffi::Error CountActiveImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> active,
+                                  ffi::Result<ffi::Buffer<ffi::S32>> out) {
+  return Status(fgx_count_active(active.typed_data(), static_cast<int64_t>(active.element_count()), out->typed_data(),
+                                 stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxCountActive, CountActiveImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>());
+
+// ---- remove_agents / add_agents with the Dice callbacks (README.md:73-90); results alias draw, (key,) active
+static ffi::Error DiceRemoveImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> remove_ids, ffi::Buffer<ffi::S32> k,
+                                 ffi::Buffer<ffi::S32> draw, ffi::Buffer<ffi::F32> active,
+                                 ffi::Result<ffi::Buffer<ffi::S32>> draw_out,
+                                 ffi::Result<ffi::Buffer<ffi::F32>> active_out) {
+  if (draw_out->typed_data() != draw.typed_data() || active_out->typed_data() != active.typed_data())
+    return NotAliased("fgx_dice_remove");
+  return Status(fgx_dice_remove(static_cast<int64_t>(active.element_count()), remove_ids.typed_data(), k.typed_data(),
+                                draw_out->typed_data(), active_out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxDiceRemove, DiceRemoveImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+static ffi::Error DiceAddImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> n_active, ffi::Buffer<ffi::S32> k,
+                              ffi::Buffer<ffi::S32> draw, ffi::Buffer<ffi::U32> key, ffi::Buffer<ffi::F32> active,
+                              int32_t sides, ffi::Result<ffi::Buffer<ffi::S32>> draw_out,
+                              ffi::Result<ffi::Buffer<ffi::U32>> key_out,
+                              ffi::Result<ffi::Buffer<ffi::F32>> active_out) {
+  if (draw_out->typed_data() != draw.typed_data() || key_out->typed_data() != key.typed_data() ||
+      active_out->typed_data() != active.typed_data())
+    return NotAliased("fgx_dice_add");
+  return Status(fgx_dice_add(static_cast<int64_t>(active.element_count()), sides, n_active.typed_data(), k.typed_data(),
+                             draw_out->typed_data(), key_out->typed_data(), active_out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxDiceAdd, DiceAddImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("sides")
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::U32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// ---- Forager leaves.  RemainingArgs layout (18 operands): the 11 state leaves in the order of
+// fgx_forager_state_t, then J, tau, E, B, D, Z, then age.  RemainingRets (13 results): the 11 state leaves, Z, age
+// -- each aliased to its operand.
+static constexpr size_t kForagerArgs = 18, kForagerRets = 13;
+
+static ffi::Error ForagerLeaves(const char* op, ffi::RemainingArgs& args, ffi::RemainingRets& rets,
+                                fgx_forager_state_t* st, fgx_wc_policy_t* pol, float** age) {
+  if (args.size() != kForagerArgs || rets.size() != kForagerRets)
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument,
+                      std::string(op) + ": expected 18 leaf operands (11 state, J, tau, E, B, D, Z, age) and 13 results");
+  float** s = reinterpret_cast<float**>(st);
+  for (size_t i = 0; i < 11; ++i) {
+    s[i] = ArgPtr<float>(args, i);
+    if (RetPtr(rets, i) != s[i]) return NotAliased(op);
+  }
+  pol->J = ArgPtr<float>(args, 11);
+  pol->tau = ArgPtr<float>(args, 12);
+  pol->E = ArgPtr<float>(args, 13);
+  pol->B = ArgPtr<float>(args, 14);
+  pol->D = ArgPtr<float>(args, 15);
+  pol->Z = ArgPtr<float>(args, 16);
+  *age = ArgPtr<float>(args, 17);
+  if (RetPtr(rets, 11) != pol->Z || RetPtr(rets, 12) != *age) return NotAliased(op);
+  return ffi::Error::Success();
+}
+
+// ---- step_agents + vmapped Forager.step_agent with WilsonCowan.step_policy (sim.py:74-136, wilson_cowan.py:34-51)
+static ffi::Error ForagerStepImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> active, ffi::Buffer<ffi::F32> obs,
+                                  ffi::Buffer<ffi::F32> energy_in, ffi::RemainingArgs args, int32_t n_neurons,
+                                  int32_t n_obs, int32_t n_act, float dt, float policy_dt, float action_scale,
+                                  float x_min, float x_max, float y_min, float y_max, float repr_thresh,
+                                  float die_thresh, float energy_min, float energy_max, float energy_cost_dt,
+                                  int32_t clip_min, ffi::RemainingRets rets) {
+  fgx_forager_params_t p{n_neurons, n_obs,       n_act,      dt,         policy_dt,  action_scale,   x_min,   x_max,
+                         y_min,     y_max,       repr_thresh, die_thresh, energy_min, energy_max, energy_cost_dt, clip_min};
+  fgx_forager_state_t st{};
+  fgx_wc_policy_t pol{};
+  float* age = nullptr;
+  ffi::Error e = ForagerLeaves("fgx_forager_step", args, rets, &st, &pol, &age);
+  if (!e.success()) return e;
+  return Status(fgx_forager_step(&p, static_cast<int64_t>(active.element_count()), active.typed_data(),
+                                 obs.typed_data(), energy_in.typed_data(), &st, &pol, age, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerStep, ForagerStepImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .RemainingArgs()
+                                  .Attr<int32_t>("n_neurons")
+                                  .Attr<int32_t>("n_obs")
+                                  .Attr<int32_t>("n_act")
+                                  .Attr<float>("dt")
+                                  .Attr<float>("policy_dt")
+                                  .Attr<float>("action_scale")
+                                  .Attr<float>("x_min")
+                                  .Attr<float>("x_max")
+                                  .Attr<float>("y_min")
+                                  .Attr<float>("y_max")
+                                  .Attr<float>("repr_thresh")
+                                  .Attr<float>("die_thresh")
+                                  .Attr<float>("energy_min")
+                                  .Attr<float>("energy_max")
+                                  .Attr<float>("energy_cost_dt")
+                                  .Attr<int32_t>("clip_min")
+                                  .RemainingRets());
+
+// ---- remove_agents / set_agents with the Forager callbacks (sim.py:139-151,213-225)
+static ffi::Error ForagerRemoveImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> remove_ids, ffi::Buffer<ffi::S32> k,
+                                    ffi::Buffer<ffi::F32> active, ffi::RemainingArgs args, int32_t n_neurons,
+                                    ffi::Result<ffi::Buffer<ffi::F32>> active_out, ffi::RemainingRets rets) {
+  fgx_forager_state_t st{};
+  fgx_wc_policy_t pol{};
+  float* age = nullptr;
+  ffi::Error e = ForagerLeaves("fgx_forager_remove", args, rets, &st, &pol, &age);
+  if (!e.success()) return e;
+  if (active_out->typed_data() != active.typed_data()) return NotAliased("fgx_forager_remove");
+  return Status(fgx_forager_remove(static_cast<int64_t>(active.element_count()), n_neurons, remove_ids.typed_data(),
+                                   k.typed_data(), &st, pol.Z, active_out->typed_data(), age, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerRemove, ForagerRemoveImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .RemainingArgs()
+                                  .Attr<int32_t>("n_neurons")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .RemainingRets());
+
+static ffi::Error ForagerSetImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> set_ids, ffi::Buffer<ffi::S32> k,
+                                 ffi::Buffer<ffi::F32> active, ffi::RemainingArgs args, ffi::RemainingRets rets) {
+  fgx_forager_state_t st{};
+  fgx_wc_policy_t pol{};
+  float* age = nullptr;
+  ffi::Error e = ForagerLeaves("fgx_forager_set", args, rets, &st, &pol, &age);
+  if (!e.success()) return e;
+  return Status(fgx_forager_set(static_cast<int64_t>(active.element_count()), set_ids.typed_data(), k.typed_data(), &st,
+                                stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerSet, ForagerSetImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .RemainingArgs()
+                                  .RemainingRets());
+
+// ---- add_agents with Forager.add_agent (sim.py:154-210): the serial key chain runs in a one-thread pre-pass
+// inside the launcher (chain_scratch uint32[n, 2]: the chain key of every added row, from the scratch allocator)
+static ffi::Error ForagerAddImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> good_ids, ffi::Buffer<ffi::S32> n_active,
+                                 ffi::Buffer<ffi::S32> k, ffi::Buffer<ffi::U32> key_in, ffi::Buffer<ffi::F32> active,
+                                 ffi::RemainingArgs args, ffi::ScratchAllocator scratch, int32_t n_neurons,
+                                 int32_t n_obs, int32_t n_act, float noise_scale, int32_t adaptive_noise,
+                                 ffi::Result<ffi::Buffer<ffi::U32>> key_out,
+                                 ffi::Result<ffi::Buffer<ffi::F32>> active_out, ffi::RemainingRets rets) {
+  fgx_forager_state_t st{};
+  fgx_wc_policy_t pol{};
+  float* age = nullptr;
+  ffi::Error e = ForagerLeaves("fgx_forager_add", args, rets, &st, &pol, &age);
+  if (!e.success()) return e;
+  if (active_out->typed_data() != active.typed_data()) return NotAliased("fgx_forager_add");
+  const int64_t n = static_cast<int64_t>(active.element_count());
+  auto buf = scratch.Allocate(static_cast<size_t>(n) * 2 * sizeof(uint32_t) + 64, 256);  // chain_scratch uint32[n, 2]
+  if (!buf.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "fgx_forager_add: scratch");
+  return Status(fgx_forager_add(n, n_neurons, n_obs, n_act, good_ids.typed_data(), n_active.typed_data(),
+                                k.typed_data(), key_in.typed_data(), key_out->typed_data(), noise_scale, adaptive_noise,
+                                &st, &pol, active_out->typed_data(), age, static_cast<uint32_t*>(*buf), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerAdd, ForagerAddImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .RemainingArgs()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Attr<int32_t>("n_neurons")
+                                  .Attr<int32_t>("n_obs")
+                                  .Attr<int32_t>("n_act")
+                                  .Attr<float>("noise_scale")
+                                  .Attr<int32_t>("adaptive_noise")
+                                  .Ret<ffi::Buffer<ffi::U32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .RemainingRets());
+
+// ---- sensor_model (EcoEvoJax/sim.py:388-468): foragers x rays x [foragers, resources, walls] -> obs [F, 3 R]
+static ffi::Error SensorModelImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> fx, ffi::Buffer<ffi::F32> fy,
+                                  ffi::Buffer<ffi::F32> fang, ffi::Buffer<ffi::F32> frad, ffi::Buffer<ffi::F32> fenergy,
+                                  ffi::Buffer<ffi::F32> factive, ffi::Buffer<ffi::S32> ftype, ffi::Buffer<ffi::F32> rx,
+                                  ffi::Buffer<ffi::F32> ry, ffi::Buffer<ffi::F32> rrad, ffi::Buffer<ffi::F32> renergy,
+                                  ffi::Buffer<ffi::F32> ractive, ffi::Buffer<ffi::S32> rtype, ffi::Buffer<ffi::F32> wx1,
+                                  ffi::Buffer<ffi::F32> wy1, ffi::Buffer<ffi::F32> wx2, ffi::Buffer<ffi::F32> wy2,
+                                  int32_t n_rays, float ray_span, float ray_length,
+                                  ffi::Result<ffi::Buffer<ffi::F32>> obs) {
+  return Status(fgx_sensor_model(static_cast<int64_t>(fx.element_count()), fx.typed_data(), fy.typed_data(),
+                                 fang.typed_data(), frad.typed_data(), fenergy.typed_data(), factive.typed_data(),
+                                 ftype.typed_data(), static_cast<int64_t>(rx.element_count()), rx.typed_data(),
+                                 ry.typed_data(), rrad.typed_data(), renergy.typed_data(), ractive.typed_data(),
+                                 rtype.typed_data(), static_cast<int64_t>(wx1.element_count()), wx1.typed_data(),
+                                 wy1.typed_data(), wx2.typed_data(), wy2.typed_data(), n_rays, ray_span, ray_length,
+                                 obs->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxSensorModel, SensorModelImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("n_rays")
+                                  .Attr<float>("ray_span")
+                                  .Attr<float>("ray_length")
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// ---- ray_generator + ray_agent_sensor + min/argmin over target circles through a uniform grid
+// (space_methods.py:71-94, sim.py:444-447); targets as separate x / y / rad / active arrays
+static ffi::Error RaycastAgentsImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> y,
+                                    ffi::Buffer<ffi::F32> ang, ffi::Buffer<ffi::F32> active, ffi::Buffer<ffi::F32> tx,
+                                    ffi::Buffer<ffi::F32> ty, ffi::Buffer<ffi::F32> trad, ffi::Buffer<ffi::F32> tactive,
+                                    ffi::ScratchAllocator scratch, int32_t n_rays, float ray_span, float ray_length,
+                                    float x_min, float x_max, float y_min, float y_max, float max_rad,
+                                    ffi::Result<ffi::Buffer<ffi::F32>> dist, ffi::Result<ffi::Buffer<ffi::S32>> hit) {
+  const int64_t n = static_cast<int64_t>(x.element_count()), m = static_cast<int64_t>(tx.element_count());
+  const size_t bytes = fgx_raycast_agents_scratch_bytes(n, m, x_min, x_max, y_min, y_max, ray_length, max_rad);
+  auto buf = scratch.Allocate(bytes, 256);
+  if (!buf.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "fgx_raycast_agents: scratch");
+  return Status(fgx_raycast_agents(x.typed_data(), y.typed_data(), ang.typed_data(), active.typed_data(), n, n_rays,
+                                   ray_span, ray_length, tx.typed_data(), ty.typed_data(), trad.typed_data(),
+                                   tactive.typed_data(), /*target_stride=*/1, m, x_min, x_max, y_min, y_max, max_rad,
+                                   /*merge_walls=*/0, dist->typed_data(), hit->typed_data(), *buf, bytes, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxRaycastAgents, RaycastAgentsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Attr<int32_t>("n_rays")
+                                  .Attr<float>("ray_span")
+                                  .Attr<float>("ray_length")
+                                  .Attr<float>("x_min")
+                                  .Attr<float>("x_max")
+                                  .Attr<float>("y_min")
+                                  .Attr<float>("y_max")
+                                  .Attr<float>("max_rad")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>());
