@@ -227,7 +227,7 @@ def run_reference(args):
     sample = (f"each step = one tick (ray cast + forager step) over the first {n_sample} agents x {N_RAYS} rays x "
               f"{N_WALLS} walls; C restatement of the reference path (oracle/c, OpenMP); the reference needs jax, "
               "absent from this image")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -235,7 +235,7 @@ def run_reference(args):
         "agent_steps_per_sec": n_sample / sec,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": tick.c.threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def build_foragers(work, rank, world, dev, n_agents=None):
@@ -751,7 +751,7 @@ def run_ours(args):
                                         "note": "like for like: neither side culls (the CPU port is all-pairs)"}
         if world == 1 and not args.no_extra:
             line["other_configs"] = other_configs()
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -771,7 +771,18 @@ def other_configs():
     return out
 
 
+_STDOUT = sys.stdout
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (everything else -- e.g. the reference API's own
+    "AgentSet initialized" print, agent_classes.py:83 -- is sent to stderr while the bench runs)."""
+    _STDOUT.write(json.dumps(line) + "\n")
+    _STDOUT.flush()
+
+
 def main():
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
