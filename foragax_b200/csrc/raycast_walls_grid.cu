@@ -73,15 +73,14 @@ __global__ void __launch_bounds__(128) wall_count_kernel(WGrid g, const float* _
                                                          const float* __restrict__ wy1, const float* __restrict__ wx2,
                                                          const float* __restrict__ wy2, int n_walls,
                                                          uint32_t* __restrict__ count, float4* __restrict__ wall4,
-                                                         float4* __restrict__ wallb, float* __restrict__ wallt,
-                                                         WState* __restrict__ st) {
+                                                         float4* __restrict__ wallr, WState* __restrict__ st) {
   const int cu = blockIdx.x * blockDim.x + threadIdx.x;
   for (int w = blockIdx.y; w < n_walls; w += gridDim.y) {
     const float ax = wx1[w], ay = wy1[w], bx = wx2[w], by = wy2[w];
-    if (cu == 0) {  // the records the sensing side reads: endpoints, bounding box, |o3| threshold of the line band
+    if (cu == 0) {  // the records the sensing side reads: end points; bounding box + unit-normal line with its band
       wall4[w] = make_float4(ax, ay, bx, by);
-      wallb[w] = make_float4(fminf(ax, bx), fminf(ay, by), fmaxf(ax, bx), fmaxf(ay, by));
-      wallt[w] = g.tol_line * norm2(f_sub(bx, ax), f_sub(by, ay));
+      wallr[2 * w] = make_float4(fminf(ax, bx), fminf(ay, by), fmaxf(ax, bx), fmaxf(ay, by));
+      wallr[2 * w + 1] = wall_line_record(ax, ay, bx, by, g.tol_line, g.scale);
     }
     if (!wall_in_scale(g, ax, ay, bx, by)) {
       if (cu == 0) st->fallback = 1;
@@ -164,8 +163,9 @@ struct WallsGridArgs {
 // IEEE division -- whose j = 0 lane takes the slow path of the software divide -- runs once per CTA, not per ray).
 constexpr int WG_STEP_TABLE = 256;
 
-template <int NR>
-__global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGridArgs a, uint32_t total) {
+// MINB: resident CTAs per SM the register allocation aims for (4 = 64 registers; 3 = 80; FGX_WG_OCC picks, default 4)
+template <int NR, int MINB>
+__global__ void __launch_bounds__(256, MINB) raycast_walls_grid_kernel(const WallsGridArgs a, uint32_t total) {
   __shared__ float s_step[WG_STEP_TABLE];
   const uint32_t nr = NR > 0 ? (uint32_t)NR : (uint32_t)a.n_rays;
   const bool table = nr <= (uint32_t)WG_STEP_TABLE;
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
     __syncthreads();
   }
   const float L = a.L, span = a.span;
+  const bool fallback = a.v.st->fallback != 0;  // written by the grid build (an earlier launch)
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const uint32_t agent = t / nr;
     const uint32_t j = t - agent * nr;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) raycast_walls_grid_kernel(const WallsGrid
     const float q1x = f_add(p1x, f_mul(cs, L)), q1y = f_add(p1y, f_mul(sn, L));
     float best = L;
     int bidx = -1;
-    walls_grid_cast(a.v, p1x, p1y, q1x, q1y, L, best, bidx);
+    walls_grid_cast(a.v, fallback, p1x, p1y, q1x, q1y, L, best, bidx);
     a.dist[t] = best;
     if (a.hit) a.hit[t] = bidx;
   }
@@ -298,8 +299,8 @@ size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float 
   WGrid g;
   if (n_walls < 0 || wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + 2 * wg_al((size_t)n_walls * 16 + 16) +
-         wg_al((size_t)n_walls * 4 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
+  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((size_t)n_walls * 16 + 16) +
+         wg_al((size_t)n_walls * 32 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
 }
 
 int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
@@ -323,10 +324,8 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
   p += wg_al(((size_t)n_cells + 1) * 4);
   float4* wall4 = reinterpret_cast<float4*>(p);
   p += wg_al((size_t)n_walls * 16 + 16);
-  float4* wallb = reinterpret_cast<float4*>(p);
-  p += wg_al((size_t)n_walls * 16 + 16);
-  float* wallt = reinterpret_cast<float*>(p);
-  p += wg_al((size_t)n_walls * 4 + 16);
+  float4* wallr = reinterpret_cast<float4*>(p);
+  p += wg_al((size_t)n_walls * 32 + 16);
   int32_t* entries = reinterpret_cast<int32_t*>(p);
   cudaError_t e = cudaSuccess;
   if (reuse_grid) {
@@ -336,14 +335,14 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     const int nmaj = g.gx > g.gy ? g.gx : g.gy;
     const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
-    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, wallb, wallt, st);
+    wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, wallr, st);
     wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
   } else {
     e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4), s);
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
-  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, wallb, wallt, st};
+  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, wallr, st};
   return FGX_OK;
 }
 
@@ -381,12 +380,16 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
     raycast_walls_grid_kernel_big<<<grid, 256, 0, s>>>(a);
   } else {
     const uint32_t t32 = (uint32_t)total;
+    static const int occ = [] { const char* v = getenv("FGX_WG_OCC"); return v && atoi(v) == 3 ? 3 : 4; }();
     switch (n_rays) {
-      case 32: raycast_walls_grid_kernel<32><<<grid, 256, 0, s>>>(a, t32); break;
-      case 16: raycast_walls_grid_kernel<16><<<grid, 256, 0, s>>>(a, t32); break;
-      case 9: raycast_walls_grid_kernel<9><<<grid, 256, 0, s>>>(a, t32); break;
-      case 8: raycast_walls_grid_kernel<8><<<grid, 256, 0, s>>>(a, t32); break;
-      default: raycast_walls_grid_kernel<0><<<grid, 256, 0, s>>>(a, t32); break;
+      case 32:
+        if (occ == 3) raycast_walls_grid_kernel<32, 3><<<grid, 256, 0, s>>>(a, t32);
+        else raycast_walls_grid_kernel<32, 4><<<grid, 256, 0, s>>>(a, t32);
+        break;
+      case 16: raycast_walls_grid_kernel<16, 4><<<grid, 256, 0, s>>>(a, t32); break;
+      case 9: raycast_walls_grid_kernel<9, 4><<<grid, 256, 0, s>>>(a, t32); break;
+      case 8: raycast_walls_grid_kernel<8, 4><<<grid, 256, 0, s>>>(a, t32); break;
+      default: raycast_walls_grid_kernel<0, 4><<<grid, 256, 0, s>>>(a, t32); break;
     }
   }
   return check_launch("fgx_raycast_walls_grid");

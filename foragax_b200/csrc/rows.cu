@@ -98,14 +98,19 @@ __global__ void __launch_bounds__(256) count_active_kernel(const float* __restri
                                                            int32_t* __restrict__ out,
                                                            const int32_t* __restrict__ clip_in) {
   int c = 0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n; i += 4 * stride) {
-    const float a0 = __ldg(active + i), a1 = __ldg(active + i + stride), a2 = __ldg(active + i + 2 * stride),
-                a3 = __ldg(active + i + 3 * stride);
-    c += (int)a0 + (int)a1 + (int)a2 + (int)a3;  // sum(x, dtype=int32) converts each element first
+  // 16-byte loads when the leaf is 16-byte aligned (it is, unless the caller passes an offset view); n < 2^31
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(active) & 15) == 0) {
+    const float4* __restrict__ a4 = reinterpret_cast<const float4*>(active);
+    const uint32_t n4 = (uint32_t)(n >> 2);
+    for (uint32_t i = tid; i < n4; i += stride) {
+      const float4 v = __ldg(a4 + i);
+      c += (int)v.x + (int)v.y + (int)v.z + (int)v.w;  // sum(x, dtype=int32) converts each element first
+    }
+    done = n4 << 2;
   }
-  for (; i < n; i += stride) c += (int)__ldg(active + i);
+  for (uint32_t i = done + tid; i < (uint32_t)n; i += stride) c += (int)__ldg(active + i);
   c = __reduce_add_sync(0xffffffffu, c);
   __shared__ int ws[8];
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
@@ -198,7 +203,7 @@ int fgx_gather_rows_from(const fgx_leaf_t* leaves_host, int32_t n_leaves, const 
 
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream) {
   using namespace fgx;
-  FGX_REQUIRE(n >= 0 && out, "fgx_count_active: bad arguments");
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31) && out, "fgx_count_active: bad arguments");
   cudaStream_t s = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int32_t), s);
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_count_active: %s", cudaGetErrorString(e));
@@ -211,7 +216,7 @@ int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_str
 int fgx_count_active_clip(const float* active_state, int64_t n, const int32_t* n_add, int32_t* out3,
                           fgx_stream_t stream) {
   using namespace fgx;
-  FGX_REQUIRE(n >= 0 && out3 && n_add, "fgx_count_active_clip: bad arguments");
+  FGX_REQUIRE(n >= 0 && n < (1ll << 31) && out3 && n_add, "fgx_count_active_clip: bad arguments");
   FGX_REQUIRE(n == 0 || active_state, "fgx_count_active_clip: null pointer");
   cudaStream_t s = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(out3, 0, 3 * sizeof(int32_t), s);

@@ -28,8 +28,8 @@ struct WallsGridView {
   const uint32_t* start;
   const int32_t* entries;
   const float4* wall4;  // (p2x, p2y, q2x, q2y) per wall, packed by the grid build
-  const float4* wallb;  // (min x, min y, max x, max y) of the wall
-  const float* wallt;   // tol_line * |q2 - p2|: |o3| above it <=> the agent is farther than tol_line from the wall's line
+  const float4* wallr;  // pre-test records, two float4 per wall: (min x, min y, max x, max y) of the wall and its
+                        // unit-normal line (a, b, c, line band): a x + b y + c = signed distance to the wall's line
   const WState* st;
 };
 
@@ -63,11 +63,10 @@ static __device__ __noinline__ float ray_wall_exact_o(float p1x, float p1y, floa
 // one (ray, wall) pair, exactly as the all-pairs kernel decides it: sure miss <=> no candidate distance of
 // ray_wall_sensor can apply (max(o1*o2, o3*o4) > 0 and all four determinants nonzero); otherwise the op-for-op
 // restatement.  (distance, wall) minima are lexicographic = argmin's first-index rule for any visiting order.
-// o3 = orient_val(p2, q2, p1) is passed in (the pre-test computed it).
-__device__ __forceinline__ void test_wall_o3(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
-                                             float q2x, float q2y, float o3, int w, float& best, int& bidx) {
+__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
+                                          float q2x, float q2y, int w, float& best, int& bidx) {
   const float o1 = orient_val(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_val(p1x, p1y, q1x, q1y, q2x, q2y);
-  const float o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
+  const float o3 = orient_val(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
   const float A = f_mul(o1, o2), B = f_mul(o3, o4);
   if (fmaxf(A, B) > 0.0f && fabsf(f_mul(A, B)) > 0.0f) return;
   const float d = ray_wall_exact_o(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, o1, o2, o3, o4);
@@ -75,10 +74,6 @@ __device__ __forceinline__ void test_wall_o3(float p1x, float p1y, float q1x, fl
     best = d;
     bidx = w;
   }
-}
-__device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
-                                          float q2x, float q2y, int w, float& best, int& bidx) {
-  test_wall_o3(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, orient_val(p2x, p2y, q2x, q2y, p1x, p1y), w, best, bidx);
 }
 
 // The ray's bounding box widened by g.margin (what the per-ray pre-test compares wall boxes with).
@@ -98,51 +93,65 @@ __device__ __forceinline__ RayBox ray_box(float p1x, float p1y, float q1x, float
 //       distance units) of zero, i.e. the wall's line passes within that noise of a ray endpoint or the ray's line
 //       of a wall endpoint, with the true crossing of the two LINES outside the widened box -- the lines are then
 //       parallel to within noise / margin and p1 sits within (2 L / margin + 1) * noise of the wall's line;
-//       tol_line is 8x that (and never below the list builder's eps); c4 (d = 0) needs o3 == 0 exactly.
-// So: skip <=> boxes disjoint AND |o3| > tol_line * |q2 - p2|.  NaN operands fail every comparison -> not skipped.
-__device__ __forceinline__ bool walls_pretest_skip(const RayBox& rb, const float4& bb, float o3, float tolw) {
+//       tol_line is 8x that (and never below the list builder's eps); c4 (d = 0) needs o3 == 0 exactly, i.e. p1 ON
+//       the line.
+// So: skip <=> boxes disjoint AND p1 farther than the line band from the wall's line.  The distance comes from the
+// wall's unit-normal line equation (two FMAs; its own rounding, a few ulp of S, is added to the band by the grid
+// build), and only walls that survive load their end points.  NaN operands fail every comparison -> not skipped;
+// a zero-length wall has the line (0, 0, 0) -> distance 0 -> never skipped by (b).
+__device__ __forceinline__ bool walls_pretest_skip(const RayBox& rb, const float4& bb, const float4& ln, float px,
+                                                   float py) {
   const bool disjoint = bb.z < rb.x0 || bb.x > rb.x1 || bb.w < rb.y0 || bb.y > rb.y1;
-  return disjoint && fabsf(o3) > tolw;
+  return disjoint && fabsf(fmaf(ln.x, px, fmaf(ln.y, py, ln.z))) > ln.w;
+}
+__device__ __forceinline__ float4 wall_line_record(float ax, float ay, float bx, float by, float tol_line, float scale) {
+  const float dx = bx - ax, dy = by - ay, len = sqrtf(dx * dx + dy * dy);
+  const float inv = len > 0.0f ? 1.0f / len : 0.0f;
+  const float na = -dy * inv, nb = dx * inv;  // unit normal; (0, 0) for a zero-length wall
+  return make_float4(na, nb, -(na * ax + nb * ay), tol_line * 1.05f + 8e-7f * scale);
 }
 
-// min / first-argmin over the walls for the ray p1 -> q1 (best = L, bidx = -1 on entry)
-__device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, float p1x, float p1y, float q1x, float q1y,
-                                                float L, float& best, int& bidx) {
+// min / first-argmin over the walls for the ray p1 -> q1 (best = L, bidx = -1 on entry); `fallback`: the value of
+// v.st->fallback (read once per thread by the caller)
+__device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, bool fallback, float p1x, float p1y, float q1x,
+                                                float q1y, float L, float& best, int& bidx) {
   // strictly inside the grid (NaN positions fail and take the all-walls loop)
   const float fx = (p1x - v.g.x0) * v.g.inv_cs, fy = (p1y - v.g.y0) * v.g.inv_cs;
   const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
   const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
-  if (inside && v.st->fallback == 0) {
+  if (inside && !fallback) {
     const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
     const uint32_t e0 = v.start[cell], e1 = v.start[cell + 1];
-    if (e0 >= e1) return;
-    // records one entry ahead of the tests: (index -> endpoints, box, tolerance) of entry e + 1 load while e is tested
-    int w = v.entries[e0];
-    float4 wl = v.wall4[w], bb = v.wallb[w];
-    float tw = v.wallt[w];
-    for (uint32_t e = e0; e < e1; ++e) {
-      const int wc = w;
-      const float4 wlc = wl, bbc = bb;
-      const float twc = tw;
-      if (e + 1 < e1) {
-        w = v.entries[e + 1];
-        wl = v.wall4[w];
-        bb = v.wallb[w];
-        tw = v.wallt[w];
+    for (uint32_t e = e0; e < e1; e += 4) {  // four independent (index -> records) load chains in flight
+      int w[4];
+      float4 bb[4], ln[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = v.entries[min(e + u, e1 - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4* __restrict__ r = v.wallr + 2 * (int64_t)w[u];
+        bb[u] = r[0];
+        ln[u] = r[1];
       }
-      const float o3 = orient_val(wlc.x, wlc.y, wlc.z, wlc.w, p1x, p1y);
-      if (walls_pretest_skip(rb, bbc, o3, twc)) continue;
-      test_wall_o3(p1x, p1y, q1x, q1y, L, wlc.x, wlc.y, wlc.z, wlc.w, o3, wc, best, bidx);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (e + u >= e1 || walls_pretest_skip(rb, bb[u], ln[u], p1x, p1y)) continue;
+        const float4 wl = v.wall4[w[u]];
+        test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, w[u], best, bidx);
+      }
     }
   } else {
     for (int w = 0; w < v.n_walls; ++w) {
       const float4 wl = make_float4(v.wx1[w], v.wy1[w], v.wx2[w], v.wy2[w]);
       const float4 bb = make_float4(fminf(wl.x, wl.z), fminf(wl.y, wl.w), fmaxf(wl.x, wl.z), fmaxf(wl.y, wl.w));
-      const float o3 = orient_val(wl.x, wl.y, wl.z, wl.w, p1x, p1y);
-      if (walls_pretest_skip(rb, bb, o3, v.g.tol_line * norm2(f_sub(wl.z, wl.x), f_sub(wl.w, wl.y)))) continue;
-      test_wall_o3(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, o3, w, best, bidx);
+      if (walls_pretest_skip(rb, bb, wall_line_record(wl.x, wl.y, wl.z, wl.w, v.g.tol_line, v.g.scale), p1x, p1y)) continue;
+      test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, w, best, bidx);
     }
   }
+}
+__device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, float p1x, float p1y, float q1x, float q1y,
+                                                float L, float& best, int& bidx) {
+  walls_grid_cast(v, v.st->fallback != 0, p1x, p1y, q1x, q1y, L, best, bidx);
 }
 
 // host side (raycast_walls_grid.cu): validates, carves the scratch and -- unless reuse_grid -- builds the wall
