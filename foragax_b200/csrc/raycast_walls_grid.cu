@@ -148,6 +148,22 @@ __global__ void __launch_bounds__(128) wall_fill_kernel(WGrid g, const float* __
                       [&](int cell) { entries[start[cell] + atomicAdd(cursor + cell, 1u)] = w; });
 }
 
+// cell records for the sensing side: list range + the first six wall indices of every cell (unused index slots
+// repeat a valid index -- 0 when the list is empty -- so that speculative record loads stay in bounds)
+__global__ void __launch_bounds__(256) wall_cellrec_kernel(int n_cells, const uint32_t* __restrict__ start,
+                                                           const int32_t* __restrict__ entries,
+                                                           uint4* __restrict__ cellrec, const WState* __restrict__ st) {
+  if (st->fallback) return;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+    const uint32_t e0 = start[c], n = start[c + 1] - e0;
+    uint32_t w[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) w[u] = n ? (uint32_t)entries[e0 + min((uint32_t)u, n - 1)] : 0u;
+    cellrec[2 * c] = make_uint4(e0, n, w[0], w[1]);
+    cellrec[2 * c + 1] = make_uint4(w[2], w[3], w[4], w[5]);
+  }
+}
+
 struct WallsGridArgs {
   WallsGridView v;
   const float *ax, *ay, *aang, *aactive;
@@ -176,15 +192,31 @@ __global__ void __launch_bounds__(256, MINB) raycast_walls_grid_kernel(const Wal
   }
   const float L = a.L, span = a.span;
   const bool fallback = a.v.st->fallback != 0;  // written by the grid build (an earlier launch)
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+  // software pipeline over the grid-stride loop: the pose of the NEXT (agent, ray) of this thread is loaded while
+  // the current one is processed, which takes the first of the dependent loads (pose -> cell record -> wall
+  // records -> end points) off every agent's critical path
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  float n_act = 1.0f, n_x = 0.0f, n_y = 0.0f, n_ang = 0.0f;
+  if (t < total) {
+    const uint32_t ag = t / nr;
+    n_act = a.aactive != nullptr ? __ldg(a.aactive + ag) : 1.0f;
+    n_x = __ldg(a.ax + ag); n_y = __ldg(a.ay + ag); n_ang = __ldg(a.aang + ag);
+  }
+  for (; t < total; t += stride) {
     const uint32_t agent = t / nr;
     const uint32_t j = t - agent * nr;
-    if (a.aactive != nullptr && __ldg(a.aactive + agent) == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
+    const float act = n_act, p1x = n_x, p1y = n_y, ang = n_ang;
+    if (t + stride < total) {
+      const uint32_t ag = (t + stride) / nr;
+      n_act = a.aactive != nullptr ? __ldg(a.aactive + ag) : 1.0f;
+      n_x = __ldg(a.ax + ag); n_y = __ldg(a.ay + ag); n_ang = __ldg(a.aang + ag);
+    }
+    if (act == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
       a.dist[t] = 0.0f;
       if (a.hit) a.hit[t] = -1;
       continue;
     }
-    const float p1x = __ldg(a.ax + agent), p1y = __ldg(a.ay + agent), ang = __ldg(a.aang + agent);
     // ray_generator (space_methods.py:56-69): linspace(ang - span, ang + span, n)[j] = lo*(1-s) + hi*s, last = hi
     const float lo = f_sub(ang, span), hi = f_add(ang, span);
     float th;
@@ -299,8 +331,8 @@ size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float 
   WGrid g;
   if (n_walls < 0 || wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((size_t)n_walls * 16 + 16) +
-         wg_al((size_t)n_walls * 32 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
+  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((cells + 1) * 32) +
+         wg_al((size_t)n_walls * 16 + 16) + wg_al((size_t)n_walls * 32 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
 }
 
 int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, const float* wx2, const float* wy2,
@@ -322,6 +354,8 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
   p += wg_al(((size_t)n_cells + 1) * 4);
   uint32_t* start = reinterpret_cast<uint32_t*>(p);
   p += wg_al(((size_t)n_cells + 1) * 4);
+  uint4* cellrec = reinterpret_cast<uint4*>(p);
+  p += wg_al(((size_t)n_cells + 1) * 32);
   float4* wall4 = reinterpret_cast<float4*>(p);
   p += wg_al((size_t)n_walls * 16 + 16);
   float4* wallr = reinterpret_cast<float4*>(p);
@@ -338,11 +372,14 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
     wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, wallr, st);
     wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
+    wall_cellrec_kernel<<<grid_for(n_cells, 256, 4), 256, 0, s>>>(n_cells, start, entries, cellrec, st);
   } else {
-    e = cudaMemsetAsync(scratch, 0, wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4), s);
+    // no walls: empty lists everywhere (start, cursors and cell records all zero)
+    e = cudaMemsetAsync(scratch, 0,
+                        wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4) + wg_al(((size_t)n_cells + 1) * 32), s);
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
-  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, wallr, st};
+  *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, cellrec, wallr, st};
   return FGX_OK;
 }
 

@@ -28,6 +28,8 @@ struct WallsGridView {
   const uint32_t* start;
   const int32_t* entries;
   const float4* wall4;  // (p2x, p2y, q2x, q2y) per wall, packed by the grid build
+  const uint4* cellrec; // two uint4 per cell: {start, count, w0, w1}, {w2, w3, w4, w5}: the list range AND its first
+                        // entries in one 32-byte record, so the common short list costs one dependent load less
   const float4* wallr;  // pre-test records, two float4 per wall: (min x, min y, max x, max y) of the wall and its
                         // unit-normal line (a, b, c, line band): a x + b y + c = signed distance to the wall's line
   const WState* st;
@@ -121,22 +123,30 @@ __device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, bool fal
   const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
   if (inside && !fallback) {
     const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
-    const uint32_t e0 = v.start[cell], e1 = v.start[cell + 1];
-    for (uint32_t e = e0; e < e1; e += 4) {  // four independent (index -> records) load chains in flight
-      int w[4];
-      float4 bb[4], ln[4];
+    const uint4 c0 = __ldg(v.cellrec + 2 * (int64_t)cell), c1 = __ldg(v.cellrec + 2 * (int64_t)cell + 1);
+    const uint32_t e0 = c0.x, n_list = c0.y;
+    // two walls per trip: their pre-test records (32 KB for 1,000 walls) live in L1, so deeper batches only cost
+    // registers; the first six indices came with the cell record, longer lists continue in entries[]
+    for (uint32_t u0 = 0; u0 < n_list; u0 += 2) {
+      int w[2];
+      if (u0 == 0) { w[0] = (int)c0.z; w[1] = (int)c0.w; }
+      else if (u0 == 2) { w[0] = (int)c1.x; w[1] = (int)c1.y; }
+      else if (u0 == 4) { w[0] = (int)c1.z; w[1] = (int)c1.w; }
+      else {
+        w[0] = v.entries[e0 + u0];
+        w[1] = v.entries[e0 + min(u0 + 1, n_list - 1)];
+      }
+      float4 bb[2], ln[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = v.entries[min(e + u, e1 - 1)];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const float4* __restrict__ r = v.wallr + 2 * (int64_t)w[u];
-        bb[u] = r[0];
-        ln[u] = r[1];
+        bb[u] = __ldg(r);
+        ln[u] = __ldg(r + 1);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (e + u >= e1 || walls_pretest_skip(rb, bb[u], ln[u], p1x, p1y)) continue;
-        const float4 wl = v.wall4[w[u]];
+      for (int u = 0; u < 2; ++u) {
+        if (u0 + u >= n_list || walls_pretest_skip(rb, bb[u], ln[u], p1x, p1y)) continue;
+        const float4 wl = __ldg(v.wall4 + w[u]);
         test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, w[u], best, bidx);
       }
     }
