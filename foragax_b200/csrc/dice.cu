@@ -22,18 +22,42 @@ __global__ void __launch_bounds__(256) dice_create_kernel(int64_t n, int32_t sid
   }
 }
 
-// Dice.step_agent under vmap (README.md:55-71); lax.cond(active_state) == (active != 0)
+// Dice.step_agent under vmap (README.md:55-71); lax.cond(active_state) == (active != 0).
+// The body is ~460 integer instructions of threefry per active slot behind three dependent loads (flag -> key, age):
+// left alone, a quarter of every warp's time went to waiting for them (ncu: long-scoreboard stalls on exactly those
+// three consumers).  The grid-stride loop is therefore software-pipelined: the flag is loaded two iterations ahead,
+// key and age one iteration ahead, and the six blocks of the current slot hide both.
 __global__ void __launch_bounds__(256) dice_step_kernel(int64_t n, int32_t sides, const float* __restrict__ active,
                                                         int32_t* __restrict__ draw, uint2* __restrict__ key,
                                                         float* __restrict__ age) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (active[i] != 0.0f) {
-      const uint2 kk = key[i];
-      Key k0, sub;
-      split2(Key{kk.x, kk.y}, k0, sub);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // prologue: flag of iterations 0 and 1, key / age of iteration 0
+  float a0 = i < n ? __ldg(active + i) : 0.0f;
+  float a1 = i + stride < n ? __ldg(active + i + stride) : 0.0f;
+  uint2 k0 = make_uint2(0u, 0u);
+  float g0 = 0.0f;
+  if (a0 != 0.0f) {
+    k0 = key[i];
+    g0 = age[i];
+  }
+  for (; i < n; i += stride) {
+    const float a_cur = a0;
+    const uint2 kk = k0;
+    const float ag = g0;
+    // advance the pipeline: key / age of the next slot (its flag is already here), flag of the one after
+    a0 = a1;
+    if (a0 != 0.0f) {
+      k0 = key[i + stride];
+      g0 = age[i + stride];
+    }
+    a1 = i + 2 * stride < n ? __ldg(active + i + 2 * stride) : 0.0f;
+    if (a_cur != 0.0f) {
+      Key k_unused, sub;
+      split2(Key{kk.x, kk.y}, k_unused, sub);
       draw[i] = randint1(sub, 1, sides + 1);
       key[i] = make_uint2(sub.a, sub.b);
-      age[i] = __fadd_rn(age[i], 1.0f);
+      age[i] = __fadd_rn(ag, 1.0f);
     }
   }
 }

@@ -137,13 +137,16 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
                         const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
-                        float* __restrict__ actions_out, int slots, const SenseArgs sense) {
+                        float* __restrict__ actions_out, int slots_flags, const SenseArgs sense) {
   // actions_out != nullptr: policy-only mode (WilsonCowan.step_policy on its own): obs has all n_obs
   // columns, actions are written out and the Forager physics is skipped.
   // slots == 2: each warp owns two weight slots -- while it computes agent i from one, the TMA copies
   // of its next active agent land in the other (mbarrier per slot).  slots == 1: one slot per warp and
   // twice the warps per SM; the copies of the other warps overlap this warp's compute.
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int slots = slots_flags & 0xff;
+  const bool stream_weights = (slots_flags >> 8) & 1;  // weights are read once per launch: L2 evict-first
+  const uint64_t l2pol = l2_policy_evict_first();
   const int n = NN ? NN : p.n_neurons, nobs = NOBS ? NOBS : p.n_obs, nact = NACT ? NACT : p.n_act;
   const WcLayout L = wc_layout(n, nobs, nact);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,11 +181,19 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     const float* gO = obs_in + a * obs_cols;
     if (lane == 0 && tx) {
       mbar_expect_tx(bar, tx);
-      if (bJ) tma_bulk_g2s(sm + L.J, gJ, bJ, bar);
-      if (bE) tma_bulk_g2s(sm + L.E, gE, bE, bar);
-      if (bD) tma_bulk_g2s(sm + L.D, gD, bD, bar);
-      if (bT) tma_bulk_g2s(sm + L.tau, gT, bT, bar);
-      if (bB) tma_bulk_g2s(sm + L.B, gB, bB, bar);
+      if (stream_weights) {
+        if (bJ) tma_bulk_g2s_hint(sm + L.J, gJ, bJ, bar, l2pol);
+        if (bE) tma_bulk_g2s_hint(sm + L.E, gE, bE, bar, l2pol);
+        if (bD) tma_bulk_g2s_hint(sm + L.D, gD, bD, bar, l2pol);
+        if (bT) tma_bulk_g2s_hint(sm + L.tau, gT, bT, bar, l2pol);
+        if (bB) tma_bulk_g2s_hint(sm + L.B, gB, bB, bar, l2pol);
+      } else {
+        if (bJ) tma_bulk_g2s(sm + L.J, gJ, bJ, bar);
+        if (bE) tma_bulk_g2s(sm + L.E, gE, bE, bar);
+        if (bD) tma_bulk_g2s(sm + L.D, gD, bD, bar);
+        if (bT) tma_bulk_g2s(sm + L.tau, gT, bT, bar);
+        if (bB) tma_bulk_g2s(sm + L.B, gB, bB, bar);
+      }
       if (bZ) tma_bulk_g2s(sm + L.Z, gZ, bZ, bar);
       if (bO) tma_bulk_g2s(sm + L.obs, gO, bO, bar);
     }
@@ -551,8 +562,10 @@ static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div(n, warps);
   const int64_t cap = (int64_t)sm_count() * per_sm;
+  // FGX_K2_EVICT_FIRST=0 switches the L2 evict-first hint of the weight copies off (A/B hook, see profiles/)
+  static const int evict_first = [] { const char* v = getenv("FGX_K2_EVICT_FIRST"); return v && atoi(v) == 0 ? 0 : 1; }();
   kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
-                                                              slots, sense);
+                                                              slots | (evict_first << 8), sense);
   return check_launch(what);
 }
 

@@ -34,4 +34,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// the same with an L2 eviction hint: data that is read exactly once per launch (the per-agent policy weights of the
+// step kernel, 11.6 GB per tick at C4) is marked evict-first so that it does not push the small re-used tables of
+// the neighbouring kernels (the wall grid of the ray cast) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 }  // namespace fgx
