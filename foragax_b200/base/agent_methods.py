@@ -11,7 +11,15 @@ Where the reference runs a serial ``lax.fori_loop`` over a per-agent callback
 (``agent_methods.py:29-35,43-49,55-61``) the native op processes all ``k`` rows in one
 launch; it receives the rows as a :class:`RowRange` / :class:`RowIds` instead of one
 ``idx`` at a time.  Rows touched by one call are distinct (they come from a permutation),
-so the parallel result equals the serial one.
+so the parallel result equals the serial one -- with ONE precondition for ``add_agents`` with an
+add function that copies from parent rows (``Forager.add_agent`` / ``Resource.add_agent``,
+``sim.py:158,320``): every parent slot ``good_ids[j]`` must lie BELOW the first new slot
+``a = sum(active_state)``.  The reference's serial loop would let a later child copy a row an
+earlier iteration already overwrote; the parallel kernels read parents while other lanes write
+children, so a parent inside ``[a, a + k)`` is a data race here.  The shipped examples meet it
+by construction (parents are selected among the actives, which the preceding descending sort
+packs below ``a``); ``check_add_parents`` verifies it on demand (host sync; ``FGX_CHECK_ADD=1``
+makes the example add functions call it).
 
 Buffers are updated in place where the reference would return an updated copy (the usual
 ``set.agents = step_agents(..., set)`` pattern drops the old value); ``sort_agents``
@@ -81,6 +89,18 @@ def count_active(agents):
     out = torch.empty(1, dtype=torch.int32, device=a.device)
     L.check(L.lib.fgx_count_active(L.ptr(a), a.shape[0], L.ptr(out), L.stream()))
     return out
+
+
+def check_add_parents(good_ids, rows):
+    """Raises unless every parent of an ``add_agents`` call lies below the first new row (see the module
+    docstring).  Reads three scalars back: debugging aid, not for the hot path."""
+    a, k = int(rows.start.reshape(-1)[0]), int(rows.count.reshape(-1)[0])
+    if k <= 0:
+        return
+    worst = int(good_ids.reshape(-1)[:k].max())
+    if worst >= a:
+        raise L.FgxError(f"add_agents: parent slot {worst} lies inside the new rows [{a}, {a + k}): the parallel add "
+                         "would race where the reference's serial loop re-reads an overwritten row")
 
 
 def count_active_clip(agents, num_agents_add):

@@ -8,6 +8,7 @@ traced JAX code.  Here a ``select_func`` returns either
   comparisons, combined through a 16-entry truth table), or
 * an already-materialised mask tensor (bool / int32 / float32; non-zero = selected).
 """
+import math
 import struct as _struct
 
 import torch
@@ -59,13 +60,17 @@ class Pred:
                 raise L.FgxError("predicate leaf size is not a multiple of the number of slots")
             keep.append(x)
             code = L.dtype_code(x)
+            op, c = t.op, t.imm
+            if isinstance(c, torch.Tensor):
+                raise L.FgxError("a predicate immediate must be a Python scalar (a tensor would force a host sync)")
             if code == L.FGX_F32:
-                imm = _struct.unpack("<I", _struct.pack("<f", float(t.imm)))[0]
+                imm = _struct.unpack("<I", _struct.pack("<f", float(c)))[0]
             else:
-                imm = int(t.imm) & 0xFFFFFFFF
+                op, c = _int_compare(op, c)
+                imm = int(c) & 0xFFFFFFFF
             p.term[k].data = L.ptr(x)
             p.term[k].dtype = code
-            p.term[k].op = t.op
+            p.term[k].op = op
             p.term[k].imm_bits = imm
             p.term[k].stride = x.numel() // n
         lut = 0
@@ -76,6 +81,29 @@ class Pred:
         # replicate over the unused high term bits (they are always 0 in-kernel, but keep it total)
         p.lut = lut
         return p, keep
+
+
+_I32_MIN = -(1 << 31)
+
+
+def _int_compare(op, c):
+    """``int_leaf <op> c`` for a possibly non-integral immediate, as an integer comparison with the same truth
+    table.  JAX promotes the integer leaf and compares in floating point (``x > 0.5`` is ``x >= 1``, not
+    ``x > 0``); truncating the immediate would silently select different agents."""
+    if op == L.OP_NONZERO or float(c) == math.floor(float(c)):
+        return op, int(c)
+    lo, hi = math.floor(c), math.ceil(c)
+    if op == L.OP_GT:
+        return L.OP_GT, lo          # x > 2.5  <=>  x > 2
+    if op == L.OP_GE:
+        return L.OP_GE, hi          # x >= 2.5 <=>  x >= 3
+    if op == L.OP_LT:
+        return L.OP_LT, hi          # x < 2.5  <=>  x < 3
+    if op == L.OP_LE:
+        return L.OP_LE, lo          # x <= 2.5 <=>  x <= 2
+    if op == L.OP_EQ:
+        return L.OP_LT, _I32_MIN    # never
+    return L.OP_GE, _I32_MIN        # OP_NE: always
 
 
 class P:

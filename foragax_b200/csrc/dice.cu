@@ -27,9 +27,9 @@ __global__ void __launch_bounds__(256) dice_create_kernel(int64_t n, int32_t sid
 // left alone, a quarter of every warp's time went to waiting for them (ncu: long-scoreboard stalls on exactly those
 // three consumers).  The grid-stride loop is therefore software-pipelined: the flag is loaded two iterations ahead,
 // key and age one iteration ahead, and the six blocks of the current slot hide both.
-__global__ void __launch_bounds__(256) dice_step_kernel(int64_t n, int32_t sides, const float* __restrict__ active,
-                                                        int32_t* __restrict__ draw, uint2* __restrict__ key,
-                                                        float* __restrict__ age) {
+__global__ void __launch_bounds__(256) dice_step_kernel(int64_t n, const RandintPlan plan,
+                                                        const float* __restrict__ active, int32_t* __restrict__ draw,
+                                                        uint2* __restrict__ key, float* __restrict__ age) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // prologue: flag of iterations 0 and 1, key / age of iteration 0
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) dice_step_kernel(int64_t n, int32_t sides
     if (a_cur != 0.0f) {
       Key k_unused, sub;
       split2(Key{kk.x, kk.y}, k_unused, sub);
-      draw[i] = randint1(sub, 1, sides + 1);
+      draw[i] = randint1_plan(sub, plan);  // randint(subkey, (1,), 1, sides + 1)
       key[i] = make_uint2(sub.a, sub.b);
       age[i] = __fadd_rn(ag, 1.0f);
     }
@@ -117,7 +117,7 @@ int fgx_dice_step(int64_t n, int32_t sides, const float* active_state, int32_t* 
   if (n == 0) return FGX_OK;
   FGX_REQUIRE(active_state && draw && key && age, "fgx_dice_step: null leaf");
   const int grid = fgx::grid_for(n, 256, 8);
-  fgx::dice_step_kernel<<<grid, 256, 0, fgx::as_stream(stream)>>>(n, sides, active_state, draw,
+  fgx::dice_step_kernel<<<grid, 256, 0, fgx::as_stream(stream)>>>(n, fgx::randint_plan(1, sides + 1), active_state, draw,
                                                                  reinterpret_cast<uint2*>(key), age);
   return fgx::check_launch("fgx_dice_step");
 }

@@ -20,12 +20,11 @@ struct Key {
 
 __host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 
-// Pipe balance on sm_100a: a round is add / rotate / xor.  ptxas puts the add on the FMA pipe (IMAD.IADD) and
-// rotate (SHF) + xor (LOP3) on the ALU pipe, which then bounds the block at 2 issue slots of 2 cycles per round
-// (each pipe issues one warp instruction per 2 cycles per scheduler).  Every other round therefore rotates with a
-// wide multiply instead: the 64-bit product x * 2^r holds x << r in its low word and x >> (32 - r) in its high
-// word (IMAD.WIDE.U32, FMA pipe), and ONE LOP3 computes (hi | lo) ^ x0.  Same bits, ~20 % fewer ALU-pipe
-// instructions (96 -> 76 per pair of blocks); the Dice step, which is nothing but threefry, is bound by that pipe.
+// Rotate = SHF (funnel shift).  A variant that rotates with a wide multiply on the FMA pipe in every other round
+// (x * 2^r: low word = x << r, high word = x >> (32 - r), one LOP3 for (hi | lo) ^ x0) was measured and REJECTED:
+// scripts/micro/threefry_pipes.cu, 4.75 M threads x 6 blocks on a B200: SHF 0.079 ms, every other round wide
+// 0.083 ms, all rounds wide 0.096 ms (profiles/r02_threefry_pipes.json) -- IMAD.WIDE.U32 costs more issue slots
+// than the SHF it replaces.
 __host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
   const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
   x0 += k0;
@@ -34,29 +33,17 @@ __host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, 
   x0 += x1;         \
   x1 = rotl32(x1, r); \
   x1 ^= x0;
-#ifdef __CUDA_ARCH__
-#define FGX_TF_W(r)                                                                   \
-  x0 += x1;                                                                           \
-  {                                                                                   \
-    unsigned long long w_;                                                            \
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(w_) : "r"(x1), "r"(1u << (r)));             \
-    x1 = ((uint32_t)(w_ >> 32) | (uint32_t)w_) ^ x0;                                  \
-  }
-#else
-#define FGX_TF_W(r) FGX_TF_R(r)
-#endif
-  FGX_TF_R(13) FGX_TF_W(15) FGX_TF_R(26) FGX_TF_W(6)
+  FGX_TF_R(13) FGX_TF_R(15) FGX_TF_R(26) FGX_TF_R(6)
   x0 += k1; x1 += k2 + 1u;
-  FGX_TF_R(17) FGX_TF_W(29) FGX_TF_R(16) FGX_TF_W(24)
+  FGX_TF_R(17) FGX_TF_R(29) FGX_TF_R(16) FGX_TF_R(24)
   x0 += k2; x1 += k0 + 2u;
-  FGX_TF_R(13) FGX_TF_W(15) FGX_TF_R(26) FGX_TF_W(6)
+  FGX_TF_R(13) FGX_TF_R(15) FGX_TF_R(26) FGX_TF_R(6)
   x0 += k0; x1 += k1 + 3u;
-  FGX_TF_R(17) FGX_TF_W(29) FGX_TF_R(16) FGX_TF_W(24)
+  FGX_TF_R(17) FGX_TF_R(29) FGX_TF_R(16) FGX_TF_R(24)
   x0 += k1; x1 += k2 + 4u;
-  FGX_TF_R(13) FGX_TF_W(15) FGX_TF_R(26) FGX_TF_W(6)
+  FGX_TF_R(13) FGX_TF_R(15) FGX_TF_R(26) FGX_TF_R(6)
   x0 += k2; x1 += k0 + 5u;
 #undef FGX_TF_R
-#undef FGX_TF_W
 }
 
 // element j of bits(key, n)
@@ -122,6 +109,41 @@ __host__ __device__ __forceinline__ int32_t randint_from_bits(uint32_t hb, uint3
   off %= span;
   return (int32_t)((uint32_t)lo + off);
 }
+
+// The same map for a span that is fixed for a whole launch (a die's number of sides): the five `% span` of
+// jax.random.randint cost ~20 instructions each as run-time divisions; with the host-side constants of
+// RandintPlan each becomes a multiply-high, a multiply-subtract and one conditional correction.  Exact:
+// magic = floor(2^32 / span) (saturated), so q = umulhi(x, magic) is the true quotient or one less, and
+// x - q * span lies in [0, 2 span).
+struct RandintPlan {
+  uint32_t span, magic, mult;  // mult = ((2^16 % span)^2) % span
+  int32_t lo;
+};
+__host__ __forceinline__ RandintPlan randint_plan(int32_t lo, int32_t hi) {
+  RandintPlan p;
+  p.span = hi > lo ? (uint32_t)hi - (uint32_t)lo : 1u;
+  const uint64_t q = (1ull << 32) / p.span;
+  p.magic = q > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)q;
+  const uint32_t m = 65536u % p.span;
+  p.mult = (uint32_t)(((uint64_t)m * m) % p.span);
+  p.lo = lo;
+  return p;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t mod_plan(uint32_t x, const RandintPlan& p) {
+  const uint32_t r = x - __umulhi(x, p.magic) * p.span;
+  return r >= p.span ? r - p.span : r;
+}
+__device__ __forceinline__ int32_t randint_from_bits_plan(uint32_t hb, uint32_t lb, const RandintPlan& p) {
+  const uint32_t off = mod_plan(mod_plan(hb, p) * p.mult + mod_plan(lb, p), p);  // uint32 wrap-around as in jax
+  return (int32_t)((uint32_t)p.lo + off);
+}
+__device__ __forceinline__ int32_t randint1_plan(Key k, const RandintPlan& p) {
+  Key k1, k2;
+  split2(k, k1, k2);
+  return randint_from_bits_plan(bits1(k1), bits1(k2), p);
+}
+#endif
 
 // randint(key, (1,), lo, hi)
 __host__ __device__ __forceinline__ int32_t randint1(Key k, int32_t lo, int32_t hi) {

@@ -35,6 +35,42 @@ def shard_bounds(n_total, world_size=None, rank=None):
     return rank * n_total // world_size, (rank + 1) * n_total // world_size
 
 
+def row_leaf_mask(agents, n_local, row_mask=None):
+    """Which leaves of an agent pytree are ROW leaves (slot axis first, one row per local slot) and therefore move
+    when rows are exchanged.  Default: every tensor leaf whose leading dimension equals the shard size -- which can
+    misfire for a replicated table that happens to have that many rows (a per-wall or parameter table; with ragged
+    shards the coincidence may even differ between ranks), so callers holding such leaves pass ``row_mask`` (one
+    bool per leaf, tree order) and :func:`check_row_leaves_agree` verifies that all ranks made the same choice."""
+    from . import struct
+    leaves = struct.tree_leaves(agents)
+    if row_mask is not None:
+        mask = [bool(m) for m in row_mask]
+        if len(mask) != len(leaves):
+            raise ValueError(f"row_mask has {len(mask)} entries for {len(leaves)} leaves")
+        for m, x in zip(mask, leaves):
+            if m and not (isinstance(x, torch.Tensor) and x.dim() > 0 and x.shape[0] == n_local):
+                raise ValueError("row_mask marks a leaf whose leading dimension is not the shard size")
+        return mask
+    return [isinstance(x, torch.Tensor) and x.dim() > 0 and x.shape[0] == n_local for x in leaves]
+
+
+def check_row_leaves_agree(mask, device):
+    """All ranks must treat the same leaves as rows, otherwise the per-leaf collectives mismatch (or silently
+    permute a replicated table on some ranks only).  One tiny all-gather; raises on disagreement."""
+    r, w = world()
+    if w == 1:
+        return
+    code = 0
+    for k, m in enumerate(mask):
+        code = (code * 3 + (2 if m else 1) * (k + 1)) % ((1 << 61) - 1)
+    mine = torch.tensor([len(mask), code], dtype=torch.int64, device=device)
+    allc = torch.empty(2 * w, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine)
+    allc = allc.view(w, 2)
+    if not bool((allc == allc[0]).all()):
+        raise RuntimeError("ranks disagree on which agent leaves are row leaves; pass an explicit row_mask")
+
+
 def all_gather_counts(local_count):
     """int32/int64 scalar tensor per rank -> int64[world] (same device / backend as the input)."""
     r, w = world()
@@ -155,7 +191,7 @@ def plan_pack_splits(active_counts, shard_sizes):
     return splits
 
 
-def global_pack_active(agents, sort_active, n_active_local=None):
+def global_pack_active(agents, sort_active, n_active_local=None, row_mask=None):
     """``sort_agents(quantity=active_state, ascend=False)`` of a set sharded in contiguous blocks: returns
     this rank's block of the globally sorted set (bit-identical to slicing the single-GPU result).
 
@@ -178,9 +214,12 @@ def global_pack_active(agents, sort_active, n_active_local=None):
     send = splits[r]
     recv = [splits[s_rank][r] for s_rank in range(w)]
     assert sum(recv) == n_local and sum(send) == n_local
+    mask = row_leaf_mask(agents, n_local, row_mask)
+    check_row_leaves_agree(mask, agents.active_state.device)
+    is_row = iter(mask)
 
     def exchange(leaf):
-        if not isinstance(leaf, torch.Tensor) or leaf.dim() == 0 or leaf.shape[0] != n_local:
+        if not next(is_row):
             return leaf
         src = leaf.contiguous()
         row = 1

@@ -9,6 +9,8 @@ functions; ``use_variant('nb')`` switches to the values of the notebook twin ``s
 that produced golden vector G2).  Recording / orbax checkpointing of the reference driver is
 visualisation I/O and is not part of the hot path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -21,6 +23,8 @@ from ..base.agent_methods import (count_active, create_agents, jit_add_agents, j
                                   jit_select_agents, jit_set_agents, jit_sort_agents, step_agents)
 from ..base.predicates import P
 from ..base.space_methods import create_space
+
+_CHECK_ADD = os.environ.get("FGX_CHECK_ADD", "0") == "1"  # verify add_agents' "parents below the new rows" precondition
 from ..policy.wilson_cowan import wc_struct
 
 f32 = np.float32
@@ -190,6 +194,9 @@ class Forager(Agent):
         n = foragers.unique_id.shape[0]
         ps = _policy_shape(foragers)
         good_ids = params.content['good_ids']
+        if _CHECK_ADD:
+            from ..base.agent_methods import check_add_parents
+            check_add_parents(good_ids, rows)
         key_out = torch.empty_like(key)
         chain = torch.empty((n, 2), dtype=torch.uint32, device=key.device)
         L.check(L.lib.fgx_forager_add(n, ps['num_neurons'], ps['num_obs'], ps['num_actions'], L.ptr(good_ids),
@@ -265,6 +272,9 @@ class Resource(Agent):
     def add_agent(params, ress, rows, key):
         n = ress.unique_id.shape[0]
         c = ress.params.content
+        if _CHECK_ADD:
+            from ..base.agent_methods import check_add_parents
+            check_add_parents(params.content['good_ids'], rows)
         key_out = torch.empty_like(key)
         chain = torch.empty((n, 2), dtype=torch.uint32, device=key.device)
         L.check(L.lib.fgx_resource_add(n, float(c['x_min']), float(c['x_max']), float(c['y_min']), float(c['y_max']),

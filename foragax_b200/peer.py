@@ -26,7 +26,9 @@ from .base.predicates import P
 
 
 class PeerPackedSet:
-    def __init__(self, agents, group=None):
+    def __init__(self, agents, group=None, row_mask=None):
+        """``row_mask`` (optional, one bool per leaf in tree order): which leaves are row leaves; default = every
+        tensor whose leading dimension is the shard size (see ``distributed.row_leaf_mask``)."""
         import torch.distributed._symmetric_memory as symm
         self.group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -42,7 +44,9 @@ class PeerPackedSet:
         self.n_max = max(self.bounds[i + 1] - self.bounds[i] for i in range(self.world))
         self._template = agents
         leaves = struct.tree_leaves(agents)
-        self._is_row = [x.dim() > 0 and x.shape[0] == self.n_local for x in leaves]
+        from .distributed import check_row_leaves_agree, row_leaf_mask
+        self._is_row = row_leaf_mask(agents, self.n_local, row_mask)
+        check_row_leaves_agree(self._is_row, dev)
         # one symmetric allocation per buffer set; every rank uses the layout of the LARGEST shard so that a
         # leaf sits at the same offset on every rank
         self._offsets, off = [], 0
