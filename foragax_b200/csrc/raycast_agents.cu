@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "geometry.cuh"
 
+#include "scan.cuh"
+
 namespace fgx {
 
 constexpr int RA_BLOCK = 256;
@@ -65,67 +67,6 @@ __global__ void __launch_bounds__(256) grid_count_kernel(GridDesc g, const float
     const int c = cell_of(g, x[i * stride], y[i * stride]);
     cell[i] = c;
     atomicAdd(count + c, 1u);
-  }
-}
-
-// single CTA: exclusive scans of the target counts and the agent counts over the cells (8 consecutive
-// cells per thread, so a 300 x 300 grid takes 11 trips); resets the counts, which double as scatter cursors
-constexpr int GS_ITEMS = 8;
-
-__global__ void __launch_bounds__(1024) grid_scan_kernel(int n_cells, uint32_t* __restrict__ tcount,
-                                                         uint32_t* __restrict__ acount, uint32_t* __restrict__ tstart,
-                                                         uint32_t* __restrict__ astart) {
-  __shared__ uint32_t carry[2];
-  __shared__ uint32_t wsum[2][32];
-  if (threadIdx.x < 2) carry[threadIdx.x] = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  uint32_t* const counts[2] = {tcount, acount};
-  uint32_t* const starts[2] = {tstart, astart};
-  for (int base = 0; base < n_cells; base += 1024 * GS_ITEMS) {
-    const int c0 = base + threadIdx.x * GS_ITEMS;
-    uint32_t v[2][GS_ITEMS], tot[2], inc[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      tot[k] = 0;
-#pragma unroll
-      for (int j = 0; j < GS_ITEMS; ++j) {
-        v[k][j] = c0 + j < n_cells ? counts[k][c0 + j] : 0u;
-        tot[k] += v[k][j];
-      }
-      inc[k] = tot[k];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc[k], d);
-        if (l >= d) inc[k] += o;
-      }
-      if (l == 31) wsum[k][w] = inc[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      uint32_t run = carry[k] + inc[k] - tot[k];
-      for (int q = 0; q < w; ++q) run += wsum[k][q];
-#pragma unroll
-      for (int j = 0; j < GS_ITEMS; ++j) {
-        if (c0 + j < n_cells) {
-          starts[k][c0 + j] = run;
-          counts[k][c0 + j] = 0;
-        }
-        run += v[k][j];
-      }
-      inc[k] = run;  // inclusive total up to and including this thread
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) {
-      carry[0] = inc[0];
-      carry[1] = inc[1];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    tstart[n_cells] = carry[0];
-    astart[n_cells] = carry[1];
   }
 }
 
@@ -436,7 +377,7 @@ __global__ void __launch_bounds__(RA_BLOCK, RA_MINB) raycast_agents_kernel(const
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct RaScratch {
-  uint32_t *tcount, *acount, *tstart, *astart;
+  uint32_t *tcount, *acount, *tstart, *astart, *partial;
   int32_t *tcell, *acell, *order, *tidx;
   SensorRec* rec;
   float4* sorted;
@@ -455,6 +396,7 @@ static size_t carve(char* base, int64_t n, int64_t m, int n_cells, RaScratch* s)
   p = take((size_t)m * 4); if (s) s->tidx = (int32_t*)p;
   p = take((size_t)m * 16); if (s) s->sorted = (float4*)p;
   p = take((size_t)n * 16); if (s) s->rec = (SensorRec*)p;
+  p = take(coop_scan_scratch_bytes(2)); if (s) s->partial = (uint32_t*)p;
   return o;
 }
 
@@ -518,7 +460,11 @@ int fgx_raycast_agents(const float* x, const float* y, const float* ang, const f
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_raycast_agents: %s", cudaGetErrorString(e));
   if (n_targets) grid_count_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(g, tx, ty, tactive, target_stride, n_targets, s.tcell, s.tcount);
   grid_count_kernel<<<grid_for(n_agents, 256, 8), 256, 0, st>>>(g, x, y, nullptr, 1, n_agents, s.acell, s.acount);
-  grid_scan_kernel<<<1, 1024, 0, st>>>(n_cells, s.tcount, s.acount, s.tstart, s.astart);
+  {  // exclusive scans of both histograms in one cooperative launch (counts are reset: they become the cursors)
+    const int rc = launch_coop_scan<2>("fgx_raycast_agents", n_cells, ScanJob{s.tcount, s.tstart}, ScanJob{s.acount, s.astart},
+                                       s.partial, nullptr, 0u, nullptr, st);
+    if (rc != FGX_OK) return rc;
+  }
   if (n_targets)
     grid_scatter_targets_kernel<<<grid_for(n_targets, 256, 8), 256, 0, st>>>(tx, ty, trad, tactive, target_stride,
                                                                              n_targets, s.tcell, s.tstart, s.tcount,

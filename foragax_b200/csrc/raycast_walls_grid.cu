@@ -25,6 +25,7 @@
 //      list (broadcast loads, wall data L1-resident) and test their own ray.
 // Agents outside the grid bounds, walls with coordinates beyond the declared scale and list overflow
 // fall back to the all-walls loop for the affected agents / launch (exact, just slower).
+#include "scan.cuh"
 #include "walls_grid.cuh"
 
 namespace fgx {
@@ -87,52 +88,6 @@ __global__ void __launch_bounds__(128) wall_count_kernel(WGrid g, const float* _
       continue;
     }
     wall_column_cells(g, ax, ay, bx, by, cu, [&](int cell) { atomicAdd(count + cell, 1u); });
-  }
-}
-
-// single CTA exclusive scan (cells <= ~100k); the counts become the fill cursors (reset to 0)
-__global__ void __launch_bounds__(1024) wall_scan_kernel(int n_cells, uint32_t capacity, uint32_t* __restrict__ count,
-                                                         uint32_t* __restrict__ start, WState* __restrict__ st) {
-  __shared__ uint32_t carry;
-  __shared__ uint32_t wsum[32];
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  constexpr int ITEMS = 8;
-  for (int base = 0; base < n_cells; base += 1024 * ITEMS) {
-    const int c0 = base + threadIdx.x * ITEMS;
-    uint32_t v[ITEMS], tot = 0;
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      v[j] = c0 + j < n_cells ? count[c0 + j] : 0u;
-      tot += v[j];
-    }
-    uint32_t inc = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (l >= d) inc += o;
-    }
-    if (l == 31) wsum[w] = inc;
-    __syncthreads();
-    uint32_t run = carry + inc - tot;
-    for (int q = 0; q < w; ++q) run += wsum[q];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      if (c0 + j < n_cells) {
-        start[c0 + j] = run;
-        count[c0 + j] = 0;
-      }
-      run += v[j];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = run;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    start[n_cells] = carry;
-    st->total = carry;
-    if (carry > capacity) st->fallback = 1;
   }
 }
 
@@ -331,7 +286,7 @@ size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float 
   WGrid g;
   if (n_walls < 0 || wgrid_dims(x_min, x_max, y_min, y_max, ray_length, &g)) return 0;
   const size_t cells = (size_t)g.gx * g.gy;
-  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al((cells + 1) * 32) +
+  return wg_al(sizeof(WState)) + 2 * wg_al((cells + 1) * 4) + wg_al(coop_scan_scratch_bytes(1)) + wg_al((cells + 1) * 32) +
          wg_al((size_t)n_walls * 16 + 16) + wg_al((size_t)n_walls * 32 + 16) + wg_al(wgrid_capacity(g, n_walls) * 4);
 }
 
@@ -354,6 +309,8 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
   p += wg_al(((size_t)n_cells + 1) * 4);
   uint32_t* start = reinterpret_cast<uint32_t*>(p);
   p += wg_al(((size_t)n_cells + 1) * 4);
+  uint32_t* partial = reinterpret_cast<uint32_t*>(p);
+  p += wg_al(coop_scan_scratch_bytes(1));
   uint4* cellrec = reinterpret_cast<uint4*>(p);
   p += wg_al(((size_t)n_cells + 1) * 32);
   float4* wall4 = reinterpret_cast<float4*>(p);
@@ -370,13 +327,19 @@ int wall_grid_prepare(const char* what, const float* wx1, const float* wy1, cons
     const int nmaj = g.gx > g.gy ? g.gx : g.gy;
     const dim3 wg((unsigned)ceil_div(nmaj, 128), (unsigned)(n_walls < 32768 ? n_walls : 32768));
     wall_count_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, count, wall4, wallr, st);
-    wall_scan_kernel<<<1, 1024, 0, s>>>(n_cells, (uint32_t)capacity, count, start, st);
+    {  // cooperative exclusive scan; the counts become the fill cursors (reset to 0); overflow -> exact fallback
+      const int rc = launch_coop_scan<1>(what, n_cells, ScanJob{count, start}, ScanJob{nullptr, nullptr}, partial,
+                                         &st->total, (uint32_t)capacity, &st->fallback, s);
+      if (rc != FGX_OK) return rc;
+    }
     wall_fill_kernel<<<wg, 128, 0, s>>>(g, wx1, wy1, wx2, wy2, (int)n_walls, start, count, entries, st);
     wall_cellrec_kernel<<<grid_for(n_cells, 256, 4), 256, 0, s>>>(n_cells, start, entries, cellrec, st);
   } else {
     // no walls: empty lists everywhere (start, cursors and cell records all zero)
     e = cudaMemsetAsync(scratch, 0,
-                        wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4) + wg_al(((size_t)n_cells + 1) * 32), s);
+                        wg_al(sizeof(WState)) + 2 * wg_al(((size_t)n_cells + 1) * 4) + wg_al(coop_scan_scratch_bytes(1)) +
+                            wg_al(((size_t)n_cells + 1) * 32),
+                        s);
     if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
   *view = WallsGridView{g, wx1, wy1, wx2, wy2, (int)n_walls, start, entries, wall4, cellrec, wallr, st};

@@ -131,6 +131,27 @@ __global__ void __launch_bounds__(256) count_active_kernel(const float* __restri
   }
 }
 
+// Recording ring (EcoEvoJax/sim.py:581-594 record_data: rec.<leaf>.at[frame].set(leaf) for eight leaves per frame):
+// every leaf's n rows are copied into slot (frame mod frames) of its [frames, n, ...] ring in ONE launch
+// (grid.y = leaf).  `frame` is a device scalar so that a recorded tick can live inside a CUDA graph.
+__global__ void __launch_bounds__(256) record_frame_kernel(const __grid_constant__ LeafTable tab, int64_t n, int32_t frames,
+                                                           const int32_t* __restrict__ frame) {
+  const fgx_leaf_t& lf = tab.leaf[blockIdx.y];
+  const int v = tab.vec[blockIdx.y];
+  int32_t f = __ldg(frame) % frames;
+  if (f < 0) f += frames;  // negative frames wrap like negative indices (jnp .at[])
+  const int64_t bytes = lf.row_bytes * n, chunks = bytes / v;
+  const char* __restrict__ src = reinterpret_cast<const char*>(lf.src);
+  char* __restrict__ dst = reinterpret_cast<char*>(lf.dst) + (int64_t)f * bytes;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
+    if (v == 16) reinterpret_cast<uint4*>(dst)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+    else if (v == 8) reinterpret_cast<uint2*>(dst)[c] = __ldg(reinterpret_cast<const uint2*>(src) + c);
+    else if (v == 4) reinterpret_cast<uint32_t*>(dst)[c] = __ldg(reinterpret_cast<const uint32_t*>(src) + c);
+    else if (v == 2) reinterpret_cast<uint16_t*>(dst)[c] = __ldg(reinterpret_cast<const uint16_t*>(src) + c);
+    else dst[c] = __ldg(src + c);
+  }
+}
+
 // create_agents' argument construction (agent_methods.py:10-15) for the slots
 // [first, first + n_local) of a set of n_total slots (a shard computes exactly its rows)
 __global__ void __launch_bounds__(256) create_base_kernel(Key root, int64_t n_total, int64_t n_active, int64_t first,
@@ -248,5 +269,31 @@ int fgx_create_base(const uint32_t key_host[2], int64_t n_total, int64_t n_activ
                     fgx_stream_t stream) {
   return fgx_create_base_shard(key_host, n_total, n_active, 0, 1, n_total, agent_type, unique_id, create_keys,
                                active_state, agent_types, stream);
+}
+
+int fgx_record_frame(const fgx_leaf_t* leaves_host, int32_t n_leaves, int64_t n, int32_t frames, const int32_t* frame,
+                     fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && frames >= 1, "fgx_record_frame: bad sizes");
+  FGX_REQUIRE(n_leaves >= 0 && n_leaves <= FGX_MAX_LEAVES, "fgx_record_frame: at most %d leaves per call", FGX_MAX_LEAVES);
+  if (n == 0 || n_leaves == 0) return FGX_OK;
+  FGX_REQUIRE(leaves_host && frame, "fgx_record_frame: null pointer");
+  LeafTable tab{};
+  int64_t most = 0;
+  for (int k = 0; k < n_leaves; ++k) {
+    const fgx_leaf_t& lf = leaves_host[k];
+    FGX_REQUIRE(lf.src && lf.dst && lf.row_bytes > 0, "fgx_record_frame: leaf %d is malformed", k);
+    tab.leaf[k] = lf;
+    // chunk width: every frame slot starts at a multiple of n * row_bytes from the ring base
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(lf.src) | reinterpret_cast<uintptr_t>(lf.dst) |
+                           (uintptr_t)(lf.row_bytes * n);
+    int v = 16;
+    while (v > 1 && (bits & (uintptr_t)(v - 1))) v >>= 1;
+    tab.vec[k] = v;
+    if (lf.row_bytes * n / v > most) most = lf.row_bytes * n / v;
+  }
+  dim3 grid(grid_for(most, 256, 4), n_leaves);
+  record_frame_kernel<<<grid, 256, 0, as_stream(stream)>>>(tab, n, frames, frame);
+  return check_launch("fgx_record_frame");
 }
 }

@@ -6,8 +6,8 @@ blossom), ``forager_resource_interaction``, ``sensor_model``, ``Neuroevolution``
 
 ``HYPER`` holds the module constants of ``sim.py:16-19`` and the constants scattered through its
 functions; ``use_variant('nb')`` switches to the values of the notebook twin ``sim.ipynb`` (the run
-that produced golden vector G2).  Recording / orbax checkpointing of the reference driver is
-visualisation I/O and is not part of the hot path.
+that produced golden vector G2).  The recording ring and its checkpoints (``sim.py:555-595,643-647,695-700``)
+are in ``foragax_b200/recording.py`` (a native ring-write kernel; orbax replaced by a small on-disk format).
 """
 import os
 
@@ -391,9 +391,9 @@ def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space,
 jit_Neuroevolution = Neuroevolution
 
 
-# sim.py:597-666 (without the recording / orbax part)
+# sim.py:597-701
 class Foraging_world:
-    def __init__(self, params: Params, key, steps, num_rec_frames=0):
+    def __init__(self, params: Params, key, steps, num_rec_frames=0, rec_dir='./rec_data'):
         self.sim_steps = steps
         space_params = params.content['space_params']
         forager_params = params.content['forager_params']
@@ -418,6 +418,14 @@ class Foraging_world:
         self.key, subkey = ks[0].contiguous(), ks[1].contiguous()
         self.resources_set.agents = create_agents(resources_create_params, self.resources_set, subkey)
         self.life_expectancy = torch.tensor(50.0, dtype=torch.float32, device=self.key.device)
+        # sim.py:640-647: the recording ring and its checkpoint manager (orbax in the reference; see recording.py)
+        self.num_rec_frames = int(num_rec_frames)
+        self.rec_data, self.checkpoint_manager = None, None
+        if self.num_rec_frames > 0:
+            from ..recording import CheckpointManager, init_rec_data
+            self.rec_data = init_rec_data(self.num_rec_frames, self.foragers_set, self.resources_set)
+            self.checkpoint_manager = CheckpointManager(rec_dir, max_to_keep=100, create=True)
+        self.sim_step = 0
 
     def step(self):
         dist_mat, energy_in, energy_out = jit_forager_resource_interaction(self.foragers_set.agents,
@@ -460,16 +468,56 @@ class Foraging_world:
         bind(state)
         return g
 
-    def run(self, print_freq=0):
+    def run(self, rec_start_frame=None, print_freq=0):
+        """sim.py:668-701: ``sim_steps`` ticks; from tick ``rec_start_frame`` on, ``num_rec_frames`` frames of
+        positions / headings / radii / blossoms are recorded into the ring and the full ring is checkpointed.
+        Returns the per-tick ``(num_active_foragers, num_active_resources, life_expectancy)`` device scalars."""
+        from ..recording import init_rec_data, jit_record_data
         out = []
-        for sim_step in range(self.sim_steps):
+        record_flag, record_frame = False, 0
+        average_life_expectancy = 0.0
+        for _ in range(self.sim_steps):
             nf, nr, le = self.step()
             out.append((nf, nr, le))
-            if print_freq and sim_step % print_freq == 0 and sim_step != 0:
-                print(sim_step)
-                print("num_active_foragers: ", int(nf))
-                print("num_active_resources: ", int(nr))
+            sim_step = self.sim_step
+            if print_freq:
+                average_life_expectancy += float(le)
+                if sim_step % print_freq == 0 and sim_step != 0:
+                    print(sim_step)
+                    print("num_active_foragers: ", int(nf))
+                    print("num_active_resources: ", int(nr))
+                    print("avg life_expectancy: ", average_life_expectancy / print_freq)
+                    average_life_expectancy = 0.0
+            self.sim_step = sim_step = sim_step + 1
+            if self.rec_data is not None and rec_start_frame is not None:
+                if sim_step == rec_start_frame:
+                    record_flag, record_frame = True, 0
+                    self.rec_data = init_rec_data(self.num_rec_frames, self.foragers_set, self.resources_set)
+                if record_flag:
+                    self.rec_data = jit_record_data(self.foragers_set.agents, self.resources_set.agents, self.rec_data,
+                                                    record_frame)
+                    record_frame += 1
+                    if record_frame == self.num_rec_frames:
+                        self.checkpoint_manager.save(sim_step, {'rec_data': self.rec_data})
+                        record_flag = False
         return out
+
+    def save_state(self, manager, step=None):
+        """Checkpoint of the simulation STATE (not in the reference, which cannot resume): both agent sets, the
+        world key, the life-expectancy average and the tick counter."""
+        from ..recording import save_state
+        step = self.sim_step if step is None else step
+        return save_state(manager, step, foragers=self.foragers_set.agents, resources=self.resources_set.agents,
+                          key=self.key, life_expectancy=self.life_expectancy, sim_step=int(self.sim_step))
+
+    def load_state(self, manager, step=None):
+        """Resume from :meth:`save_state`: the checkpointed leaves are copied into this world's buffers."""
+        from ..recording import load_state
+        template = {'foragers': self.foragers_set.agents, 'resources': self.resources_set.agents, 'key': self.key,
+                    'life_expectancy': self.life_expectancy}
+        step, scalars = load_state(manager, template, step)
+        self.sim_step = int(scalars.get('sim_step', step))
+        return step
 
 
 def default_params(variant='sim'):

@@ -169,6 +169,12 @@ int fgx_sort_key_images(const void* keys, int32_t key_dtype, int64_t n, int32_t 
 int fgx_sort_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, const int32_t* perm, int64_t n_local,
                        const uint32_t* images_all, int64_t n_pad, const int64_t* bounds_host, int32_t rank,
                        int32_t world, int64_t* gpos_scratch, fgx_stream_t stream);
+/* The recording ring of the example drivers (EcoEvoJax/sim.py:555-595 Rec_Data / record_data;
+ * wolf_sheep_grass/sim.ipynb:301-362): for every leaf, ring[frame mod frames] = leaf, i.e. the n rows at src are
+ * copied to dst + (frame mod frames) * n * row_bytes (dst = base of the [frames, n, ...] ring).  One launch for
+ * all leaves; *frame is a device int32 so that a recorded tick can be captured in a CUDA graph.               */
+int fgx_record_frame(const fgx_leaf_t* leaves_host, int32_t n_leaves, int64_t n, int32_t frames, const int32_t* frame,
+                     fgx_stream_t stream);
 /* jnp.sum(active_state, dtype=int32) (agent_methods.py:27): out int32[1] */
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream);
 /* the same count plus the caller's clip of hello_world.ipynb:138-139 / README.md:124-125 in one launch:

@@ -295,3 +295,61 @@ def test_bench_instantiation_forager_step_matches_oracle(cuda):
         for k in ofo.FSTATE:
             np.testing.assert_array_equal(got["state"][k][~on], before["state"][k][~on], err_msg=k)
     assert float((dist < bench.RAY_LEN).float().mean()) > 0.01  # the observations are not all "no hit"
+
+
+def test_recording_ring_and_checkpoint(cuda, tmp_path):
+    """Foraging_world.run with the recording ring (sim.py:555-595,668-701): frame f of the ring holds the positions
+    after tick rec_start_frame + f, the full ring is checkpointed once, and the ring write wraps like .at[frame]."""
+    from foragax_b200 import random as fgx_random
+    from foragax_b200.examples import foraging as fg
+    from foragax_b200.recording import CheckpointManager, init_rec_data, record_data
+    fg.use_variant("sim")
+    frames, start = 4, 3
+    w = fg.Foraging_world(fg.default_params("sim"), fgx_random.PRNGKey(1), 8, num_rec_frames=frames,
+                          rec_dir=str(tmp_path / "rec"))
+    w2 = fg.Foraging_world(fg.default_params("sim"), fgx_random.PRNGKey(1), 8)
+    w.run(rec_start_frame=start)
+    want = {k: [] for k in ("X", "Y", "ang", "rad")}
+    blossom = []
+    for t in range(1, 9):
+        w2.step()
+        if start <= t < start + frames:
+            for k in want:
+                want[k].append(w2.foragers_set.agents.state.content[k].clone())
+            blossom.append(w2.resources_set.agents.state.content["blossom"].reshape(-1).float().clone())
+    mgr = CheckpointManager(str(tmp_path / "rec"))
+    assert mgr.all_steps() == [start + frames - 1]
+    got = mgr.restore()
+    for k, name in (("X", "forager_xs"), ("Y", "forager_ys"), ("ang", "forager_angs"), ("rad", "forager_rads")):
+        assert torch.equal(got[f"rec_data.{name}"], torch.stack(want[k]).cpu()), name
+    assert torch.equal(got["rec_data.resource_blossoms"], torch.stack(blossom).cpu())
+    assert torch.equal(w.rec_data.forager_xs.cpu(), got["rec_data.forager_xs"])
+    # frame indices wrap (device scalar index, as inside a captured tick)
+    rec = init_rec_data(3, w.foragers_set, w.resources_set)
+    record_data(w.foragers_set.agents, w.resources_set.agents, rec, torch.tensor(4, dtype=torch.int32, device=cuda))
+    assert torch.equal(rec.forager_xs[1], w.foragers_set.agents.state.content["X"])
+    assert float(rec.forager_xs[0].abs().sum()) == 0.0 and float(rec.forager_xs[2].abs().sum()) == 0.0
+
+
+def test_state_checkpoint_resume_is_bit_exact(cuda, tmp_path):
+    """save_state after 6 ticks, 6 more ticks; a fresh world that loads the checkpoint and runs 6 ticks must hold
+    exactly the same leaves, key and counters (the reference has no resume)."""
+    from foragax_b200 import random as fgx_random
+    from foragax_b200 import struct
+    from foragax_b200.examples import foraging as fg
+    from foragax_b200.recording import CheckpointManager
+    fg.use_variant("nb")
+    mgr = CheckpointManager(str(tmp_path / "state"))
+    a = fg.Foraging_world(fg.default_params("nb"), fgx_random.PRNGKey(0), 6)
+    a.run()
+    a.save_state(mgr)
+    out_a = a.run()
+    b = fg.Foraging_world(fg.default_params("nb"), fgx_random.PRNGKey(5), 6)   # different seed: everything is overwritten
+    assert b.load_state(mgr) == 6 and b.sim_step == 6
+    out_b = b.run()
+    for x, y in zip(struct.tree_leaves(a.foragers_set.agents) + struct.tree_leaves(a.resources_set.agents),
+                    struct.tree_leaves(b.foragers_set.agents) + struct.tree_leaves(b.resources_set.agents)):
+        assert torch.equal(x, y)
+    assert torch.equal(a.key, b.key) and torch.equal(a.life_expectancy, b.life_expectancy)
+    assert [(int(f), int(r)) for f, r, _ in out_a] == [(int(f), int(r)) for f, r, _ in out_b]
+    assert [(int(f), int(r)) for f, r, _ in out_a] == [tuple(G2[t][:2]) for t in range(6, 12)]  # and they are G2's ticks
