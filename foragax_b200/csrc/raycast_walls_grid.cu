@@ -147,34 +147,26 @@ __global__ void __launch_bounds__(256, MINB) raycast_walls_grid_kernel(const Wal
   }
   const float L = a.L, span = a.span;
   const bool fallback = a.v.st->fallback != 0;  // written by the grid build (an earlier launch)
-  // two-deep software pipeline over the grid-stride loop: while (agent, ray) number i of this thread is processed,
-  // the pose of number i + 2 is being loaded and the cell record of number i + 1 (whose pose arrived during i - 1)
-  // is being pulled into L2 -- of the dependent chain pose -> cell record -> wall records -> end points only the
-  // L1-resident wall records stay on an agent's critical path
+  // software pipeline over the grid-stride loop: the pose of the NEXT (agent, ray) of this thread is loaded while
+  // the current one is processed, which takes the first of the dependent loads (pose -> cell record -> wall
+  // records -> end points) off every agent's critical path
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  auto load_pose = [&](uint32_t tt, float& pa, float& px, float& py, float& pang) {
-    if (tt < total) {
-      const uint32_t ag = tt / nr;
-      pa = a.aactive != nullptr ? __ldg(a.aactive + ag) : 1.0f;
-      px = __ldg(a.ax + ag); py = __ldg(a.ay + ag); pang = __ldg(a.aang + ag);
-    }
-  };
-  float c_act = 0.0f, c_x = 0.0f, c_y = 0.0f, c_ang = 0.0f;   // pose of iteration i
-  float n_act = 0.0f, n_x = 0.0f, n_y = 0.0f, n_ang = 0.0f;   // pose of iteration i + 1
-  load_pose(t, c_act, c_x, c_y, c_ang);
-  load_pose(t + stride, n_act, n_x, n_y, n_ang);
-  int cell = walls_grid_cell(a.v, c_x, c_y);
+  float n_act = 1.0f, n_x = 0.0f, n_y = 0.0f, n_ang = 0.0f;
+  if (t < total) {
+    const uint32_t ag = t / nr;
+    n_act = a.aactive != nullptr ? __ldg(a.aactive + ag) : 1.0f;
+    n_x = __ldg(a.ax + ag); n_y = __ldg(a.ay + ag); n_ang = __ldg(a.aang + ag);
+  }
   for (; t < total; t += stride) {
     const uint32_t agent = t / nr;
     const uint32_t j = t - agent * nr;
-    const float act = c_act, p1x = c_x, p1y = c_y, ang = c_ang;
-    const int cell_cur = cell;
-    // advance: i + 1 becomes current for the next trip; start its cell record towards L2, load the pose of i + 2
-    c_act = n_act; c_x = n_x; c_y = n_y; c_ang = n_ang;
-    cell = walls_grid_cell(a.v, c_x, c_y);
-    if (c_act != 0.0f && !fallback) walls_grid_prefetch(a.v, cell);
-    load_pose(t + 2 * stride, n_act, n_x, n_y, n_ang);
+    const float act = n_act, p1x = n_x, p1y = n_y, ang = n_ang;
+    if (t + stride < total) {
+      const uint32_t ag = (t + stride) / nr;
+      n_act = a.aactive != nullptr ? __ldg(a.aactive + ag) : 1.0f;
+      n_x = __ldg(a.ax + ag); n_y = __ldg(a.ay + ag); n_ang = __ldg(a.aang + ag);
+    }
     if (act == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
       a.dist[t] = 0.0f;
       if (a.hit) a.hit[t] = -1;
@@ -195,7 +187,7 @@ __global__ void __launch_bounds__(256, MINB) raycast_walls_grid_kernel(const Wal
     const float q1x = f_add(p1x, f_mul(cs, L)), q1y = f_add(p1y, f_mul(sn, L));
     float best = L;
     int bidx = -1;
-    walls_grid_cast(a.v, fallback, cell_cur, p1x, p1y, q1x, q1y, L, best, bidx);
+    walls_grid_cast(a.v, fallback, p1x, p1y, q1x, q1y, L, best, bidx);
     a.dist[t] = best;
     if (a.hit) a.hit[t] = bidx;
   }
@@ -383,7 +375,7 @@ int fgx_raycast_walls_grid(const float* x, const float* y, const float* ang, con
   a.n = n_agents; a.n_rays = n_rays; a.span = ray_span; a.L = ray_length;
   a.dist = dist; a.hit = hit;
   const int64_t total = n_agents * (int64_t)n_rays;
-  const int grid = grid_for(total, 256, 4);  // one resident wave (4 CTAs of 64-register threads per SM), grid-stride
+  const int grid = grid_for(total, 256, 8);
   if (total >= (1ll << 31)) {
     raycast_walls_grid_kernel_big<<<grid, 256, 0, s>>>(a);
   } else {

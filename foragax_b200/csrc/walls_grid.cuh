@@ -113,25 +113,16 @@ __device__ __forceinline__ float4 wall_line_record(float ax, float ay, float bx,
   return make_float4(na, nb, -(na * ax + nb * ay), tol_line * 1.05f + 8e-7f * scale);
 }
 
-// cell of a position, or -1 when it lies outside the grid (NaN positions fail every comparison -> -1): such
-// agents take the all-walls loop
-__device__ __forceinline__ int walls_grid_cell(const WallsGridView& v, float px, float py) {
-  const float fx = (px - v.g.x0) * v.g.inv_cs, fy = (py - v.g.y0) * v.g.inv_cs;
+// min / first-argmin over the walls for the ray p1 -> q1 (best = L, bidx = -1 on entry); `fallback`: the value of
+// v.st->fallback (read once per thread by the caller)
+__device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, bool fallback, float p1x, float p1y, float q1x,
+                                                float q1y, float L, float& best, int& bidx) {
+  // strictly inside the grid (NaN positions fail and take the all-walls loop)
+  const float fx = (p1x - v.g.x0) * v.g.inv_cs, fy = (p1y - v.g.y0) * v.g.inv_cs;
   const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
-  return inside ? min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1) : -1;
-}
-// pulls the cell record of `cell` into L2 ahead of its use (the record loads of consecutive agents are independent
-// random 32-byte reads: the only DRAM-latency load left on an agent's critical path)
-__device__ __forceinline__ void walls_grid_prefetch(const WallsGridView& v, int cell) {
-  if (cell >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.cellrec + 2 * (int64_t)cell));
-}
-
-// min / first-argmin over the walls for the ray p1 -> q1 (best = L, bidx = -1 on entry); `cell` from
-// walls_grid_cell, `fallback`: the value of v.st->fallback (read once per thread by the caller)
-__device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, bool fallback, int cell, float p1x, float p1y,
-                                                float q1x, float q1y, float L, float& best, int& bidx) {
   const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
-  if (cell >= 0 && !fallback) {
+  if (inside && !fallback) {
+    const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
     const uint4 c0 = __ldg(v.cellrec + 2 * (int64_t)cell), c1 = __ldg(v.cellrec + 2 * (int64_t)cell + 1);
     const uint32_t e0 = c0.x, n_list = c0.y;
     // two walls per trip: their pre-test records (32 KB for 1,000 walls) live in L1, so deeper batches only cost
@@ -170,7 +161,7 @@ __device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, bool fal
 }
 __device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, float p1x, float p1y, float q1x, float q1y,
                                                 float L, float& best, int& bidx) {
-  walls_grid_cast(v, v.st->fallback != 0, walls_grid_cell(v, p1x, p1y), p1x, p1y, q1x, q1y, L, best, bidx);
+  walls_grid_cast(v, v.st->fallback != 0, p1x, p1y, q1x, q1y, L, best, bidx);
 }
 
 // host side (raycast_walls_grid.cu): validates, carves the scratch and -- unless reuse_grid -- builds the wall
