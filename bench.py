@@ -136,9 +136,11 @@ class ClockSampler:
 
 
 def measured_traffic(kernel, n_local):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json),
-    scaled to this rank's shard; None if there is no capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r02_traffic.json, else the
+    round-1 file), scaled to this rank's shard; None if there is no capture."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p)).get(kernel)
@@ -698,6 +700,7 @@ def run_ours(args):
         roof_rc = {"kernel": "raycast_walls_grid_kernel (wall lists built once, cached)", "kernel_ms": k1_ms,
                    "share_of_step": k1_ms / (k1_ms + k2_ms),
                    "algorithmic_bytes": rc_bytes, "gbs": rc_bytes / (k1_ms * 1e-3) / 1e9,
+                   "traffic": measured_traffic("raycast_walls_grid_kernel", n_local),
                    "frac_of_hbm": rc_bytes / (k1_ms * 1e-3) / 1e9 / hbm,
                    "listed_walls_per_active_agent": listed_host[0] / max(listed_host[1], 1),
                    "floors_ms": {"bytes": floor_bytes_ms, "fp32_of_listed_tests": floor_inst_ms},
