@@ -85,6 +85,9 @@ _decl("fgx_peer_add_range", C.c_int, C.POINTER(PeerSync), vp, vp, i64, i64, i64,
 _decl("fgx_key_chain_advance", C.c_int, i32, vp, vp, vp, vp)
 _decl("fgx_sort_key_images", C.c_int, vp, i32, i64, i32, vp, vp, vp)
 _decl("fgx_sort_rows_peer", C.c_int, C.POINTER(PeerLeaf), i32, vp, i64, vp, i64, C.POINTER(i64), i32, i32, vp, vp)
+_decl("fgx_sum_f32_scratch_bytes", sz)
+_decl("fgx_sum_f32", C.c_int, vp, i64, vp, vp, sz, vp)
+_decl("fgx_life_expectancy", C.c_int, vp, vp, vp, vp, vp, vp)
 _decl("fgx_record_frame", C.c_int, C.POINTER(Leaf), i32, i64, i32, vp, vp)
 _decl("fgx_count_active", C.c_int, vp, i64, vp, vp)
 _decl("fgx_count_active_clip", C.c_int, vp, i64, vp, vp, vp)

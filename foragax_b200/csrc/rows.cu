@@ -131,6 +131,48 @@ __global__ void __launch_bounds__(256) count_active_kernel(const float* __restri
   }
 }
 
+// jnp.sum(x) of a float32 leaf as ONE launch with a fixed summation order (run-to-run deterministic): every CTA
+// reduces a contiguous chunk (thread-serial, then a fixed shuffle tree), writes its partial, and the last CTA to
+// finish (ticket) adds the partials in index order.
+constexpr int SUM_MAX_GRID = 256;
+__global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
+                                                      float* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ float ws[8];
+  __shared__ int last;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  float s = 0.0f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s += x[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 8; ++k) t += ws[k];
+    __stcg(partial + blockIdx.x, t);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.0f;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += __ldcg(partial + k);
+    *out = t;
+    *ticket = 0u;  // the scratch is reusable without another memset
+  }
+}
+
+// the life-expectancy update of EcoEvoJax/sim.py:486-493 on device scalars:
+// le = (age_before - age_after) / (n_removed + 0.01); le = where(le == 0, old, le)
+__global__ void life_expectancy_kernel(const float* __restrict__ before, const float* __restrict__ after,
+                                       const int32_t* __restrict__ n_removed, const float* __restrict__ old,
+                                       float* __restrict__ out) {
+  const float le = __fdiv_rn(__fsub_rn(*before, *after), __fadd_rn((float)*n_removed, 0.01f));
+  *out = le == 0.0f ? *old : le;
+}
+
 // Recording ring (EcoEvoJax/sim.py:581-594 record_data: rec.<leaf>.at[frame].set(leaf) for eight leaves per frame):
 // every leaf's n rows are copied into slot (frame mod frames) of its [frames, n, ...] ring in ONE launch
 // (grid.y = leaf).  `frame` is a device scalar so that a recorded tick can live inside a CUDA graph.
@@ -295,5 +337,32 @@ int fgx_record_frame(const fgx_leaf_t* leaves_host, int32_t n_leaves, int64_t n,
   dim3 grid(grid_for(most, 256, 4), n_leaves);
   record_frame_kernel<<<grid, 256, 0, as_stream(stream)>>>(tab, n, frames, frame);
   return check_launch("fgx_record_frame");
+}
+
+size_t fgx_sum_f32_scratch_bytes(void) { return (size_t)(fgx::SUM_MAX_GRID + 1) * 4; }
+
+int fgx_sum_f32(const float* x, int64_t n, float* out, void* scratch, size_t scratch_bytes, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(n >= 0 && out, "fgx_sum_f32: bad arguments");
+  FGX_REQUIRE(scratch && scratch_bytes >= fgx_sum_f32_scratch_bytes() && (reinterpret_cast<uintptr_t>(scratch) & 3) == 0,
+              "fgx_sum_f32: scratch too small / unaligned");
+  FGX_REQUIRE(n == 0 || x, "fgx_sum_f32: null pointer");
+  cudaStream_t s = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(scratch);
+  unsigned* ticket = reinterpret_cast<unsigned*>(partial + SUM_MAX_GRID);
+  cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
+  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_sum_f32: %s", cudaGetErrorString(e));
+  int64_t grid = ceil_div(n, 256 * 16);
+  grid = grid < 1 ? 1 : (grid > SUM_MAX_GRID ? SUM_MAX_GRID : grid);
+  sum_f32_kernel<<<(int)grid, 256, 0, s>>>(x, n, out, partial, ticket);
+  return check_launch("fgx_sum_f32");
+}
+
+int fgx_life_expectancy(const float* age_before, const float* age_after, const int32_t* n_removed, const float* old_value,
+                        float* out, fgx_stream_t stream) {
+  using namespace fgx;
+  FGX_REQUIRE(age_before && age_after && n_removed && old_value && out, "fgx_life_expectancy: null pointer");
+  life_expectancy_kernel<<<1, 1, 0, as_stream(stream)>>>(age_before, age_after, n_removed, old_value, out);
+  return check_launch("fgx_life_expectancy");
 }
 }

@@ -19,7 +19,7 @@ from .. import random as fgx_random
 from .. import struct
 from ..base import space_methods as sm
 from ..base.agent_classes import Agent, Agent_Set, Params, Policy, Signal, State, native
-from ..base.agent_methods import (count_active, create_agents, jit_add_agents, jit_remove_agents,
+from ..base.agent_methods import (count_active, count_active_clip, create_agents, jit_add_agents, jit_remove_agents,
                                   jit_select_agents, jit_set_agents, jit_sort_agents, step_agents)
 from ..base.predicates import P
 from ..base.space_methods import create_space
@@ -331,6 +331,16 @@ jit_sensor_model = sensor_model
 
 
 # sim.py:474-553
+def _sum_f32(x):
+    """``jnp.sum(x)`` of a float32 leaf as a 1-element device tensor (``fgx_sum_f32``: one launch, fixed order)."""
+    x = x.reshape(-1)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    nbytes = L.lib.fgx_sum_f32_scratch_bytes()
+    scr = L.scratch(nbytes)
+    L.check(L.lib.fgx_sum_f32(L.ptr(x.contiguous()), x.shape[0], L.ptr(out), L.ptr(scr), nbytes, L.stream()))
+    return out
+
+
 def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space, life_expectancy_old):
     def select_weak_or_old_foragers(foragers, select_params):
         cond = (P(foragers.active_state) == 1.0) & (P(foragers.state.content['time_below_die_thresh'])
@@ -339,14 +349,18 @@ def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space,
 
     select_params = Params(content={'time_to_die': HYPER.TIME_TO_DIE, 'max_age': HYPER.MAX_AGE})
     num_foragers_remove, remove_indx = jit_select_agents(select_weak_or_old_foragers, select_params, foragers)
-    age_before_death = foragers.age.sum(dtype=torch.float32)
+    age_before_death = _sum_f32(foragers.age)
     foragers = jit_remove_agents(Forager.remove_agent, num_foragers_remove, Params(content={'remove_ids': remove_indx}),
                                  foragers)
-    age_after_death = foragers.age.sum(dtype=torch.float32)
-    life_expectancy = (age_before_death - age_after_death) / (num_foragers_remove + 0.01)
+    age_after_death = _sum_f32(foragers.age)
+    # sim.py:486-493 on device scalars, one launch (no host read-back, no framework elementwise kernels)
     if not isinstance(life_expectancy_old, torch.Tensor):
-        life_expectancy_old = torch.as_tensor(life_expectancy_old, dtype=torch.float32, device=life_expectancy.device)
-    life_expectancy = torch.where(life_expectancy == 0.0, life_expectancy_old.reshape(()), life_expectancy)
+        life_expectancy_old = torch.as_tensor(life_expectancy_old, dtype=torch.float32, device=foragers.age.device)
+    life_expectancy = torch.empty((), dtype=torch.float32, device=foragers.age.device)
+    L.check(L.lib.fgx_life_expectancy(L.ptr(age_before_death), L.ptr(age_after_death),
+                                      L.ptr(L.device_i32(num_foragers_remove)),
+                                      L.ptr(life_expectancy_old.reshape(1).to(torch.float32)), L.ptr(life_expectancy),
+                                      L.stream()))
 
     def select_depleted_resources(resources, select_params):
         return (P(resources.active_state) == 1.0) & (P(resources.state.content['energy'])
@@ -368,10 +382,12 @@ def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space,
     num_foragers_add, add_indx = jit_select_agents(select_good_foragers,
                                                    Params(content={'time_to_reproduce': HYPER.time_to_reproduce}),
                                                    foragers)
-    num_active_foragers = count_active(foragers)
-    num_foragers_add = torch.minimum(num_foragers_add, max_foragers - num_active_foragers)
+    if int(max_foragers) != int(foragers.active_state.shape[0]):
+        raise L.FgxError("Neuroevolution: max_foragers must be the slot count of the forager set (sim.py:664)")
+    num_active_foragers, num_foragers_add = count_active_clip(foragers, num_foragers_add)  # sim.py:520-521
     add_params = Params(content={'good_ids': add_indx, 'num_active_foragers': num_active_foragers})
-    foragers, key = jit_add_agents(Forager.add_agent, num_foragers_add, add_params, foragers, key)
+    foragers, key = jit_add_agents(Forager.add_agent, num_foragers_add, add_params, foragers, key,
+                                   num_active=num_active_foragers)
     foragers, key = jit_set_agents(Forager.set_agent, num_foragers_add, Params(content={'set_ids': add_indx}), foragers,
                                    key)
 
@@ -379,10 +395,12 @@ def Neuroevolution(foragers, resources, key, max_foragers, max_resources, space,
         return (P(resources.active_state) == 1.0) & P(resources.state.content['blossom']).nonzero()
 
     num_resources_add, add_indx = jit_select_agents(select_blossom_resources, None, resources)
-    num_active_resources = count_active(resources)
-    num_resources_add = torch.minimum(num_resources_add, max_resources - num_active_resources)
+    if int(max_resources) != int(resources.active_state.shape[0]):
+        raise L.FgxError("Neuroevolution: max_resources must be the slot count of the resource set (sim.py:664)")
+    num_active_resources, num_resources_add = count_active_clip(resources, num_resources_add)  # sim.py:539-540
     add_params = Params(content={'good_ids': add_indx, 'num_active_resources': num_active_resources})
-    resources, key = jit_add_agents(Resource.add_agent, num_resources_add, add_params, resources, key)
+    resources, key = jit_add_agents(Resource.add_agent, num_resources_add, add_params, resources, key,
+                                    num_active=num_active_resources)
     resources, key = jit_set_agents(Resource.set_agent, num_resources_add, Params(content={'set_ids': add_indx}),
                                     resources, key)
     return foragers, resources, key, num_active_foragers, num_active_resources, life_expectancy

@@ -175,6 +175,14 @@ int fgx_sort_rows_peer(const fgx_peer_leaf_t* leaves_host, int32_t n_leaves, con
  * all leaves; *frame is a device int32 so that a recorded tick can be captured in a CUDA graph.               */
 int fgx_record_frame(const fgx_leaf_t* leaves_host, int32_t n_leaves, int64_t n, int32_t frames, const int32_t* frame,
                      fgx_stream_t stream);
+/* jnp.sum(x) of a float32 leaf (EcoEvoJax/sim.py:486,491: the age sums around remove_agents) in one launch
+ * with a fixed summation order (deterministic run to run; float32 accumulation like jnp.sum).  out float32[1]. */
+size_t fgx_sum_f32_scratch_bytes(void);
+int fgx_sum_f32(const float* x, int64_t n, float* out, void* scratch, size_t scratch_bytes, fgx_stream_t stream);
+/* The life-expectancy update of Neuroevolution (EcoEvoJax/sim.py:486-493) on device scalars:
+ * le = (age_before - age_after) / (n_removed + 0.01); out = (le == 0) ? old_value : le                        */
+int fgx_life_expectancy(const float* age_before, const float* age_after, const int32_t* n_removed, const float* old_value,
+                        float* out, fgx_stream_t stream);
 /* jnp.sum(active_state, dtype=int32) (agent_methods.py:27): out int32[1] */
 int fgx_count_active(const float* active_state, int64_t n, int32_t* out, fgx_stream_t stream);
 /* the same count plus the caller's clip of hello_world.ipynb:138-139 / README.md:124-125 in one launch:
