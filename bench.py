@@ -537,19 +537,22 @@ def run_ours(args):
     tests_per_step = float(N_AGENTS) * N_RAYS * N_WALLS
     value = tests_per_step / (ms_step * 1e-3)
 
-    # per-kernel durations, live, with CUDA events on the launching stream
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    k1_ms, k2_ms = [], []
-    for _ in range(max(args.steps, 20)):
-        ev[0].record(stream)
+    # per-kernel durations, live, with CUDA events on the launching stream.  All launches of the loop are enqueued
+    # without a host sync in between (events are read afterwards): with a sync per iteration the GPU idles while
+    # Python prepares the next launch and that CPU time lands inside the event interval of the short kernel
+    # (round 1 and the first round-2 lines reported K1c ~45 us too long for this reason).
+    reps = max(args.steps, 20)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+    for r in range(reps):
+        evs[r][0].record(stream)
         k1()
-        ev[1].record(stream)
+        evs[r][1].record(stream)
         k2()
-        ev[2].record(stream)
-        ev[2].synchronize()
-        k1_ms.append(ev[0].elapsed_time(ev[1]))
-        k2_ms.append(ev[1].elapsed_time(ev[2]))
-    k1_ms, k2_ms = float(np.mean(k1_ms)), float(np.mean(k2_ms))
+        evs[r][2].record(stream)
+    torch.cuda.synchronize()
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs[1:]]))   # the first K1c follows an idle GPU
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs[1:]]))
+    ev = evs[0]
     listed = sm.wall_grid_listed((st["X"], st["Y"]), space.walls, BOUNDS, RAY_LEN, active_state=F.active_state)
 
     # the same tick with the all-pairs ray cast (every (ray, wall) pair evaluates all four determinants): the

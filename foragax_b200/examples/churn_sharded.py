@@ -106,11 +106,21 @@ class ShardedChurnWorld:
             torch.cuda.synchronize()
             ms, mode = e0.elapsed_time(e1) / ticks, "CUDA graph of two ticks per rank, replayed"
             self.packed.check()
-        # rows that crossed NVLink in one pack at the current fill: the plan of the exchange from the gathered counts
-        n_act = fgx_methods.count_active(self.agents)
-        acts = fd.all_gather_counts(n_act.reshape(()))
+        # rows that cross NVLink in one pack: the exchange plan from the active counts AFTER the removals of a tick
+        # (the state the pack sees); the tick is completed afterwards so that the set stays consistent
+        s, D, st = self.set, self.D, self.packed
+        fgx_methods.step_agents(None, None, s)
+        n_dead, rem = fgx_methods.jit_select_agents(self._dead, None, s.agents)
+        fgx_methods.jit_remove_agents(D.remove_agent, n_dead, fgx_classes.Params(content={'remove_ids': rem}), s.agents)
+        acts = fd.all_gather_counts(fgx_methods.count_active(s.agents).reshape(()))
         sizes = [self.packed.bounds[i + 1] - self.packed.bounds[i] for i in range(self.world)]
         splits = fd.plan_pack_splits(acts.tolist(), sizes)
         remote = sum(v for d, v in enumerate(splits[self.rank]) if d != self.rank)
+        s.agents = st.pack_active()
+        n_sel, _ = fgx_methods.jit_select_agents(self._birth, None, s.agents)
+        n_act = fgx_methods.count_active(s.agents)
+        _, local_count, _ = st.add_range(n_sel, n_act, self.n)
+        fgx_methods.jit_add_agents(D.add_agent, local_count, None, s.agents, None, num_active=n_act)
+        n_act = fgx_methods.count_active(self.agents)
         return {"ms_per_tick": ms, "eager_ms_per_tick": eager_ms, "mode": mode, "final_active_local": int(n_act),
                 "rows_sent_remote_per_tick": remote}
