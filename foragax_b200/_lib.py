@@ -81,6 +81,8 @@ class PeerSync(C.Structure):
 
 _decl("fgx_peer_mailbox_bytes", sz)
 _decl("fgx_peer_exchange", C.c_int, C.POINTER(PeerSync), vp, vp, vp, vp)
+_decl("fgx_peer_gather_positions", C.c_int, C.POINTER(PeerSync), C.POINTER(vp), i64, vp, vp, vp, vp, i64, i64, i32,
+      C.POINTER(i64), vp, vp)
 _decl("fgx_peer_add_range", C.c_int, C.POINTER(PeerSync), vp, vp, i64, i64, i64, vp, vp)
 _decl("fgx_key_chain_advance", C.c_int, i32, vp, vp, vp, vp)
 _decl("fgx_sort_key_images", C.c_int, vp, i32, i64, i32, vp, vp, vp)

@@ -294,6 +294,44 @@ __global__ void __launch_bounds__(32) peer_add_range_kernel(const PeerSync sy, c
   }
 }
 
+// ---- positions for agent-agent sensing: pack -> barrier -> pull over NVLink, in slot order -----------------
+struct GatherPlan {
+  const float4* stage[FGX_MAX_PEERS];  // every rank's staging buffer (both parities) as mapped here
+  long long bounds[FGX_MAX_PEERS + 1];
+  long long n_max;
+  int32_t world, layout;
+};
+
+// rows of this rank -> its staging buffer, parity of the NEXT epoch (the barrier that follows bumps the epoch)
+__global__ void __launch_bounds__(256) peer_stage_positions_kernel(const unsigned long long* __restrict__ epoch, float4* stage,
+                                                                   long long n_max, const float* __restrict__ x,
+                                                                   const float* __restrict__ y, const float* __restrict__ r,
+                                                                   const float* __restrict__ a, long long n) {
+  float4* dst = stage + (long long)((*epoch + 1ull) & 1ull) * n_max;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = make_float4(x[i], y[i], r[i], a[i]);
+}
+
+// every global slot <- the owning rank's staged row (peer loads), parity of the CURRENT epoch
+__global__ void __launch_bounds__(256) peer_pull_positions_kernel(const unsigned long long* __restrict__ epoch,
+                                                                  const __grid_constant__ GatherPlan pl, long long n_total,
+                                                                  float4* __restrict__ table) {
+  const long long par = (long long)(*epoch & 1ull) * pl.n_max;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+    int d;
+    long long row;
+    if (pl.layout == 1) {
+      d = (int)(i % pl.world);
+      row = i / pl.world;
+    } else {
+      d = 0;
+      while (d + 1 < pl.world && i >= pl.bounds[d + 1]) ++d;
+      row = i - pl.bounds[d];
+    }
+    table[i] = pl.stage[d][par + row];  // plain (coherent) load: the rows were published by the barrier's fences
+  }
+}
+
 static int make_sync(const char* what, const fgx_peer_sync_t* sync, PeerSync* out) {
   FGX_REQUIRE(sync, "%s: null sync", what);
   FGX_REQUIRE(sync->world >= 1 && sync->world <= FGX_MAX_PEERS && sync->rank >= 0 && sync->rank < sync->world,
@@ -325,6 +363,50 @@ int fgx_peer_exchange(const fgx_peer_sync_t* sync, const int32_t* v0, const int3
   if (rc != FGX_OK) return rc;
   peer_exchange_kernel<<<1, 32, 0, as_stream(stream)>>>(sy, v0, v1, reinterpret_cast<long long*>(out_all));
   return check_launch("fgx_peer_exchange");
+}
+
+int fgx_peer_gather_positions(const fgx_peer_sync_t* sync, void* const* stage, int64_t n_max, const float* x,
+                              const float* y, const float* rad, const float* active, int64_t n_local, int64_t n_total,
+                              int32_t layout, const int64_t* bounds_host, float* table, fgx_stream_t stream) {
+  using namespace fgx;
+  PeerSync sy{};
+  const int rc = make_sync("fgx_peer_gather_positions", sync, &sy);
+  if (rc != FGX_OK) return rc;
+  FGX_REQUIRE(stage && table && n_local >= 0 && n_total >= n_local && n_max >= n_local,
+              "fgx_peer_gather_positions: bad arguments");
+  FGX_REQUIRE(n_local == 0 || (x && y && rad && active), "fgx_peer_gather_positions: null leaf");
+  FGX_REQUIRE(layout == 0 || layout == 1, "fgx_peer_gather_positions: layout must be 0 (blocks) or 1 (round robin)");
+  GatherPlan pl{};
+  pl.world = sy.world;
+  pl.layout = layout;
+  pl.n_max = n_max;
+  for (int d = 0; d < sy.world; ++d) {
+    FGX_REQUIRE(stage[d] && (reinterpret_cast<uintptr_t>(stage[d]) & 15) == 0,
+                "fgx_peer_gather_positions: staging buffer %d missing / unaligned", d);
+    pl.stage[d] = reinterpret_cast<const float4*>(stage[d]);
+  }
+  if (layout == 0) {
+    FGX_REQUIRE(bounds_host && bounds_host[0] == 0 && bounds_host[sy.world] == n_total,
+                "fgx_peer_gather_positions: block layout needs shard bounds covering [0, n_total)");
+    for (int d = 0; d < sy.world; ++d) {
+      FGX_REQUIRE(bounds_host[d] <= bounds_host[d + 1] && bounds_host[d + 1] - bounds_host[d] <= n_max,
+                  "fgx_peer_gather_positions: bad shard bounds");
+      pl.bounds[d] = bounds_host[d];
+    }
+    pl.bounds[sy.world] = bounds_host[sy.world];
+    FGX_REQUIRE(bounds_host[sy.rank + 1] - bounds_host[sy.rank] == n_local, "fgx_peer_gather_positions: n_local != own block");
+  } else {
+    FGX_REQUIRE((n_total + sy.world - 1 - sy.rank) / sy.world == n_local && (n_total + sy.world - 1) / sy.world <= n_max,
+                "fgx_peer_gather_positions: n_local does not match slot i -> rank i mod world");
+  }
+  cudaStream_t s = as_stream(stream);
+  float4* own = reinterpret_cast<float4*>(stage[sy.rank]);
+  if (n_local)
+    peer_stage_positions_kernel<<<grid_for(n_local, 256, 4), 256, 0, s>>>(sy.epoch, own, n_max, x, y, rad, active, n_local);
+  peer_exchange_kernel<<<1, 32, 0, s>>>(sy, nullptr, nullptr, nullptr);  // barrier: every rank's rows are staged
+  if (n_total)
+    peer_pull_positions_kernel<<<grid_for(n_total, 256, 8), 256, 0, s>>>(sy.epoch, pl, n_total, reinterpret_cast<float4*>(table));
+  return check_launch("fgx_peer_gather_positions");
 }
 
 int fgx_peer_add_range(const fgx_peer_sync_t* sync, const int32_t* n_selected_local, const int32_t* n_active_local,

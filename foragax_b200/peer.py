@@ -199,3 +199,65 @@ class PeerPackedSet:
             self.exchange()  # system fence + flags: every rank's scatter has landed before anyone reads set `dst`
         self.cur = dst
         return self.agents
+
+
+class PeerPositions:
+    """``distributed.all_gather_positions`` without NCCL (``fgx_peer_gather_positions``): each rank stages its
+    ``float4 (x, y, rad, active)`` rows in symmetric memory, the ranks meet in a mailbox barrier and every rank pulls
+    all rows over NVLink into a table IN GLOBAL SLOT ORDER (so the hit indices of ``fgx_raycast_agents`` are global
+    slot ids).  Three small launches on the current stream, no host sync: the whole sensing leg can be captured in a
+    CUDA graph.  ``layout``: ``"block"`` (contiguous blocks, ``distributed.shard_bounds``) or ``"round_robin"``."""
+
+    def __init__(self, n_local, layout="block", group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        if layout not in ("block", "round_robin"):
+            raise ValueError(f"unknown shard layout {layout!r}")
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > L.MAX_PEERS:
+            raise L.FgxError(f"at most {L.MAX_PEERS} ranks of one node")
+        dev = L.device() if device is None else device
+        self.layout, self.n_local = layout, int(n_local)
+        sizes = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([self.n_local], dtype=torch.int64, device=dev), group=self.group)
+        sizes = [int(v) for v in sizes.tolist()]
+        self.n_total, self.n_max = sum(sizes), max(sizes)
+        bounds = [0]
+        for v in sizes:
+            bounds.append(bounds[-1] + v)
+        self._bounds_c = (C.c_int64 * (self.world + 1))(*bounds)
+        self._stage = symm.empty(max(2 * self.n_max * 16, 256), dtype=torch.uint8, device=dev)
+        self._stage_hdl = symm.rendezvous(self._stage, self.group)
+        self._stage_c = (C.c_void_p * self.world)(*[int(p) for p in self._stage_hdl.buffer_ptrs])
+        self._mailbox = symm.empty(int(L.lib.fgx_peer_mailbox_bytes()), dtype=torch.uint8, device=dev)
+        self._mailbox.zero_()
+        self._mailbox_hdl = symm.rendezvous(self._mailbox, self.group)
+        self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._sync = L.PeerSync()
+        for d in range(self.world):
+            self._sync.mailbox[d] = int(self._mailbox_hdl.buffer_ptrs[d])
+        self._sync.epoch, self._sync.error = self._epoch.data_ptr(), self._error.data_ptr()
+        self._sync.rank, self._sync.world = self.rank, self.world
+        self.table = torch.empty((self.n_total, 4), dtype=torch.float32, device=dev)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.all_reduce(token, group=self.group)  # every rank's staging buffer and zeroed mailbox exist
+
+    def gather(self, x, y, rad, active):
+        """float32[n_total, 4] rows ``(x, y, rad, active)`` of all agents in slot order (a buffer owned by this
+        object, overwritten by the next call)."""
+        f = lambda t: t.reshape(-1) if t.is_contiguous() else t.contiguous().reshape(-1)  # noqa: E731
+        x, y, rad, active = f(x), f(y), f(rad), f(active)
+        if x.shape[0] != self.n_local:
+            raise L.FgxError("PeerPositions.gather: leaf length differs from the shard size given at construction")
+        L.check(L.lib.fgx_peer_gather_positions(C.byref(self._sync), self._stage_c, self.n_max, L.ptr(x), L.ptr(y), L.ptr(rad),
+                                                L.ptr(active), self.n_local, self.n_total,
+                                                1 if self.layout == "round_robin" else 0, self._bounds_c,
+                                                L.ptr(self.table), L.stream()))
+        return self.table
+
+    def check(self):
+        e = int(self._error.item())
+        if e:
+            raise L.FgxError(f"peer position gather timed out waiting for rank {e - 1}")

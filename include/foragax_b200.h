@@ -151,6 +151,16 @@ typedef struct {
 size_t fgx_peer_mailbox_bytes(void);
 int fgx_peer_exchange(const fgx_peer_sync_t* sync, const int32_t* v0, const int32_t* v1, int64_t* out_all,
                       fgx_stream_t stream);
+/* The position exchange of agent-agent sensing (all-gather of float4 (x, y, rad, active), 16 B per
+ * agent) without NCCL: every rank packs its rows into its own STAGING buffer in peer-mapped memory (stage[d] = rank
+ * d's staging buffer as mapped here, 2 * n_max float4: two parities), the ranks meet in a mailbox barrier
+ * (fgx_peer_exchange semantics, same sync state rules) and every rank then pulls all rows over NVLink into
+ * table[n_total] IN GLOBAL SLOT ORDER.  layout 0: contiguous blocks (bounds_host int64[world + 1]); layout 1:
+ * round-robin (slot i on rank i mod world at row i / world; bounds_host ignored).  All launches are enqueued on
+ * `stream`; no host synchronisation, capturable in a CUDA graph.                                             */
+int fgx_peer_gather_positions(const fgx_peer_sync_t* sync, void* const* stage, int64_t n_max, const float* x,
+                              const float* y, const float* rad, const float* active, int64_t n_local, int64_t n_total,
+                              int32_t layout, const int64_t* bounds_host, float* table, fgx_stream_t stream);
 /* add_agents over a globally packed, block-sharded set (agent_methods.py:26-38 + the caller's clip
  * min(n_selected, N - n_active), README.md:124-125) in one launch: exchanges (n_selected_local, n_active_local)
  * as above and writes out3 = { k = min(sum selected, n_total - sum active),

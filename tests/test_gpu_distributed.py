@@ -391,6 +391,16 @@ def _sense_worker(rank, world, port, n, layout, q):
     d, h = sm.raycast_agents((up(x[mine]), up(y[mine]), up(ang[mine])), 0.7, L, tg, bounds, 6.0,
                              active_state=up(act[mine]), n_rays=R)
     ok = torch.equal(d, full_d[mine]) and torch.equal(h, full_h[mine])
+    # the same table through peer memory (no NCCL: stage, mailbox barrier, pull over NVLink), several rounds
+    from foragax_b200.peer import PeerPositions
+    pp = PeerPositions(int(up(x[mine]).shape[0]), layout=layout)
+    for rnd in range(3):
+        shift = float(rnd)
+        t2 = pp.gather(up(x[mine]) + shift, up(y[mine]), up(rad[mine]), up(act[mine]))
+        want = tg.clone()
+        want[:, 0] += shift
+        ok = ok and torch.equal(t2, want)
+    pp.check()
     q.put((rank, bool(ok), float((full_h >= 0).float().mean())))
     dist.destroy_process_group()
 
