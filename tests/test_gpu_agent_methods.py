@@ -336,3 +336,41 @@ def test_churn_world_matches_oracle(cuda, n):
         ref = odice.churn_tick(ref, n, 20)
         assert_same(w.agents, ref)
     assert 0 < int(n_act) <= n  # the count before the add of the last tick
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 100_003, 2_000_001])
+def test_count_active_and_clip(cuda, n):
+    """fgx_count_active / fgx_count_active_clip (agent_methods.py:27 + README.md:124-125): float4 body + scalar tail,
+    16-byte-misaligned views (scalar path), the last-CTA clip epilogue."""
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200.base.agent_classes import Agent
+    rng = np.random.default_rng(n)
+    flags = (rng.random(n + 3) < 0.37).astype(np.float32)
+    base = torch.from_numpy(flags).to(cuda)
+    for off in (0, 1, 3):  # data pointers at +0, +4, +12 bytes
+        act = base[off:off + n]
+        ag = Agent(params=None, state=None, unique_id=torch.zeros(n, dtype=torch.int32, device=cuda), agent_type=None,
+                   active_state=act, age=None, policy=None)
+        want = int(flags[off:off + n].sum())
+        assert int(fgx_methods.count_active(ag)) == want
+        for n_add in (0, 5, n, 2 * n + 7):
+            n_act, clipped = fgx_methods.count_active_clip(ag, n_add)
+            assert int(n_act) == want and int(clipped) == min(n_add, n - want)
+            n_act, clipped = fgx_methods.count_active_clip(ag, torch.tensor([n_add], dtype=torch.int32, device=cuda))
+            assert int(n_act) == want and int(clipped) == min(n_add, n - want)
+
+
+@pytest.mark.parametrize("n", [0, 1, 257, 4096, 1_000_003])
+def test_deterministic_float_sum(cuda, n):
+    """fgx_sum_f32 (the age sums of Neuroevolution, sim.py:486,491): exact for integer-valued leaves (ages are tick
+    counts), float32-accurate and bit-identical run to run otherwise."""
+    from foragax_b200.examples.foraging import _sum_f32
+    rng = np.random.default_rng(n + 1)
+    ages = rng.integers(0, 1000, n).astype(np.float32)
+    assert float(_sum_f32(torch.from_numpy(ages).to(cuda))) == float(ages.astype(np.float64).sum())
+    x = rng.standard_normal(n).astype(np.float32)
+    xt = torch.from_numpy(x).to(cuda)
+    a, b = _sum_f32(xt), _sum_f32(xt)
+    assert torch.equal(a, b)
+    ref = float(x.astype(np.float64).sum())
+    assert abs(float(a) - ref) <= 1e-6 * float(np.abs(x).astype(np.float64).sum()) + 1e-6
