@@ -35,25 +35,26 @@ struct WallsGridView {
   const WState* st;
 };
 
-// ray_wall_sensor (space_methods.py:96-143) given the four orientation determinants the caller already holds.
-// When none of them is zero the collinear cases c2..c5 (each needs an o == 0) cannot apply, so only the
-// proper-crossing candidate d1 is evaluated: the same bits as ray_wall_exact, without its three extra norms.
+// line_intercept + distance of the proper-crossing candidate d1 (space_methods.py:98-103,124-128)
+__device__ __forceinline__ float crossing_dist(float p1x, float p1y, float q1x, float q1y, float p2x, float p2y,
+                                               float q2x, float q2y) {
+  const float ax = f_sub(q1x, p1x), ay = f_sub(q1y, p1y);
+  const float c1 = f_sub(f_mul(ax, f_sub(p2y, p1y)), f_mul(ay, f_sub(p2x, p1x)));
+  const float c2 = f_sub(f_mul(ax, f_sub(q2y, p1y)), f_mul(ay, f_sub(q2x, p1x)));
+  const float r = __fdiv_rn(c1, f_add(f_sub(c1, c2), 1e-6f));
+  const float ix = f_add(p2x, f_mul(r, f_sub(q2x, p2x)));
+  const float iy = f_add(p2y, f_mul(r, f_sub(q2y, p2y)));
+  return norm2(f_sub(ix, p1x), f_sub(iy, p1y));
+}
+
+// ray_wall_sensor (space_methods.py:96-143) given the four orientation determinants the caller already holds, for
+// the rare pairs with a ZERO determinant (the collinear cases c2..c5 each need an o == 0).
 static __device__ __noinline__ float ray_wall_exact_o(float p1x, float p1y, float q1x, float q1y, float L, float p2x,
                                                       float p2y, float q2x, float q2y, float v1, float v2, float v3,
                                                       float v4) {
   const int o1 = orient_cls(v1), o2 = orient_cls(v2), o3 = orient_cls(v3), o4 = orient_cls(v4);
   float d1 = L;
-  if (o1 != o2 && o3 != o4) {
-    // line_intercept (space_methods.py:98-103)
-    const float ax = f_sub(q1x, p1x), ay = f_sub(q1y, p1y);
-    const float c1 = f_sub(f_mul(ax, f_sub(p2y, p1y)), f_mul(ay, f_sub(p2x, p1x)));
-    const float c2 = f_sub(f_mul(ax, f_sub(q2y, p1y)), f_mul(ay, f_sub(q2x, p1x)));
-    const float r = __fdiv_rn(c1, f_add(f_sub(c1, c2), 1e-6f));
-    const float ix = f_add(p2x, f_mul(r, f_sub(q2x, p2x)));
-    const float iy = f_add(p2y, f_mul(r, f_sub(q2y, p2y)));
-    d1 = norm2(f_sub(ix, p1x), f_sub(iy, p1y));
-  }
-  if (o1 != 0 && o2 != 0 && o3 != 0 && o4 != 0) return min_nan(d1, L);
+  if (o1 != o2 && o3 != o4) d1 = crossing_dist(p1x, p1y, q1x, q1y, p2x, p2y, q2x, q2y);
   float d2 = L, d3 = L, d4 = L, d5 = L;
   if (o1 == 0 && on_segment(p1x, p1y, p2x, p2y, q1x, q1y)) d2 = norm2(f_sub(p1x, p2x), f_sub(p1y, p2y));
   if (o2 == 0 && on_segment(p1x, p1y, q2x, q2y, q1x, q1y)) d3 = norm2(f_sub(p1x, q2x), f_sub(p1y, q2y));
@@ -65,13 +66,24 @@ static __device__ __noinline__ float ray_wall_exact_o(float p1x, float p1y, floa
 // one (ray, wall) pair, exactly as the all-pairs kernel decides it: sure miss <=> no candidate distance of
 // ray_wall_sensor can apply (max(o1*o2, o3*o4) > 0 and all four determinants nonzero); otherwise the op-for-op
 // restatement.  (distance, wall) minima are lexicographic = argmin's first-index rule for any visiting order.
+// When no determinant is zero (NaN counts as nonzero: class 2, space_methods.py:113) only the proper-crossing
+// candidate d1 can apply, and it does iff the classes differ pairwise, i.e. iff (o1 > 0) != (o2 > 0) and
+// (o3 > 0) != (o4 > 0); that common case runs inline.  Without a crossing the pair yields exactly L, which can
+// never replace the running minimum: bidx >= 0 implies best < L (an update needs d < best <= L, or a tie with
+// an earlier update), so the early return is exact.
 __device__ __forceinline__ void test_wall(float p1x, float p1y, float q1x, float q1y, float L, float p2x, float p2y,
                                           float q2x, float q2y, int w, float& best, int& bidx) {
   const float o1 = orient_val(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_val(p1x, p1y, q1x, q1y, q2x, q2y);
   const float o3 = orient_val(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_val(p2x, p2y, q2x, q2y, q1x, q1y);
   const float A = f_mul(o1, o2), B = f_mul(o3, o4);
   if (fmaxf(A, B) > 0.0f && fabsf(f_mul(A, B)) > 0.0f) return;
-  const float d = ray_wall_exact_o(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, o1, o2, o3, o4);
+  float d;
+  if (o1 != 0.0f && o2 != 0.0f && o3 != 0.0f && o4 != 0.0f) {
+    if (((o1 > 0.0f) == (o2 > 0.0f)) || ((o3 > 0.0f) == (o4 > 0.0f))) return;
+    d = min_nan(crossing_dist(p1x, p1y, q1x, q1y, p2x, p2y, q2x, q2y), L);
+  } else {
+    d = ray_wall_exact_o(p1x, p1y, q1x, q1y, L, p2x, p2y, q2x, q2y, o1, o2, o3, o4);
+  }
   if (d < best || (d == best && bidx >= 0 && w < bidx)) {
     best = d;
     bidx = w;

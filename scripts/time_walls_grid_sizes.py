@@ -46,6 +46,9 @@ for n in (125_000, 250_000, 500_000, 1_000_000):
         e1.record()
         torch.cuda.synchronize()
         cold.append(e0.elapsed_time(e1))
-    out[str(x.shape[0])] = {"ms_back_to_back": warm, "ms_after_l2_flush": float(np.median(cold)),
+    import hashlib
+    dig = hashlib.sha256(d.cpu().numpy().tobytes() + h.cpu().numpy().tobytes()).hexdigest()[:16]
+    out[str(x.shape[0])] = {"digest": dig, "ms_back_to_back": warm, "ms_after_l2_flush": float(np.median(cold)),
                            "ns_per_agent_back_to_back": warm * 1e6 / x.shape[0]}
-print(json.dumps({"kernel": "raycast_walls_grid_kernel", "by_agents": out}))
+print(json.dumps({"kernel": "raycast_walls_grid_kernel", "env": {k: v for k, v in os.environ.items() if k.startswith("FGX_")},
+                  "by_agents": out}))
