@@ -340,7 +340,9 @@ def c5_churn_leg(args, rank, world, dev):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     if world == 1:
         w = churn.ChurnWorld(n)
-        tick_ms, ops, n_act = churn.time_ticks(w, ticks)
+        eager_ms, ops, n_act = churn.time_ticks(w, ticks)
+        tick_ms, graph = churn.time_graph_ticks(w, ticks)  # the same 13 launches per tick, two ticks per graph launch
+        del graph
         alg = churn.algorithmic_bytes(n, n_act, 0.05 * n_act)
         rows = {}
         for name in churn.OPS:
@@ -350,7 +352,9 @@ def c5_churn_leg(args, rank, world, dev):
         out = {"workload": f"C5: {n} Dice slots (28 B rows), D20, ~{n_act:.0f} active, ~5% + 5% turnover per tick; tick = "
                            "step -> select -> remove -> sort(active_state, desc) -> select -> clip -> add "
                            "(hello_world.ipynb:104-144)",
-               "n_gpus": 1, "ms_per_tick": tick_ms, "slot_steps_per_sec": n / (tick_ms * 1e-3),
+               "n_gpus": 1, "ms_per_tick": tick_ms, "eager_ms_per_tick": eager_ms,
+               "mode": "CUDA graph of two ticks, replayed (per-op times: eager, events around every op)",
+               "slot_steps_per_sec": n / (tick_ms * 1e-3),
                "active_agent_steps_per_sec": n_act / (tick_ms * 1e-3), "ops": rows,
                "algorithmic_bytes_per_tick": tot, "tick_gbs": tot / (tick_ms * 1e-3) / 1e9,
                "tick_frac_of_hbm": tot / (tick_ms * 1e-3) / 1e9 / hbm, "hbm_peak_gbs": hbm, "peak_basis": peak_src,

@@ -191,16 +191,27 @@ def argsort(quantity, ascend=True):
     return perm
 
 
-def _leaf_table(agents, n_out):
-    """(leaves, fresh destination buffers of n_out rows, [(src, dst, row_bytes)]) of an agent pytree."""
+def _leaf_table(agents, n_out, out=None):
+    """(leaves, destination buffers of n_out rows, [(src, dst, row_bytes)]) of an agent pytree; the destinations are
+    fresh unless ``out`` (a pytree of the same structure holding contiguous n_out-row buffers) supplies them."""
     leaves = struct.tree_leaves(agents)
     n_src = leaves[0].shape[0] if leaves else 0
+    given = struct.tree_leaves(out) if out is not None else None
+    if given is not None and len(given) != len(leaves):
+        raise L.FgxError("out= must have the structure of the agent pytree")
     outs, table = [], []
-    for x in leaves:
+    for k, x in enumerate(leaves):
         if x.shape[0] != n_src:
             raise L.FgxError("every agent leaf must have the slot axis first")
         src = x if x.is_contiguous() else x.contiguous()
-        dst = torch.empty((n_out,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        shape = (n_out,) + tuple(src.shape[1:])
+        if given is None:
+            dst = torch.empty(shape, dtype=src.dtype, device=src.device)
+        else:
+            dst = given[k]
+            if (tuple(dst.shape) != shape or dst.dtype != src.dtype or not dst.is_contiguous()
+                    or dst.data_ptr() == src.data_ptr()):
+                raise L.FgxError("out= leaves must be contiguous buffers of the sorted shape, distinct from the input")
         outs.append(dst)
         row_bytes = src.element_size() * (src.numel() // n_src) if n_src else 0
         table.append((src, dst, row_bytes))
@@ -228,17 +239,22 @@ def take_rows(agents, ids):
 
 
 # agent_methods.py:74-79
-def sort_agents(quantity, ascend, agents):
+def sort_agents(quantity, ascend, agents, out=None):
     """argsort + ``take`` of every leaf as ONE native call (``fgx_sort_rows``): a two-valued key (the sort on
-    ``active_state``) is partitioned and its rows are moved by a single kernel that reads the key once."""
+    ``active_state``) is partitioned and its rows are moved by a single kernel that reads the key once.
+    ``out`` (optional, beyond the reference signature): an agent pytree of preallocated destination buffers -- a
+    world that alternates between two buffer sets returns to its first set every second tick, which is what lets
+    a pair of ticks be captured as one CUDA graph."""
     q = quantity.reshape(-1)
     if q.dtype == torch.bool:
         q = q.to(torch.int32)
     if not q.is_contiguous():
         q = q.contiguous()
     n = q.shape[0]
-    n_src, outs, table = _leaf_table(agents, n)
+    n_src, outs, table = _leaf_table(agents, n, out)
     if len(table) > L.MAX_LEAVES or n_src != n:
+        if out is not None:
+            raise L.FgxError("sort_agents(out=): the fused row move handles at most %d leaves" % L.MAX_LEAVES)
         sorted_ids = argsort(quantity, ascend)
         return take_rows(agents, sorted_ids), sorted_ids
     if isinstance(ascend, torch.Tensor):

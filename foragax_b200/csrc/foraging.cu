@@ -103,16 +103,20 @@ __device__ __forceinline__ uint32_t leaf_tma_bytes(const float* base, int row_fl
 struct ActiveScan {
   int64_t base, probe_base;
   unsigned mask;
+  uint32_t next_round = 0u, probe_round = 0u, round = 0u;  // round = index of the returned agent in the warp's sequence
   __device__ __forceinline__ int64_t next(const float* __restrict__ active, int64_t GW, int64_t n_agents, int lane) {
     while (mask == 0u) {
       if (base >= n_agents) return n_agents;
       const int64_t mine = base + lane * GW;
       mask = __ballot_sync(0xffffffffu, mine < n_agents && active[mine] != 0.0f);
       probe_base = base;
+      probe_round = next_round;
       base += 32 * GW;
+      next_round += 32u;
     }
     const int b = __ffs(mask) - 1;
     mask &= mask - 1u;
+    round = probe_round + (uint32_t)b;
     return probe_base + (int64_t)b * GW;
   }
 };
@@ -130,10 +134,85 @@ struct SenseArgs {
   int32_t* hit;
 };
 
+// ---- warp-specialised fused sensing (RW > 0 extra warps per CTA; 32 rays) ------------------------------------------
+// The step warps of a CTA consume, in round j, the 8 consecutive agents first + j * GW + (0..7) (first = 8 * blockIdx,
+// GW = 8 * gridDim).  The CTA's RW ray warps produce exactly those tiles ahead of them -- warp r the rounds r, r + RW,
+// ... -- with the warp-cooperative walk of walls_grid.cuh, write dist / hit to global memory and publish the number of
+// the last finished round in shared memory (fence.cta + volatile flag).  A step warp issues the weight copies of its
+// agent, then waits for the agent's round and reads its 32 distances back as the observation.  The ray warps never
+// wait for the step warps, so there is no cycle; the step kernel is HBM-bound and leaves > 80 % of the issue slots idle,
+// which is what the (issue-bound) ray cast runs in.  Positions are updated in place by the step warps: an agent's pose
+// is read by its ray warp before the flag of its round is published, i.e. before its step can start.
+struct RaySmem {  // per ray warp: two parked tiles (a tile = the 8 agents of one round) + the survivor area
+  WgwTileSmem<FS_WARPS> tile[2];
+  WgwSurvSmem surv;
+};
+
+template <int RW>
+__device__ __forceinline__ void ray_warps_role(const SenseArgs& sense, const fgx_forager_state_t& st,
+                                               const float* __restrict__ active, uint32_t n, RaySmem* wsm,
+                                               volatile uint32_t* done, uint32_t r, uint32_t lane) {
+  // two parked tiles per warp: while the agents of one are cast, the next one lands in the other, so that the
+  // first agent of every tile can be prefetched like the others
+  WgwTileSmem<FS_WARPS>* sm2 = wsm[r].tile;
+  WgwSurvSmem& surv = wsm[r].surv;
+  const WallsGridView& v = sense.v;
+  const bool fallback = v.st->fallback != 0;
+  float sj, omsj;
+  wgw_lane_weights(lane, sj, omsj);
+  const uint32_t GW = gridDim.x * FS_WARPS, first = blockIdx.x * FS_WARPS;
+  const uint32_t rounds = first < n ? (n - first + GW - 1u) / GW : 0u;
+  uint32_t j = r;
+  if (j >= rounds) return;
+  WgwTile nx;
+  {
+    const uint32_t base = first + j * GW;
+    wgw_load_pose<true>(st.X, st.Y, st.ang, active, min(n, base + FS_WARPS), base + lane, nx);
+    wgw_load_rec(v, fallback, nx);
+    wgw_park(sm2[0], lane, nx, FS_WARPS);
+    __syncwarp();
+  }
+  uint32_t buf = 0;
+  WgwPre cur, nxt;
+  wgw_prefetch(v, sm2[0], 0, lane, cur);
+  for (; j < rounds; j += RW) {
+    const uint32_t base = first + j * GW;
+    const uint32_t cnt = min((uint32_t)FS_WARPS, n - base);
+    const uint32_t jn = j + RW;
+    const uint32_t base_n = first + jn * GW;
+    const bool more = jn < rounds;
+    if (more) wgw_load_pose<true>(st.X, st.Y, st.ang, active, min(n, base_n + FS_WARPS), base_n + lane, nx);
+#pragma unroll 1  // one copy of the per-agent code: eight would push the step warps' loop out of the instruction cache
+    for (uint32_t k = 0; k < cnt; ++k) {
+      // next tile: cell records requested a quarter into this tile, parked three quarters in, so that ...
+      if (more && k == (cnt >> 2)) wgw_load_rec(v, fallback, nx);
+      if (more && k == cnt - 1u - (cnt >> 2)) {
+        wgw_park(sm2[buf ^ 1u], lane, nx, FS_WARPS);
+        __syncwarp();
+      }
+      // ... the loads of the NEXT agent (this tile's, or the first of the next tile) fly during this agent's cast
+      if (k + 1u < cnt) wgw_prefetch(v, sm2[buf], k + 1u, lane, nxt);
+      else if (more) wgw_prefetch(v, sm2[buf ^ 1u], 0, lane, nxt);
+      const uint32_t o = (base + k) * 32u + lane;
+      float best;
+      int bidx;
+      wgw_cast_agent(v, surv, lane, sense.L, sense.span, sj, omsj, cur, best, bidx);
+      sense.dist[o] = best;
+      if (sense.hit) sense.hit[o] = bidx;
+      cur = nxt;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) done[r] = j + 1u;
+    buf ^= 1u;
+  }
+}
+
 // NN / NOBS / NACT > 0 fix the policy shape at compile time (constant trip counts, immediate
 // shared-memory offsets, no shape branches); 0 = read it from the params (any shape).
-template <int NN, int NOBS, int NACT>
-__global__ void __launch_bounds__(FS_WARPS * 32)
+// RW > 0: RW more warps per CTA cast the rays (ray_warps_role above); two CTAs per SM then cap the kernel at 96 registers.
+template <int NN, int NOBS, int NACT, int RW = 0>
+__global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
                         const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
@@ -150,7 +229,20 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   const int n = NN ? NN : p.n_neurons, nobs = NOBS ? NOBS : p.n_obs, nact = NACT ? NACT : p.n_act;
   const WcLayout L = wc_layout(n, nobs, nact);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
+  const int nwarps = RW ? FS_WARPS : (int)(blockDim.x >> 5);  // step warps
+  volatile uint32_t* ray_done = nullptr;
+  if constexpr (RW > 0) {
+    // tail of the dynamic shared memory: RW parked-tile areas + the per-ray-warp round counters
+    unsigned char* tail = smem_raw + 16 * FS_WARPS + (size_t)FS_WARPS * slots * L.total * sizeof(float);
+    RaySmem* wsm = reinterpret_cast<RaySmem*>(tail);
+    ray_done = reinterpret_cast<volatile uint32_t*>(tail + RW * sizeof(RaySmem));
+    if (threadIdx.x < RW) ray_done[threadIdx.x] = 0u;
+    __syncthreads();
+    if (warp >= FS_WARPS) {
+      ray_warps_role<RW>(sense, st, active, (uint32_t)n_agents, wsm, ray_done, (uint32_t)(warp - FS_WARPS), (uint32_t)lane);
+      return;
+    }
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
   float* slot0 = reinterpret_cast<float*>(smem_raw + 16 * FS_WARPS) + (size_t)warp * slots * L.total;
   if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
@@ -231,21 +323,31 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   int64_t a = scan.next(active, GW, n_agents, lane);
   int s = 0;
   float sv = 0.0f;
+  uint32_t round = scan.round;
   if (a < n_agents) {
     sv = issue(a, 0);
-    if (sense.enabled) cast_rays(a, sv, 0);
+    if (RW == 0 && sense.enabled) cast_rays(a, sv, 0);
   }
   while (a < n_agents) {
     const int64_t a_next = scan.next(active, GW, n_agents, lane);
+    const uint32_t round_next = scan.round;
     float sv_next = 0.0f;
     if (slots == 2 && a_next < n_agents) {  // slot s^1 was released by the last __syncwarp
       sv_next = issue(a_next, s ^ 1);
-      if (sense.enabled) cast_rays(a_next, sv_next, s ^ 1);
+      if (RW == 0 && sense.enabled) cast_rays(a_next, sv_next, s ^ 1);
     }
     float* sm = slot0 + (size_t)s * L.total;
     float* gZ = pol.Z + a * n;
     const float energy = __shfl_sync(0xffffffffu, sv, 7);
     __syncwarp();
+    if constexpr (RW > 0) {
+      // the agent's rays: wait for its round (normally long done), then its 32 distances are the observation
+      const uint32_t need = round + 1u;
+      volatile uint32_t* d = ray_done + (round % RW);
+      while (*d < need) __nanosleep(256);
+      __threadfence_block();
+      sm[L.obs + lane] = *reinterpret_cast<const volatile float*>(sense.dist + a * 32 + lane);
+    }
     if (tx) {
       mbar_wait(bars + s, parity[s]);
       parity[s] ^= 1u;
@@ -318,13 +420,14 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
     if (slots == 1) {
       if (a_next < n_agents) {
         sv_next = issue(a_next, 0);
-        if (sense.enabled) cast_rays(a_next, sv_next, 0);
+        if (RW == 0 && sense.enabled) cast_rays(a_next, sv_next, 0);
       }
     } else {
       s ^= 1;
     }
     a = a_next;
     sv = sv_next;
+    round = round_next;
   }
 }
 
@@ -553,7 +656,30 @@ static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p
   while (warps > 1 && head + warps * per_warp > budget) --warps;
   FGX_REQUIRE(head + warps * per_warp <= 227 * 1024,
               "%s: policy too large for shared memory (%zu bytes per agent)", what, per_warp);
-  const size_t smem = head + warps * per_warp;
+  size_t smem = head + warps * per_warp;
+  // FGX_K2_EVICT_FIRST=0 switches the L2 evict-first hint of the weight copies off (A/B hook, see profiles/)
+  static const int evict_first = [] { const char* v = getenv("FGX_K2_EVICT_FIRST"); return v && atoi(v) == 0 ? 0 : 1; }();
+  if constexpr (NOBS == 33) {
+    // warp-specialised fused sensing (sense.enabled == 2): RW ray warps beside the 8 step warps of every CTA
+    if (sense.enabled == 2 && warps == FS_WARPS && slots == 1 && n < (1ll << 27)) {
+      const char* rw_env = getenv("FGX_SENSE_RW");
+      // 2 or 4 ray warps per CTA (registers are allotted per 4 warps: 3 would cost what 4 do); default 4
+      const int rw = rw_env && atoi(rw_env) == 2 ? 2 : 4;
+      const size_t smem_f = smem + rw * sizeof(RaySmem) + 16;
+      auto launch = [&](auto kern_f) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern_f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+        if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_f, (FS_WARPS + rw) * 32, smem_f);
+        if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int64_t need = ceil_div(n, FS_WARPS), cap = (int64_t)sm_count() * per_sm;
+        kern_f<<<(int)(need < cap ? need : cap), (FS_WARPS + rw) * 32, smem_f, s>>>(
+            p, n, active, obs, energy_in, st, pol, age, actions, slots | (evict_first << 8), sense);
+        return check_launch(what);
+      };
+      return rw == 4 ? launch(forager_step_kernel<NN, NOBS, NACT, 4>) : launch(forager_step_kernel<NN, NOBS, NACT, 2>);
+    }
+  }
   auto kern = forager_step_kernel<NN, NOBS, NACT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -562,8 +688,6 @@ static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div(n, warps);
   const int64_t cap = (int64_t)sm_count() * per_sm;
-  // FGX_K2_EVICT_FIRST=0 switches the L2 evict-first hint of the weight copies off (A/B hook, see profiles/)
-  static const int evict_first = [] { const char* v = getenv("FGX_K2_EVICT_FIRST"); return v && atoi(v) == 0 ? 0 : 1; }();
   kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
                                                               slots | (evict_first << 8), sense);
   return check_launch(what);
@@ -630,13 +754,19 @@ int fgx_forager_sense_step(const fgx_forager_params_t* p, int64_t n, const float
   if (rc != FGX_OK) return rc;
   if (n == 0) return FGX_OK;
   FGX_REQUIRE(active_state && energy_in && age && dist, "fgx_forager_sense_step: null pointer");
-  sense.enabled = 1;
+  // mode 2 (default when it applies: 32 rays, the 40 / 33 / 2 policy): ray warps beside the step warps of every CTA;
+  // mode 1 (FGX_SENSE_STEP_MODE=1, or any other shape): the warp that steps an agent casts its rays first
+  const char* mode_env = getenv("FGX_SENSE_STEP_MODE");  // read per call (tests switch it)
+  const bool specialised = !(mode_env && atoi(mode_env) == 1) && n_rays == 32 && p->n_neurons == 40 && p->n_obs == 33 && p->n_act == 2 &&
+                           n < (1ll << 27) && !getenv("FGX_FS_SLOTS");
+  sense.enabled = specialised ? 2 : 1;
   sense.n_rays = n_rays;
   sense.span = ray_span;
   sense.L = ray_length;
   sense.dist = dist;
   sense.hit = hit;
-  fill_inactive_rays_kernel<<<grid_for(n * n_rays, 256, 8), 256, 0, s>>>(n, n_rays, active_state, dist, hit);
+  // mode 1 visits active agents only; the ray warps of mode 2 write the rows of inactive agents themselves
+  if (!specialised) fill_inactive_rays_kernel<<<grid_for(n * n_rays, 256, 8), 256, 0, s>>>(n, n_rays, active_state, dist, hit);
   return launch_forager_step("fgx_forager_sense_step", *p, n, active_state, nullptr, energy_in, *state, *policy, age,
                              nullptr, s, sense);
 }

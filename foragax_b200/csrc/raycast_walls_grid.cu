@@ -213,141 +213,40 @@ __global__ void __launch_bounds__(256, MINB) raycast_walls_grid_kernel(const Wal
 // walls_pretest_skip; the line band condition is per agent and is evaluated once, by the lane that owns the wall.
 constexpr int WGW_WARPS = 8;
 
-__device__ __forceinline__ float warp_min_f32(float v) {
-  float r;
-  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
-}
-__device__ __forceinline__ float warp_max_f32(float v) {
-  float r;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
-}
-
-struct WgwTile {
-  float x, y, ang, act;
-  uint4 r0, r1;
-};
-constexpr uint32_t WGW_ALL_WALLS = 0xffffffffu;  // cell record count: take the all-walls loop (outside the grid / fallback)
-
-__device__ __forceinline__ void wgw_load_pose(const WallsGridArgs& a, uint32_t end, uint32_t agent, WgwTile& t) {
-  const bool valid = agent < end;
-  t.act = 0.0f; t.x = 0.0f; t.y = 0.0f; t.ang = 0.0f;
-  if (valid) {
-    t.act = a.aactive != nullptr ? __ldg(a.aactive + agent) : 1.0f;
-    t.x = __ldg(a.ax + agent); t.y = __ldg(a.ay + agent); t.ang = __ldg(a.aang + agent);
-  }
-}
-__device__ __forceinline__ void wgw_load_rec(const WallsGridView& v, bool fallback, WgwTile& t) {
-  t.r0 = make_uint4(0u, 0u, 0u, 0u);
-  t.r1 = make_uint4(0u, 0u, 0u, 0u);
-  if (t.act == 0.0f) return;
-  const float fx = (t.x - v.g.x0) * v.g.inv_cs, fy = (t.y - v.g.y0) * v.g.inv_cs;  // as walls_grid_cast
-  const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
-  if (inside && !fallback) {
-    const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
-    t.r0 = __ldg(v.cellrec + 2 * (int64_t)cell);
-    t.r1 = __ldg(v.cellrec + 2 * (int64_t)cell + 1);
-  } else {
-    t.r0.y = WGW_ALL_WALLS;
-  }
-}
-
 template <int MINB>
 __global__ void __launch_bounds__(32 * WGW_WARPS, MINB)
     raycast_walls_grid_warp32_kernel(const WallsGridArgs a, uint32_t n_agents, uint32_t tile, uint32_t n_tiles) {
-  __shared__ float4 s_pose[WGW_WARPS][32];
-  __shared__ uint32_t s_rec[WGW_WARPS][32][8];
-  __shared__ float4 s_bb[WGW_WARPS][32];
-  __shared__ int2 s_w[WGW_WARPS][32];
+  __shared__ WgwTileSmem<32> s_tile[WGW_WARPS];
+  __shared__ WgwSurvSmem s_surv[WGW_WARPS];
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  WgwTileSmem<32>& sm = s_tile[wid];
   const float L = a.L, span = a.span;
   const WallsGridView& v = a.v;
   const bool fallback = v.st->fallback != 0;
-  // linspace(lo, hi, 32)[lane] = lo * (1 - s) + hi * s, s = lane / 31; the last element is hi (linspace_elem)
-  const float sj = __fdiv_rn((float)lane, 31.0f), omsj = f_sub(1.0f, sj);
+  float sj, omsj;
+  wgw_lane_weights(lane, sj, omsj);
   const uint32_t stride = gridDim.x * WGW_WARPS;
   uint32_t t = blockIdx.x * WGW_WARPS + wid;
   WgwTile nx;
   if (t < n_tiles) {
-    wgw_load_pose(a, min(n_agents, (t + 1u) * tile), t * tile + lane, nx);
+    wgw_load_pose(a.ax, a.ay, a.aang, a.aactive, min(n_agents, (t + 1u) * tile), t * tile + lane, nx);
     wgw_load_rec(v, fallback, nx);
   }
   for (; t < n_tiles; t += stride) {
     const uint32_t base = t * tile;
     const uint32_t cnt = min(tile, n_agents - base);
-    s_pose[wid][lane] = make_float4(nx.x, nx.y, nx.ang, nx.act);
-    *reinterpret_cast<uint4*>(&s_rec[wid][lane][0]) = nx.r0;
-    *reinterpret_cast<uint4*>(&s_rec[wid][lane][4]) = nx.r1;
+    wgw_park(sm, lane, nx);
     __syncwarp();
     const uint32_t tn = t + stride;
-    if (tn < n_tiles) wgw_load_pose(a, min(n_agents, (tn + 1u) * tile), tn * tile + lane, nx);
+    if (tn < n_tiles) wgw_load_pose(a.ax, a.ay, a.aang, a.aactive, min(n_agents, (tn + 1u) * tile), tn * tile + lane, nx);
     for (uint32_t k = 0; k < cnt; ++k) {
       if (k == (cnt >> 1) && tn < n_tiles) wgw_load_rec(v, fallback, nx);
-      const float4 pose = s_pose[wid][k];
       const uint32_t o = (base + k) * 32u + lane;
-      if (pose.w == 0.0f) {  // inactive agents sense nothing (sim.py:459-460)
-        a.dist[o] = 0.0f;
-        if (a.hit) a.hit[o] = -1;
-        continue;
-      }
-      const float p1x = pose.x, p1y = pose.y;
-      const uint2 hdr = *reinterpret_cast<const uint2*>(&s_rec[wid][k][0]);
-      const uint32_t e0 = hdr.x, n_list = hdr.y;
-      // the pre-test records of the first 32 listed walls are requested before the ray direction is computed (they
-      // depend on the cell only); lanes beyond the list repeat its last entry, an empty list reads wall 0's record
-      int w = (int)s_rec[wid][k][2u + min(lane, 5u)];
-      if (n_list > 6u && n_list != WGW_ALL_WALLS) w = __ldg(v.entries + e0 + min(lane, n_list - 1u));
-      float4 bb, ln;
-      {
-        const float4* __restrict__ r = v.wallr + 2 * (int64_t)w;
-        bb = __ldg(r);
-        ln = __ldg(r + 1);
-      }
-      // ray_generator (space_methods.py:56-69)
-      const float lo = f_sub(pose.z, span), hi = f_add(pose.z, span);
-      const float th = lane == 31u ? hi : f_add(f_mul(lo, omsj), f_mul(hi, sj));
-      float sn, cs;
-      sincosf(th, &sn, &cs);
-      const float q1x = f_add(p1x, f_mul(cs, L)), q1y = f_add(p1y, f_mul(sn, L));
-      float best = L;
-      int bidx = -1;
-      if (n_list == WGW_ALL_WALLS) {
-        walls_grid_cast(v, true, p1x, p1y, q1x, q1y, L, best, bidx);
-      } else if (n_list != 0u) {
-        const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
-        // union of the 32 ray boxes (x - m is monotone in x, so the reduction commutes with the widening)
-        const RayBox fb = RayBox{fminf(p1x, warp_min_f32(q1x)) - v.g.margin, fminf(p1y, warp_min_f32(q1y)) - v.g.margin,
-                                 fmaxf(p1x, warp_max_f32(q1x)) + v.g.margin, fmaxf(p1y, warp_max_f32(q1y)) + v.g.margin};
-        for (uint32_t u0 = 0;;) {
-          const bool have = u0 + lane < n_list;
-          const bool disjoint = bb.z < fb.x0 || bb.x > fb.x1 || bb.w < fb.y0 || bb.y > fb.y1;
-          const bool far = fabsf(fmaf(ln.x, p1x, fmaf(ln.y, p1y, ln.z))) > ln.w;
-          uint32_t m = __ballot_sync(0xffffffffu, have && !(disjoint && far));
-          if (m) {
-            s_bb[wid][lane] = bb;
-            s_w[wid][lane] = make_int2(w, far ? 1 : 0);
-            __syncwarp();
-            do {
-              const uint32_t src = 31u - (uint32_t)__clz(m);
-              m ^= 1u << src;
-              const float4 sb = s_bb[wid][src];
-              const int2 sw = s_w[wid][src];
-              const bool dj = sb.z < rb.x0 || sb.x > rb.x1 || sb.w < rb.y0 || sb.y > rb.y1;
-              if (dj && sw.y) continue;
-              const float4 wl = __ldg(v.wall4 + sw.x);
-              test_wall(p1x, p1y, q1x, q1y, L, wl.x, wl.y, wl.z, wl.w, sw.x, best, bidx);
-            } while (m);
-            __syncwarp();
-          }
-          u0 += 32u;
-          if (u0 >= n_list) break;
-          w = __ldg(v.entries + e0 + min(u0 + lane, n_list - 1u));
-          const float4* __restrict__ r = v.wallr + 2 * (int64_t)w;
-          bb = __ldg(r);
-          ln = __ldg(r + 1);
-        }
-      }
+      float best;
+      int bidx;
+      WgwPre pre;
+      wgw_prefetch(v, sm, k, lane, pre);
+      wgw_cast_agent(v, s_surv[wid], lane, L, span, sj, omsj, pre, best, bidx);
       a.dist[o] = best;
       if (a.hit) a.hit[o] = bidx;
     }

@@ -176,6 +176,164 @@ __device__ __forceinline__ void walls_grid_cast(const WallsGridView& v, float p1
   walls_grid_cast(v, v.st->fallback != 0, p1x, p1y, q1x, q1y, L, best, bidx);
 }
 
+// ---- n_rays == 32, warp-cooperative: a warp owns an agent (lane = ray) and walks its cell's wall list together ----
+// Used by raycast_walls_grid_warp32_kernel (raycast_walls_grid.cu, where the scheme is described) and by the
+// ray-casting warps of the fused sense + step kernel (foraging.cu).
+template <int TILE = 32>
+struct WgwTileSmem {  // per warp: a parked tile of up to TILE agents
+  float4 pose[TILE];      // x, y, ang, active
+  uint32_t rec[TILE][8];  // the agent's cell record {start, count, w0..w5}
+};
+struct WgwSurvSmem {  // per warp: the survivors of one pre-test trip
+  float4 bb[32];  // bounding box
+  float4 wl[32];  // end points
+  int2 w[32];     // {wall index, agent outside the wall's line band}
+};
+struct WgwTile {  // lane k's agent of a tile, in registers while its loads are in flight
+  float x, y, ang, act;
+  uint4 r0, r1;
+};
+constexpr uint32_t WGW_ALL_WALLS = 0xffffffffu;  // cell record count: take the all-walls loop (outside the grid / fallback)
+
+__device__ __forceinline__ float warp_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// linspace(lo, hi, 32)[lane] = lo * (1 - s) + hi * s, s = lane / 31; the last element is hi (linspace_elem)
+__device__ __forceinline__ void wgw_lane_weights(uint32_t lane, float& sj, float& omsj) {
+  sj = __fdiv_rn((float)lane, 31.0f);
+  omsj = f_sub(1.0f, sj);
+}
+// MUTABLE: the pose arrays are written by other warps of the running kernel (the fused sense + step kernel updates
+// positions in place, each agent after its own rays) -> coherent loads instead of the read-only path
+template <bool MUTABLE = false>
+__device__ __forceinline__ void wgw_load_pose(const float* ax, const float* ay, const float* aang, const float* aactive,
+                                              uint32_t end, uint32_t agent, WgwTile& t) {
+  t.act = 0.0f; t.x = 0.0f; t.y = 0.0f; t.ang = 0.0f;
+  if (agent < end) {
+    t.act = aactive != nullptr ? __ldg(aactive + agent) : 1.0f;
+    if (MUTABLE) {
+      t.x = __ldcg(ax + agent); t.y = __ldcg(ay + agent); t.ang = __ldcg(aang + agent);
+    } else {
+      t.x = __ldg(ax + agent); t.y = __ldg(ay + agent); t.ang = __ldg(aang + agent);
+    }
+  }
+}
+__device__ __forceinline__ void wgw_load_rec(const WallsGridView& v, bool fallback, WgwTile& t) {
+  t.r0 = make_uint4(0u, 0u, 0u, 0u);
+  t.r1 = make_uint4(0u, 0u, 0u, 0u);
+  if (t.act == 0.0f) return;
+  const float fx = (t.x - v.g.x0) * v.g.inv_cs, fy = (t.y - v.g.y0) * v.g.inv_cs;  // as walls_grid_cast
+  const bool inside = fx >= 0.0f && fy >= 0.0f && fx < (float)v.g.gx && fy < (float)v.g.gy;
+  if (inside && !fallback) {
+    const int cell = min((int)fy, v.g.gy - 1) * v.g.gx + min((int)fx, v.g.gx - 1);
+    t.r0 = __ldg(v.cellrec + 2 * (int64_t)cell);
+    t.r1 = __ldg(v.cellrec + 2 * (int64_t)cell + 1);
+  } else {
+    t.r0.y = WGW_ALL_WALLS;
+  }
+}
+template <class SM>
+__device__ __forceinline__ void wgw_park(SM& sm, uint32_t lane, const WgwTile& t, uint32_t tile = 32u) {
+  if (lane < tile) {
+    sm.pose[lane] = make_float4(t.x, t.y, t.ang, t.act);
+    *reinterpret_cast<uint4*>(&sm.rec[lane][0]) = t.r0;
+    *reinterpret_cast<uint4*>(&sm.rec[lane][4]) = t.r1;
+  }
+}
+
+// What an agent's cast needs from memory, requested ahead of its arithmetic: the pose and list header (shared
+// memory), and lane u's listed wall of the first 32 -- its index, pre-test record and end points (they depend on the
+// cell only).  Lanes beyond the list repeat its last entry, an empty list reads wall 0's records.
+struct WgwPre {
+  float4 pose;
+  uint32_t e0, n_list;
+  int w;
+  float4 bb, ln, wl;
+};
+template <class SM>
+__device__ __forceinline__ void wgw_prefetch(const WallsGridView& v, const SM& sm, uint32_t k, uint32_t lane, WgwPre& p) {
+  p.pose = sm.pose[k];
+  const uint2 hdr = *reinterpret_cast<const uint2*>(&sm.rec[k][0]);
+  p.e0 = hdr.x;
+  p.n_list = hdr.y;
+  if (p.pose.w == 0.0f) return;
+  int w = (int)sm.rec[k][2u + min(lane, 5u)];
+  if (p.n_list > 6u && p.n_list != WGW_ALL_WALLS) w = __ldg(v.entries + p.e0 + min(lane, p.n_list - 1u));
+  const float4* __restrict__ r = v.wallr + 2 * (int64_t)w;
+  p.w = w;
+  p.bb = __ldg(r);
+  p.ln = __ldg(r + 1);
+  p.wl = __ldg(v.wall4 + w);
+}
+
+// ray `lane` of the prefetched agent: min / first-argmin over the walls (best = 0, bidx = -1 for an inactive
+// agent: sim.py:459-460).  Must be called by all 32 lanes.
+__device__ __forceinline__ void wgw_cast_agent(const WallsGridView& v, WgwSurvSmem& sm, uint32_t lane, float L, float span,
+                                               float sj, float omsj, const WgwPre& p, float& best, int& bidx) {
+  bidx = -1;
+  if (p.pose.w == 0.0f) {
+    best = 0.0f;
+    return;
+  }
+  best = L;
+  const float p1x = p.pose.x, p1y = p.pose.y;
+  const uint32_t n_list = p.n_list;
+  // ray_generator (space_methods.py:56-69)
+  const float lo = f_sub(p.pose.z, span), hi = f_add(p.pose.z, span);
+  const float th = lane == 31u ? hi : f_add(f_mul(lo, omsj), f_mul(hi, sj));
+  float sn, cs;
+  sincosf(th, &sn, &cs);
+  const float q1x = f_add(p1x, f_mul(cs, L)), q1y = f_add(p1y, f_mul(sn, L));
+  if (n_list == WGW_ALL_WALLS) {
+    walls_grid_cast(v, true, p1x, p1y, q1x, q1y, L, best, bidx);
+  } else if (n_list != 0u) {
+    const RayBox rb = ray_box(p1x, p1y, q1x, q1y, v.g.margin);
+    // union of the 32 ray boxes (x - m is monotone in x, so the reduction commutes with the widening)
+    const RayBox fb = RayBox{fminf(p1x, warp_min_f32(q1x)) - v.g.margin, fminf(p1y, warp_min_f32(q1y)) - v.g.margin,
+                             fmaxf(p1x, warp_max_f32(q1x)) + v.g.margin, fmaxf(p1y, warp_max_f32(q1y)) + v.g.margin};
+    int w = p.w;
+    float4 bb = p.bb, ln = p.ln, wl = p.wl;
+    for (uint32_t u0 = 0;;) {
+      const bool have = u0 + lane < n_list;
+      const bool disjoint = bb.z < fb.x0 || bb.x > fb.x1 || bb.w < fb.y0 || bb.y > fb.y1;
+      const bool far = fabsf(fmaf(ln.x, p1x, fmaf(ln.y, p1y, ln.z))) > ln.w;
+      uint32_t m = __ballot_sync(0xffffffffu, have && !(disjoint && far));
+      if (m) {
+        sm.bb[lane] = bb;
+        sm.wl[lane] = wl;
+        sm.w[lane] = make_int2(w, far ? 1 : 0);
+        __syncwarp();
+        do {
+          const uint32_t src = 31u - (uint32_t)__clz(m);
+          m ^= 1u << src;
+          const float4 sb = sm.bb[src];
+          const int2 sw = sm.w[src];
+          const bool dj = sb.z < rb.x0 || sb.x > rb.x1 || sb.w < rb.y0 || sb.y > rb.y1;
+          if (dj && sw.y) continue;
+          const float4 swl = sm.wl[src];
+          test_wall(p1x, p1y, q1x, q1y, L, swl.x, swl.y, swl.z, swl.w, sw.x, best, bidx);
+        } while (m);
+        __syncwarp();
+      }
+      u0 += 32u;
+      if (u0 >= n_list) break;
+      w = __ldg(v.entries + p.e0 + min(u0 + lane, n_list - 1u));
+      const float4* __restrict__ r = v.wallr + 2 * (int64_t)w;
+      bb = __ldg(r);
+      ln = __ldg(r + 1);
+      wl = __ldg(v.wall4 + w);
+    }
+  }
+}
+
 // host side (raycast_walls_grid.cu): validates, carves the scratch and -- unless reuse_grid -- builds the wall
 // lists on `stream`; fills `view`.  Returns an fgx status code.
 size_t wall_grid_scratch_bytes(int64_t n_walls, float x_min, float x_max, float y_min, float y_max, float ray_length);

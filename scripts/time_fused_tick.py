@@ -12,9 +12,9 @@ from foragax_b200.base.agent_methods import step_agents  # noqa: E402
 from foragax_b200.examples.foraging import Forager  # noqa: E402
 
 dev = torch.device("cuda", 0)
-work = bench.make_workload()
-fset, space = bench.build_foragers(work, 0, 1, dev)
-n = bench.N_AGENTS
+n = int(os.environ.get("N", bench.N_AGENTS))
+work = bench.make_workload(n)
+fset, space = bench.build_foragers(work, 0, 1, dev, n_agents=n)
 st = fset.agents.state.content
 out = (torch.empty((n, bench.N_RAYS), device=dev), torch.empty((n, bench.N_RAYS), dtype=torch.int32, device=dev))
 energy_in = torch.zeros(n, device=dev)
@@ -76,5 +76,5 @@ def t(fn, k=20):
     return e0.elapsed_time(e1) / k
 
 
-print(f"two kernels {t(two):.3f} ms per tick, fused {t(fused):.3f} ms per tick, "
+print(f"n = {n}: two kernels {t(two):.3f} ms per tick, fused {t(fused):.3f} ms per tick, "
       f"pipelined over {CHUNKS} chunks on two streams {t(pipelined):.3f} ms per tick")

@@ -338,6 +338,48 @@ def test_churn_world_matches_oracle(cuda, n):
     assert 0 < int(n_act) <= n  # the count before the add of the last tick
 
 
+def test_churn_world_graph_replay_matches_oracle(cuda):
+    """ChurnWorld.capture_two_ticks: the sort alternates between two fixed buffer sets (sort_agents(out=)), two ticks
+    are one CUDA graph; after 2 warm-up ticks and k replays the state equals 2 + 2k oracle ticks leaf by leaf."""
+    import functools
+    from foragax_b200.examples.churn import ChurnWorld
+    n = 120_011
+    w = ChurnWorld(n, sides=20, n_active=n // 2, key=None)
+    ref = oam.create_agents(functools.partial(odice.create_agent, sides=20), None, n, n // 2, 0, jr.PRNGKey(0))
+    graph = w.capture_two_ticks()
+    for _ in range(2):
+        ref = odice.churn_tick(ref, n, 20)
+    assert_same(w.agents, ref)  # capturing does not execute
+    for _ in range(3):
+        graph.replay()
+        for _ in range(2):
+            ref = odice.churn_tick(ref, n, 20)
+        torch.cuda.synchronize()
+        assert_same(w.agents, ref)
+    # an eager tick after the replays continues from the same state (and flips the buffer sets)
+    w.tick()
+    assert_same(w.agents, odice.churn_tick(ref, n, 20))
+
+
+def test_sort_agents_out_buffers(cuda):
+    """sort_agents(out=): rows land in the caller's buffers, bit-identical to the fresh-buffer call; misuse raises."""
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200 import struct
+    from foragax_b200._lib import FgxError
+    from foragax_b200.examples.churn import ChurnWorld
+    w = ChurnWorld(50_003, sides=6, n_active=20_000, key=None)
+    w.tick()
+    ag = w.agents
+    want, perm = fgx_methods.jit_sort_agents(ag.active_state, False, ag)
+    out = struct.tree_map(torch.empty_like, ag)
+    got, perm2 = fgx_methods.jit_sort_agents(ag.active_state, False, ag, out=out)
+    assert torch.equal(perm, perm2)
+    for a, b, c in zip(struct.tree_leaves(want), struct.tree_leaves(got), struct.tree_leaves(out)):
+        assert torch.equal(a, b) and b.data_ptr() == c.data_ptr()
+    with pytest.raises(FgxError):
+        fgx_methods.jit_sort_agents(ag.active_state, False, ag, out=ag)
+
+
 @pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 100_003, 2_000_001])
 def test_count_active_and_clip(cuda, n):
     """fgx_count_active / fgx_count_active_clip (agent_methods.py:27 + README.md:124-125): float4 body + scalar tail,

@@ -195,11 +195,14 @@ def test_cuda_graph_replay_equals_eager_ticks(cuda):
         fg.use_variant("sim")
 
 
-def test_fused_sense_step_equals_raycast_then_step(cuda):
-    """fgx_forager_sense_step (rays cast inside the step kernel, distances fed to the policy from shared memory)
-    must give the same bits as fgx_raycast_walls_grid followed by fgx_forager_step: distances, hit indices and
-    every state / policy leaf, over several ticks, with inactive agents and agents outside the bounds."""
-    import copy
+@pytest.mark.parametrize("mode", ["specialised-2", "specialised-4", "same-warp"])
+def test_fused_sense_step_equals_raycast_then_step(cuda, mode, monkeypatch):
+    """fgx_forager_sense_step must give the same bits as fgx_raycast_walls_grid followed by fgx_forager_step:
+    distances, hit indices and every state / policy leaf, over several ticks, with inactive agents and agents
+    outside the bounds.  Modes: ray warps beside the step warps of every CTA (2 or 4 of them; rounds published
+    through shared-memory flags), and the older variant where the warp that steps an agent casts its rays first."""
+    monkeypatch.setenv("FGX_SENSE_STEP_MODE", "1" if mode == "same-warp" else "2")
+    monkeypatch.setenv("FGX_SENSE_RW", "4" if mode.endswith("4") else "2")
 
     import bench
     from foragax_b200.base.agent_classes import Params, Signal
