@@ -421,6 +421,7 @@ def run_ours(args):
     from foragax_b200 import distributed as fd
     from foragax_b200.base.agent_classes import Params, Signal
     from foragax_b200.base.agent_methods import step_agents
+    from foragax_b200.examples.foraging import Forager
 
     work = make_workload()
     mine = slice(rank, None, world)  # round-robin sharding by slot index
@@ -450,9 +451,19 @@ def run_ours(args):
     def k2():
         fset.agents = step_agents(step_params, step_input, fset)
 
-    def tick():
+    def tick_two():
         k1()
         k2()
+
+    def tick_fused():
+        # the same tick as ONE kernel: fgx_forager_sense_step -- four ray-casting warps beside the eight step warps of
+        # every CTA; same bits as k1 + k2 (parity block below, tests/test_gpu_foraging.py)
+        Forager.sense_step(step_params, energy_in, fset.agents, space.walls, BOUNDS, RAY_SPAN, RAY_LEN,
+                           out=(dist_out, hit_out))
+
+    fused = not args.two_kernel_tick
+    tick = tick_fused if fused else tick_two
+    launches_per_step = 1 if fused else 2
 
     peer_positions = None
     if world > 1 and not args.no_agent_sensing and not args.nccl_positions:
@@ -518,11 +529,34 @@ def run_ours(args):
             sense()
             dg["agent_sensing_dist"] = digest(dist_out)
             dg["agent_sensing_hit"] = digest(hit_out)
+        other_dg = None
+        other_name = "two_kernel" if fused else "fused"
+        if not args.no_other_tick:
+            # the same PARITY_TICKS ticks through the OTHER form of the tick (two kernels: fgx_raycast_walls_grid +
+            # fgx_forager_step / one kernel: fgx_forager_sense_step) on a second set built from the same seed: its
+            # digests must equal the same golden
+            fset2, _ = build_foragers(work, rank, world, dev)
+            d2, h2 = torch.empty_like(dist_out), torch.empty_like(hit_out)
+            s2 = fset2.agents.state.content
+            for _ in range(PARITY_TICKS):
+                if fused:
+                    sm.raycast_walls((s2["X"], s2["Y"], s2["ang"]), RAY_SPAN, RAY_LEN, space.walls,
+                                     active_state=fset2.agents.active_state, n_rays=N_RAYS, out=(d2, h2), bounds=BOUNDS)
+                    fset2.agents = step_agents(step_params, Signal(content={'obs': d2, 'energy_in': energy_in}), fset2)
+                else:
+                    Forager.sense_step(step_params, energy_in, fset2.agents, space.walls, BOUNDS, RAY_SPAN, RAY_LEN,
+                                       out=(d2, h2))
+            other_dg = {"dist": digest(d2), "hit": digest(h2), "X": digest(s2["X"]),
+                        "Z": digest(fset2.agents.policy.state.content["Z"])}
+            del fset2, d2, h2, s2
+            torch.cuda.empty_cache()
         if rank == 0:
             golden = json.load(open(PARITY_GOLDEN)) if os.path.exists(PARITY_GOLDEN) else None
             same = None
             if golden:
                 same = {k: (golden["sha256"].get(k) == v) for k, v in dg.items()}
+                if other_dg:
+                    same.update({other_name + "_" + k: (golden["sha256"].get(k) == v) for k, v in other_dg.items()})
             parity = {"ticks": PARITY_TICKS, "order": "global slot order (round-robin shards un-interleaved)",
                       "sha256": dg, "golden": "tests/golden/bench_parity_digest.json (1-GPU run)" if golden else None,
                       "equals_1gpu_golden": same, "all_equal": (all(same.values()) if same else None),
@@ -583,6 +617,20 @@ def run_ours(args):
         ap_tick.append(ev[0].elapsed_time(ev[2]))
     ap_k1_ms, ap_tick_ms = max_over_ranks(float(np.mean(ap_k1))), max_over_ranks(float(np.mean(ap_tick)))
 
+    # the other form of the tick, timed the same way as the default one
+    other_ms = None
+    if not args.no_other_tick:
+        other_tick = tick_two if fused else tick_fused
+        for _ in range(3):
+            other_tick()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            other_tick()
+        e1.record(stream)
+        barrier()
+        other_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
     # end to end through the public API with HOST buffers: every step copies the agents' pose and active
     # flags from pinned host memory (H2D), runs the tick and reads back its result (ray distances, hit
     # indices and the stepped positions, D2H).  The result read-back of step i runs on a side stream
@@ -612,9 +660,12 @@ def run_ours(args):
         if i >= 2:
             stream.wait_event(ev_out[b])      # this output buffer's previous read-back has landed
         d_o, h_o = outs[b]
-        sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
-                         n_rays=N_RAYS, out=(d_o, h_o), bounds=BOUNDS)
-        fset.agents = step_agents(step_params, Signal(content={'obs': d_o, 'energy_in': energy_in}), fset)
+        if fused:
+            Forager.sense_step(step_params, energy_in, fset.agents, space.walls, BOUNDS, RAY_SPAN, RAY_LEN, out=(d_o, h_o))
+        else:
+            sm.raycast_walls((st["X"], st["Y"], st["ang"]), RAY_SPAN, RAY_LEN, space.walls, active_state=F.active_state,
+                             n_rays=N_RAYS, out=(d_o, h_o), bounds=BOUNDS)
+            fset.agents = step_agents(step_params, Signal(content={'obs': d_o, 'energy_in': energy_in}), fset)
         ev_done[b].record(stream)
         with torch.cuda.stream(side):
             side.wait_event(ev_done[b])
@@ -729,12 +780,32 @@ def run_ours(args):
         k2_bytes = K2_BYTES_ACTIVE * n_active_local + 4 * (n_local - n_active_local)
         k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        roof = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
-                "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
-                "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
-                "share_of_step": k2_ms / (k1_ms + k2_ms),
-                "frac_of_nominal_8tbs": k2_gbs / 8000.0,
-                "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
+        roof_k2 = {"bound": "hbm", "achieved": k2_gbs, "peak": hbm, "unit": "GB/s", "frac": k2_gbs / hbm,
+                   "traffic": measured_traffic("forager_step_kernel", n_local), "algorithmic_bytes": float(k2_bytes),
+                   "kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
+                   "share_of_step": k2_ms / (k1_ms + k2_ms),
+                   "frac_of_nominal_8tbs": k2_gbs / 8000.0,
+                   "bytes_per_active_agent": K2_BYTES_ACTIVE, "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json"}
+        if fused:
+            # one launch per step: the kernel's duration is the step's; its algorithmic bytes are the step kernel's
+            # (weights, policy state, scalars) plus the ray stage's (pose in, dist + hit out)
+            fk_bytes = k2_bytes + float(n_local) * 16 + float(n_local) * N_RAYS * 8
+            fk_gbs = fk_bytes / (ms_step * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": fk_gbs, "peak": hbm, "unit": "GB/s", "frac": fk_gbs / hbm,
+                    "traffic": measured_traffic("forager_sense_step_kernel", n_local),
+                    "algorithmic_bytes": float(fk_bytes),
+                    "kernel": "forager_step_kernel<40,33,2,RW=4> (fgx_forager_sense_step: 8 step warps + 4 ray-casting "
+                              "warps per CTA, 2 CTAs per SM)",
+                    "kernel_ms": ms_step, "share_of_step": 1.0, "frac_of_nominal_8tbs": fk_gbs / 8000.0,
+                    "bytes_per_active_agent": K2_BYTES_ACTIVE, "bytes_per_agent_ray_stage": 16 + 8 * N_RAYS,
+                    "peak_basis": f"hbm_gbs, {peak_src} MEASURED_PEAKS.json",
+                    "step_kernel_alone": {"kernel": "forager_step_kernel<40,33,2>", "kernel_ms": k2_ms,
+                                          "achieved": k2_gbs, "frac": k2_gbs / hbm,
+                                          "note": "the HBM-bound half of the two-kernel tick, timed in the same run "
+                                                  "(two_kernel_tick); the fused kernel hides the ray cast in its idle "
+                                                  "issue slots at the price of some of this fraction"}}
+        else:
+            roof = roof_k2
         # the culled ray cast against its two floors: bytes (pose in, dist + hit out) and instructions (the walls the
         # grid lists for the agents' cells x 16 executed FP32 ops per (ray, wall) + the output), not against its own
         # instruction count
@@ -764,9 +835,13 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents": N_AGENTS, "active_agents": int(0.9 * N_AGENTS), "rays": N_RAYS,
                        "walls": N_WALLS, "sharding": f"agents by slot index, round-robin over {world} rank(s), walls replicated",
-                       "tick": ["fgx_raycast_walls_grid (ray_generator + ray_wall_sensor + min/argmin over the walls a "
-                                "uniform grid lists for the agent's cell; results bit-identical to all-pairs)",
-                                "fgx_forager_step (WilsonCowan policy + physics)"],
+                       "tick": (["fgx_forager_sense_step = fgx_raycast_walls_grid (ray_generator + ray_wall_sensor + min/argmin "
+                                 "over the walls a uniform grid lists for the agent's cell; bit-identical to all-pairs) "
+                                 "and fgx_forager_step (WilsonCowan policy + physics) as ONE kernel; the two-kernel "
+                                 "form is timed in `two_kernel_tick`"] if fused else
+                                ["fgx_raycast_walls_grid (ray_generator + ray_wall_sensor + min/argmin over the walls a "
+                                 "uniform grid lists for the agent's cell; results bit-identical to all-pairs)",
+                                 "fgx_forager_step (WilsonCowan policy + physics)"]),
                        "value_counts": "agents x rays x walls per tick = algorithmic pairs (SURVEY.md 8d), all slots, "
                                        "whether or not the kernel culls them; see executed_tests_per_sec and all_pairs",
                        "l2": "per-step working set 11.6 GB of per-agent weights + 272 MB ray I/O >> 126 MB L2"},
@@ -785,6 +860,13 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if other_ms is not None:
+            line["two_kernel_tick" if fused else "fused_tick"] = {
+                "ms_per_step": other_ms, "value": tests_per_step / (other_ms * 1e-3), "unit": UNIT,
+                "agent_steps_per_sec": N_AGENTS / (other_ms * 1e-3), "default_tick_speedup": other_ms / ms_step,
+                "roofline": roof_k2 if fused else None,
+                "note": ("fgx_raycast_walls_grid + fgx_forager_step as two launches; same bits (parity.equals_1gpu_golden "
+                         "two_kernel_*)" if fused else "fgx_forager_sense_step: one launch; same bits")}
         if parity:
             line["parity"] = parity
         if agent_sensing:
@@ -838,6 +920,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=40_000, help="agents in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--two-kernel-tick", action="store_true",
+                    help="time fgx_raycast_walls_grid + fgx_forager_step as the tick (default: the one-kernel fgx_forager_sense_step)")
+    ap.add_argument("--no-other-tick", action="store_true", help="skip the leg / parity digests of the other tick form")
     ap.add_argument("--no-agent-sensing", action="store_true", help="skip the extra agent-agent sensing stage")
     ap.add_argument("--nccl-positions", action="store_true",
                     help="agent sensing at N > 1: exchange positions with an NCCL all-gather instead of peer memory")

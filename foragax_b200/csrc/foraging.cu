@@ -100,23 +100,28 @@ __device__ __forceinline__ uint32_t leaf_tma_bytes(const float* base, int row_fl
 
 // Iterator over the ACTIVE agents of this warp's sequence a0, a0+GW, a0+2GW, ...: one coalesced
 // probe of 32 candidates (ballot) serves up to 32 agents, so inactive runs cost nothing per slot.
+// ROUNDS: also track `round`, the index of the returned agent in the warp's sequence (the fused kernel's step warps
+// wait for the ray warps by round)
+template <bool ROUNDS>
 struct ActiveScan {
   int64_t base, probe_base;
   unsigned mask;
-  uint32_t next_round = 0u, probe_round = 0u, round = 0u;  // round = index of the returned agent in the warp's sequence
+  uint32_t next_round = 0u, probe_round = 0u, round = 0u;
   __device__ __forceinline__ int64_t next(const float* __restrict__ active, int64_t GW, int64_t n_agents, int lane) {
     while (mask == 0u) {
       if (base >= n_agents) return n_agents;
       const int64_t mine = base + lane * GW;
       mask = __ballot_sync(0xffffffffu, mine < n_agents && active[mine] != 0.0f);
       probe_base = base;
-      probe_round = next_round;
       base += 32 * GW;
-      next_round += 32u;
+      if (ROUNDS) {
+        probe_round = next_round;
+        next_round += 32u;
+      }
     }
     const int b = __ffs(mask) - 1;
     mask &= mask - 1u;
-    round = probe_round + (uint32_t)b;
+    if (ROUNDS) round = probe_round + (uint32_t)b;
     return probe_base + (int64_t)b * GW;
   }
 };
@@ -182,6 +187,8 @@ __device__ __forceinline__ void ray_warps_role(const SenseArgs& sense, const fgx
     const uint32_t base_n = first + jn * GW;
     const bool more = jn < rounds;
     if (more) wgw_load_pose<true>(st.X, st.Y, st.ang, active, min(n, base_n + FS_WARPS), base_n + lane, nx);
+    // (an L2 bulk prefetch of the next agent's J / E rows by the step warps, cp.async.bulk.prefetch.L2 a turn ahead, was
+    // measured here: fused 2.21 -> 2.25 ms, plain step kernel 2.00 -> 2.11 ms -- rejected)
 #pragma unroll 1  // one copy of the per-agent code: eight would push the step warps' loop out of the instruction cache
     for (uint32_t k = 0; k < cnt; ++k) {
       // next tile: cell records requested a quarter into this tile, parked three quarters in, so that ...
@@ -210,9 +217,10 @@ __device__ __forceinline__ void ray_warps_role(const SenseArgs& sense, const fgx
 
 // NN / NOBS / NACT > 0 fix the policy shape at compile time (constant trip counts, immediate
 // shared-memory offsets, no shape branches); 0 = read it from the params (any shape).
-// RW > 0: RW more warps per CTA cast the rays (ray_warps_role above); two CTAs per SM then cap the kernel at 96 registers.
+// RW > 0: RW more warps per CTA cast the rays (ray_warps_role above); two CTAs per SM then cap the registers.
+// RW == -1: the warp that steps an agent casts its rays itself (the older fused mode).  RW == 0: no sensing code at all.
 template <int NN, int NOBS, int NACT, int RW = 0>
-__global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
+__global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
     forager_step_kernel(const fgx_forager_params_t p, int64_t n_agents, const float* __restrict__ active,
                         const float* __restrict__ obs_in, const float* __restrict__ energy_in,
                         const fgx_forager_state_t st, const fgx_wc_policy_t pol, float* __restrict__ age,
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
   const uint32_t bJ = leaf_tma_bytes(pol.J, n * n), bE = leaf_tma_bytes(pol.E, n * nobs),
                  bD = leaf_tma_bytes(pol.D, nact * n), bT = leaf_tma_bytes(pol.tau, n),
                  bB = leaf_tma_bytes(pol.B, n), bZ = leaf_tma_bytes(pol.Z, n),
-                 bO = sense.enabled ? 0u : leaf_tma_bytes(obs_in, obs_cols);
+                 bO = RW != 0 ? 0u : leaf_tma_bytes(obs_in, obs_cols);
   const uint32_t tx = bJ + bE + bD + bT + bB + bZ + bO;
 
   // lane l < 11 owns state leaf l of an agent, lane 11 its age, lane 12 its energy_in: the scalars are
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
     if (!bT) for (int i = lane; i < n; i += 32) sm[L.tau + i] = __ldg(gT + i);
     if (!bB) for (int i = lane; i < n; i += 32) sm[L.B + i] = __ldg(gB + i);
     if (!bZ) for (int i = lane; i < n; i += 32) sm[L.Z + i] = gZ[i];
-    if (!bO && !sense.enabled) for (int k = lane; k < obs_cols; k += 32) sm[L.obs + k] = __ldg(gO + k);
+    if (RW == 0 && !bO) for (int k = lane; k < obs_cols; k += 32) sm[L.obs + k] = __ldg(gO + k);
     return my_leaf ? my_leaf[a] : 0.0f;
   };
   // ray_generator + ray_wall_sensor + min / argmin for agent g (pose in the scalars `svv` just fetched), one lane
@@ -319,14 +327,14 @@ __global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
   };
 
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
-  ActiveScan scan{gw, gw, 0u};
+  ActiveScan<(RW > 0)> scan{gw, gw, 0u};
   int64_t a = scan.next(active, GW, n_agents, lane);
   int s = 0;
   float sv = 0.0f;
   uint32_t round = scan.round;
   if (a < n_agents) {
     sv = issue(a, 0);
-    if (RW == 0 && sense.enabled) cast_rays(a, sv, 0);
+    if constexpr (RW == -1) cast_rays(a, sv, 0);
   }
   while (a < n_agents) {
     const int64_t a_next = scan.next(active, GW, n_agents, lane);
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
     float sv_next = 0.0f;
     if (slots == 2 && a_next < n_agents) {  // slot s^1 was released by the last __syncwarp
       sv_next = issue(a_next, s ^ 1);
-      if (RW == 0 && sense.enabled) cast_rays(a_next, sv_next, s ^ 1);
+      if constexpr (RW == -1) cast_rays(a_next, sv_next, s ^ 1);
     }
     float* sm = slot0 + (size_t)s * L.total;
     float* gZ = pol.Z + a * n;
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__((FS_WARPS + RW) * 32, RW ? 2 : 0)
     if (slots == 1) {
       if (a_next < n_agents) {
         sv_next = issue(a_next, 0);
-        if (RW == 0 && sense.enabled) cast_rays(a_next, sv_next, 0);
+        if constexpr (RW == -1) cast_rays(a_next, sv_next, 0);
       }
     } else {
       s ^= 1;
@@ -680,17 +688,21 @@ static int launch_forager_step_t(const char* what, const fgx_forager_params_t& p
       return rw == 4 ? launch(forager_step_kernel<NN, NOBS, NACT, 4>) : launch(forager_step_kernel<NN, NOBS, NACT, 2>);
     }
   }
-  auto kern = forager_step_kernel<NN, NOBS, NACT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
-  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int64_t need = ceil_div(n, warps);
-  const int64_t cap = (int64_t)sm_count() * per_sm;
-  kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
-                                                              slots | (evict_first << 8), sense);
-  return check_launch(what);
+  auto launch_plain = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t need = ceil_div(n, warps);
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    kern<<<(int)(need < cap ? need : cap), warps * 32, smem, s>>>(p, n, active, obs, energy_in, st, pol, age, actions,
+                                                                slots | (evict_first << 8), sense);
+    return check_launch(what);
+  };
+  // the sensing code lives in its own instantiation (RW = -1): the plain step kernel carries none of it
+  return sense.enabled ? launch_plain(forager_step_kernel<NN, NOBS, NACT, -1>)
+                       : launch_plain(forager_step_kernel<NN, NOBS, NACT, 0>);
 }
 
 static int launch_forager_step(const char* what, const fgx_forager_params_t& p, int64_t n, const float* active,
