@@ -461,7 +461,7 @@ def run_ours(args):
         Forager.sense_step(step_params, energy_in, fset.agents, space.walls, BOUNDS, RAY_SPAN, RAY_LEN,
                            out=(dist_out, hit_out))
 
-    fused = not args.two_kernel_tick
+    fused = args.fused_tick
     tick = tick_fused if fused else tick_two
     launches_per_step = 1 if fused else 2
 
@@ -866,7 +866,16 @@ def run_ours(args):
                 "agent_steps_per_sec": N_AGENTS / (other_ms * 1e-3), "default_tick_speedup": other_ms / ms_step,
                 "roofline": roof_k2 if fused else None,
                 "note": ("fgx_raycast_walls_grid + fgx_forager_step as two launches; same bits (parity.equals_1gpu_golden "
-                         "two_kernel_*)" if fused else "fgx_forager_sense_step: one launch; same bits")}
+                         "two_kernel_*)" if fused else
+                         "fgx_forager_sense_step: the same tick as ONE launch -- 4 ray-casting warps beside the 8 step "
+                         "warps of every CTA (forager_step_kernel<40,33,2,RW=4>); same bits (parity.equals_1gpu_golden "
+                         "fused_*)")}
+            tick_bytes = float(k2_bytes) + rc_bytes
+            line["tick_frac_of_hbm"] = {
+                "algorithmic_bytes_per_tick": tick_bytes,
+                "two_kernel": tick_bytes / ((other_ms if fused else ms_step) * 1e-3) / 1e9 / hbm,
+                "fused": tick_bytes / ((ms_step if fused else other_ms) * 1e-3) / 1e9 / hbm,
+                "note": "whole tick (step kernel's bytes + pose in / dist + hit out of the ray stage) against measured HBM"}
         if parity:
             line["parity"] = parity
         if agent_sensing:
@@ -920,8 +929,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=40_000, help="agents in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--two-kernel-tick", action="store_true",
-                    help="time fgx_raycast_walls_grid + fgx_forager_step as the tick (default: the one-kernel fgx_forager_sense_step)")
+    ap.add_argument("--fused-tick", action="store_true",
+                    help="time the one-kernel fgx_forager_sense_step as the tick (default: fgx_raycast_walls_grid + "
+                         "fgx_forager_step, two launches; the other form is always timed as a leg)")
     ap.add_argument("--no-other-tick", action="store_true", help="skip the leg / parity digests of the other tick form")
     ap.add_argument("--no-agent-sensing", action="store_true", help="skip the extra agent-agent sensing stage")
     ap.add_argument("--nccl-positions", action="store_true",

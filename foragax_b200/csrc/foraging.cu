@@ -332,6 +332,8 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
   int s = 0;
   float sv = 0.0f;
   uint32_t round = scan.round;
+  [[maybe_unused]] float obs_cur = 0.0f;
+  [[maybe_unused]] bool have_cur = false;
   if (a < n_agents) {
     sv = issue(a, 0);
     if constexpr (RW == -1) cast_rays(a, sv, 0);
@@ -340,6 +342,17 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
     const int64_t a_next = scan.next(active, GW, n_agents, lane);
     const uint32_t round_next = scan.round;
     float sv_next = 0.0f;
+    // the NEXT agent's observation, requested a whole turn ahead when its rays are already done (the usual case: the
+    // ray warps run ahead), so that the L2 round trip of the 128-byte row is off the warp's critical path
+    [[maybe_unused]] float obs_ahead = 0.0f;
+    [[maybe_unused]] bool have_ahead = false;
+    if constexpr (RW > 0) {
+      if (a_next < n_agents && ray_done[round_next % RW] > round_next) {  // warp-uniform: one shared-memory word
+        __threadfence_block();
+        obs_ahead = *reinterpret_cast<const volatile float*>(sense.dist + a_next * 32 + lane);
+        have_ahead = true;
+      }
+    }
     if (slots == 2 && a_next < n_agents) {  // slot s^1 was released by the last __syncwarp
       sv_next = issue(a_next, s ^ 1);
       if constexpr (RW == -1) cast_rays(a_next, sv_next, s ^ 1);
@@ -349,12 +362,16 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
     const float energy = __shfl_sync(0xffffffffu, sv, 7);
     __syncwarp();
     if constexpr (RW > 0) {
-      // the agent's rays: wait for its round (normally long done), then its 32 distances are the observation
-      const uint32_t need = round + 1u;
-      volatile uint32_t* d = ray_done + (round % RW);
-      while (*d < need) __nanosleep(256);
-      __threadfence_block();
-      sm[L.obs + lane] = *reinterpret_cast<const volatile float*>(sense.dist + a * 32 + lane);
+      // the agent's rays: its 32 distances are the observation -- fetched a turn ahead (obs_cur), else wait for its
+      // round now
+      if (!have_cur) {
+        const uint32_t need = round + 1u;
+        volatile uint32_t* d = ray_done + (round % RW);
+        while (*d < need) __nanosleep(256);
+        __threadfence_block();
+        obs_cur = *reinterpret_cast<const volatile float*>(sense.dist + a * 32 + lane);
+      }
+      sm[L.obs + lane] = obs_cur;
     }
     if (tx) {
       mbar_wait(bars + s, parity[s]);
@@ -436,6 +453,8 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
     a = a_next;
     sv = sv_next;
     round = round_next;
+    obs_cur = obs_ahead;
+    have_cur = have_ahead;
   }
 }
 
