@@ -85,53 +85,99 @@ def wall_array(work):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+    """SM clock, power and throttle reasons sampled DURING the timed regions: NVML polled every ~2 ms from a thread
+    (an `nvidia-smi -lms 20` child, round 1's sampler, saw one sample of the 6 ms timed loop at N = 8); falls back to
+    nvidia-smi when NVML cannot be loaded."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.rows, self.p, self.t, self.via = [], None, None, None   # rows: (sm MHz, max MHz, W, reason bitmask)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else gpu_index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self._bits = bits
+            self._stop = threading.Event()
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), smax,
+                                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                          int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except nv.NVMLError:
+                        pass
+                    self._stop.wait(0.002)
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.via = "nvml, 2 ms"
+        except Exception:  # noqa: BLE001 -- any NVML problem: fall back to the nvidia-smi child
+            self.t = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                          stderr=subprocess.DEVNULL)
+                self.via = "nvidia-smi -lms 20"
+            except OSError:
+                self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "via": self.via}
         sm, smax, power, reasons = [], [], [], set()
-        for line in self.f.read().splitlines():
-            c = [s.strip() for s in line.split(",")]
-            if len(c) < 7:
-                continue
+        if self.t is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            for s_, m_, w_, r_ in self.rows:
+                sm.append(s_)
+                smax.append(m_)
+                power.append(w_)
+                for name, bit in self._bits.items():
+                    if r_ & bit:
+                        reasons.add(name)
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[0]))
-                smax.append(float(c[1]))
-                power.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            for line in self.f.read().splitlines():
+                c = [s.strip() for s in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    smax.append(float(c[1]))
+                    power.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.f.name)
+        else:
+            return out
         if sm:
-            # "under load" = samples whose power draw is in the upper half of what was seen
-            thr = (max(power) + min(power)) / 2.0
+            # "under load" = samples whose power draw is in the upper half of what was seen (90th percentile instead of
+            # the maximum: NVML's instantaneous power reading has isolated spikes far above the board limit)
+            thr = (float(np.percentile(power, 90)) + min(power)) / 2.0
             load = [s for s, pw in zip(sm, power) if pw >= thr] or sm
             out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+                       samples=len(sm), samples_under_load=len(load), power_w_p90=float(np.percentile(power, 90)),
+                       power_w_max=float(max(power)))
         return out
 
 

@@ -73,7 +73,10 @@ __device__ __forceinline__ void row_dot2(const float* rowA, const float* rowB, c
   } else if (len & 1) {
     int j = 0;
     for (; j + 4 <= len; j += 4) {
-      const float x0 = v[j], x1 = v[j + 1], x2 = v[j + 2], x3 = v[j + 3];
+      // v is 16-byte aligned (every slot of WcLayout is) and the same for all lanes: one broadcast LDS.128 per four
+      // columns; the odd row pitch keeps the rows on scalar loads.  Same products in the same order as before.
+      const float4 x = *reinterpret_cast<const float4*>(v + j);
+      const float x0 = x.x, x1 = x.y, x2 = x.z, x3 = x.w;
       a0 += rowA[j] * x0; a1 += rowA[j + 1] * x1; a2 += rowA[j + 2] * x2; a3 += rowA[j + 3] * x3;
       b0 += rowB[j] * x0; b1 += rowB[j + 1] * x1; b2 += rowB[j + 2] * x2; b3 += rowB[j + 3] * x3;
     }
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
   float* slot0 = reinterpret_cast<float*>(smem_raw + 16 * FS_WARPS) + (size_t)warp * slots * L.total;
   if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
   __syncwarp();
-  uint32_t parity[2] = {0u, 0u};
+  uint32_t parity = 0u;  // bit s = phase of slot s's mbarrier (a register: an array indexed by s lived in local memory)
 
   const int obs_cols = actions_out ? nobs : nobs - 1;
   const uint32_t bJ = leaf_tma_bytes(pol.J, n * n), bE = leaf_tma_bytes(pol.E, n * nobs),
@@ -374,12 +377,21 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
       sm[L.obs + lane] = obs_cur;
     }
     if (tx) {
-      mbar_wait(bars + s, parity[s]);
-      parity[s] ^= 1u;
+      mbar_wait(bars + s, (parity >> s) & 1u);
+      parity ^= 1u << s;
     }
     if (!actions_out && lane == 0) sm[L.obs + nobs - 1] = energy;  // obs = concat(sensor obs, own energy)
     // WilsonCowan.step_policy (wilson_cowan.py:34-51)
-    for (int j = lane; j < n; j += 32) sm[L.tz + j] = tanhf(sm[L.Z + j]);
+    // The per-agent arithmetic is a chain of short dependent sequences (tanh, sigmoid, shuffle reductions) and a warp
+    // issues one instruction per ~9 cycles through it, so independent pieces are written side by side: the two tanh
+    // of a lane's neurons, the two rows' epilogues, the two actions' reductions.  Same operations per value, same bits.
+    for (int j = lane; j < n; j += 64) {
+      const bool two = j + 32 < n;
+      const float z0 = sm[L.Z + j], z1 = sm[L.Z + (two ? j + 32 : j)];
+      const float t0 = tanhf(z0), t1 = tanhf(z1);
+      sm[L.tz + j] = t0;
+      if (two) sm[L.tz + j + 32] = t1;
+    }
     __syncwarp();
     for (int rA = lane; rA < n; rA += 64) {  // lane-rows rA and rA+32 together
       const bool hasB = rA + 32 < n;
@@ -387,28 +399,51 @@ __global__ void __launch_bounds__((FS_WARPS + (RW > 0 ? RW : 2)) * 32, 2)
       float sJ[2], sE[2];
       row_dot2<NN>(sm + L.J + rA * n, sm + L.J + rB * n, sm + L.tz, n, rA, sJ[0], sJ[1]);
       row_dot2<NOBS>(sm + L.E + rA * nobs, sm + L.E + rB * nobs, sm + L.obs, nobs, rA, sE[0], sE[1]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !hasB) break;
-        const int r = h ? rB : rA;
-        const float z = sm[L.Z + r];
-        float dz = ((sJ[h] + sE[h]) + sm[L.B + r]) - z;
-        dz = dz * (10.0f * sigmoidf_(sm[L.tau + r]));
-        const float nz = z + p.policy_dt * dz;
-        gZ[r] = nz;
-        sm[L.tnz + r] = tanhf(nz);
+      // both rows' epilogues as straight-line code (a lane without a second row repeats its first and does not store)
+      const float zA = sm[L.Z + rA], zB = sm[L.Z + rB];
+      const float gA = 10.0f * sigmoidf_(sm[L.tau + rA]), gB = 10.0f * sigmoidf_(sm[L.tau + rB]);
+      float dzA = ((sJ[0] + sE[0]) + sm[L.B + rA]) - zA, dzB = ((sJ[1] + sE[1]) + sm[L.B + rB]) - zB;
+      dzA = dzA * gA;
+      dzB = dzB * gB;
+      const float nzA = zA + p.policy_dt * dzA, nzB = zB + p.policy_dt * dzB;
+      const float tA = tanhf(nzA), tB = tanhf(nzB);
+      gZ[rA] = nzA;
+      sm[L.tnz + rA] = tA;
+      if (hasB) {
+        gZ[rB] = nzB;
+        sm[L.tnz + rB] = tB;
       }
     }
     __syncwarp();
     float act0 = 0.0f, act1 = 0.0f;  // the Forager uses actions[0], actions[1] (sim.py:86-87)
-    for (int k = 0; k < nact; ++k) {
+    {
+      // actions 0 and 1 together (nact >= 2 is checked by the launchers of the Forager step; the policy-only entry
+      // point may have a single action: its second sum then repeats the first)
+      const int k1 = nact > 1 ? 1 : 0;
+      float d0 = 0.0f, d1 = 0.0f;
+      for (int j = lane; j < n; j += 32) {
+        const float t = sm[L.tnz + j];
+        d0 += sm[L.D + j] * t;
+        d1 += sm[L.D + k1 * n + j] * t;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      }
+      act0 = p.action_scale * tanhf(d0);
+      act1 = p.action_scale * tanhf(d1);
+      if (actions_out && lane == 0) {
+        actions_out[a * nact] = act0;
+        if (nact > 1) actions_out[a * nact + 1] = act1;
+      }
+    }
+    for (int k = 2; k < nact; ++k) {  // further actions (policy-only mode with nact > 2)
       float d = 0.0f;
       for (int j = lane; j < n; j += 32) d += sm[L.D + k * n + j] * sm[L.tnz + j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
       const float v = p.action_scale * tanhf(d);
-      if (k == 0) act0 = v;
-      if (k == 1) act1 = v;
       if (actions_out && lane == 0) actions_out[a * nact + k] = v;
     }
     const float X = __shfl_sync(0xffffffffu, sv, 0), Xv = __shfl_sync(0xffffffffu, sv, 1);
