@@ -233,6 +233,35 @@ def test_fused_sense_step_equals_raycast_then_step(cuda, mode, monkeypatch):
     assert float((h0 >= 0).float().mean()) > 0.01
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 63, 300])
+def test_fused_sense_step_small_sets(cuda, n, monkeypatch):
+    """The warp-specialised fused tick on tiny agent sets (fewer agents than one round of one CTA, partial last tile,
+    ray warps without any round): same bits as the two-kernel tick, no hang."""
+    import bench
+    from foragax_b200.base.agent_classes import Params, Signal
+    from foragax_b200.base.agent_methods import step_agents
+    import foragax_b200.base.space_methods as sm
+    from foragax_b200 import struct
+    from foragax_b200.examples.foraging import Forager
+    monkeypatch.setenv("FGX_SENSE_STEP_MODE", "2")
+    work = bench.make_workload(n, 200)
+    fa, space = bench.build_foragers(work, 0, 1, cuda, n_agents=n)
+    fb, _ = bench.build_foragers(work, 0, 1, cuda, n_agents=n)
+    bounds = (0.0, bench.ARENA, 0.0, bench.ARENA)
+    params = Params(content={'space': space, 'repr_thresh': 5.0, 'die_thresh': 0.0, 'energy_min': -1.0, 'energy_max': 15.0})
+    energy_in = torch.zeros(n, device=cuda)
+    for _ in range(3):
+        sa = fa.agents.state.content
+        d0, h0 = sm.raycast_walls((sa["X"], sa["Y"], sa["ang"]), bench.RAY_SPAN, bench.RAY_LEN, space.walls,
+                                  active_state=fa.agents.active_state, n_rays=bench.N_RAYS, bounds=bounds)
+        fa.agents = step_agents(params, Signal(content={'obs': d0, 'energy_in': energy_in}), fa)
+        fb.agents, d1, h1 = Forager.sense_step(params, energy_in, fb.agents, space.walls, bounds, bench.RAY_SPAN,
+                                               bench.RAY_LEN)
+        assert torch.equal(d0, d1) and torch.equal(h0, h1)
+        for x, y in zip(struct.tree_leaves(fa.agents), struct.tree_leaves(fb.agents)):
+            assert torch.equal(x, y)
+
+
 def test_bench_instantiation_forager_step_matches_oracle(cuda):
     """The kernel instantiation bench.py times -- forager_step_kernel<40,33,2> on the C4 workload (32 ray
     distances + own energy = 33 observations) -- against oracle.foraging.forager_step (Forager.step_agent,
