@@ -373,6 +373,69 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerStep, ForagerStepImpl,
                                   .Attr<int32_t>("clip_min")
                                   .RemainingRets());
 
+// ---- the tick as one kernel: sensor (wall rays) -> step_agents (sim.py:652-660) = fgx_forager_sense_step.  Operands:
+// active, energy_in, the four wall arrays, then the 18 Forager leaves; results: dist, hit, then the 13 aliased leaves.
+// XLA owns the scratch, so the wall lists are rebuilt per call (reuse_grid = 0).
+static ffi::Error ForagerSenseStepImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> active, ffi::Buffer<ffi::F32> energy_in,
+                                       ffi::Buffer<ffi::F32> wx1, ffi::Buffer<ffi::F32> wy1, ffi::Buffer<ffi::F32> wx2,
+                                       ffi::Buffer<ffi::F32> wy2, ffi::RemainingArgs args, ffi::ScratchAllocator scratch,
+                                       int32_t n_neurons, int32_t n_obs, int32_t n_act, float dt, float policy_dt,
+                                       float action_scale, float x_min, float x_max, float y_min, float y_max,
+                                       float repr_thresh, float die_thresh, float energy_min, float energy_max,
+                                       float energy_cost_dt, int32_t clip_min, int32_t n_rays, float ray_span,
+                                       float ray_length, ffi::Result<ffi::Buffer<ffi::F32>> dist,
+                                       ffi::Result<ffi::Buffer<ffi::S32>> hit, ffi::RemainingRets rets) {
+  fgx_forager_params_t p{n_neurons, n_obs,       n_act,      dt,         policy_dt,  action_scale,   x_min,   x_max,
+                         y_min,     y_max,       repr_thresh, die_thresh, energy_min, energy_max, energy_cost_dt, clip_min};
+  fgx_forager_state_t st{};
+  fgx_wc_policy_t pol{};
+  float* age = nullptr;
+  ffi::Error e = ForagerLeaves("fgx_forager_sense_step", args, rets, &st, &pol, &age);
+  if (!e.success()) return e;
+  const int64_t n_walls = static_cast<int64_t>(wx1.element_count());
+  const size_t bytes = fgx_raycast_walls_grid_scratch_bytes(n_walls, x_min, x_max, y_min, y_max, ray_length);
+  auto buf = scratch.Allocate(bytes, 256);
+  if (!buf.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "fgx_forager_sense_step: scratch");
+  return Status(fgx_forager_sense_step(&p, static_cast<int64_t>(active.element_count()), active.typed_data(),
+                                       energy_in.typed_data(), &st, &pol, age, n_rays, ray_span, ray_length,
+                                       wx1.typed_data(), wy1.typed_data(), wx2.typed_data(), wy2.typed_data(), n_walls,
+                                       x_min, x_max, y_min, y_max, *buf, bytes, /*reuse_grid=*/0, dist->typed_data(),
+                                       hit->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FgxForagerSenseStep, ForagerSenseStepImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .RemainingArgs()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Attr<int32_t>("n_neurons")
+                                  .Attr<int32_t>("n_obs")
+                                  .Attr<int32_t>("n_act")
+                                  .Attr<float>("dt")
+                                  .Attr<float>("policy_dt")
+                                  .Attr<float>("action_scale")
+                                  .Attr<float>("x_min")
+                                  .Attr<float>("x_max")
+                                  .Attr<float>("y_min")
+                                  .Attr<float>("y_max")
+                                  .Attr<float>("repr_thresh")
+                                  .Attr<float>("die_thresh")
+                                  .Attr<float>("energy_min")
+                                  .Attr<float>("energy_max")
+                                  .Attr<float>("energy_cost_dt")
+                                  .Attr<int32_t>("clip_min")
+                                  .Attr<int32_t>("n_rays")
+                                  .Attr<float>("ray_span")
+                                  .Attr<float>("ray_length")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .RemainingRets());
+
 // ---- remove_agents / set_agents with the Forager callbacks (sim.py:139-151,213-225)
 static ffi::Error ForagerRemoveImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> remove_ids, ffi::Buffer<ffi::S32> k,
                                     ffi::Buffer<ffi::F32> active, ffi::RemainingArgs args, int32_t n_neurons,

@@ -24,7 +24,7 @@ def test_shim_covers_the_per_tick_path():
     want = {"FgxSelect", "FgxArgsort", "FgxTakeRows", "FgxRaycastWalls", "FgxRaycastWallsGrid", "FgxRaycastAgents",
             "FgxThreefrySplit", "FgxThreefryUniform", "FgxThreefryRandint", "FgxCountActive", "FgxDiceStep",
             "FgxDiceRemove", "FgxDiceAdd", "FgxForagerStep", "FgxForagerRemove", "FgxForagerAdd", "FgxForagerSet",
-            "FgxSensorModel"}
+            "FgxSensorModel", "FgxForagerSenseStep"}
     assert want <= handlers, sorted(want - handlers)
     # every launcher the handlers forward to is declared in the public header
     hdr = open(os.path.join(ROOT, "include", "foragax_b200.h")).read()
