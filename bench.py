@@ -115,7 +115,8 @@ class ClockSampler:
                     try:
                         self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), smax,
                                           nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
-                                          int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                                          int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)),
+                                          float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_MEM))))
                     except nv.NVMLError:
                         pass
                     self._stop.wait(0.002)
@@ -135,11 +136,12 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "via": self.via}
-        sm, smax, power, reasons = [], [], [], set()
+        sm, smax, power, reasons, mem = [], [], [], set(), []
         if self.t is not None:
             self._stop.set()
             self.t.join(timeout=2)
-            for s_, m_, w_, r_ in self.rows:
+            for s_, m_, w_, r_, mc_ in self.rows:
+                mem.append(mc_)
                 sm.append(s_)
                 smax.append(m_)
                 power.append(w_)
@@ -178,6 +180,9 @@ class ClockSampler:
             out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
                        samples=len(sm), samples_under_load=len(load), power_w_p90=float(np.percentile(power, 90)),
                        power_w_max=float(max(power)))
+            if mem:
+                out["mem_mhz_min"] = float(min(mem))
+                out["mem_mhz_median"] = float(np.median(mem))
         return out
 
 
@@ -621,30 +626,38 @@ def run_ours(args):
         tick()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        tick()
-    e1.record(stream)
-    barrier()
-    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    def timed_ticks(one_kernel):
+        """K ticks between e0 and e1 (barrier + synchronize on both sides; max over ranks).  The two-kernel form also
+        records an event between and after its kernels INSIDE the timed loop, without any host sync: the per-kernel
+        durations then come from the very launches the step time comes from (a separate later loop can run at a
+        different power / clock state -- one round-2 line had K1c + K2 above its own step time that way -- and a
+        sync per iteration would put Python's launch latency into the short kernel's interval, which is how round 1
+        reported K1c ~45 us too long)."""
+        marks = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            if one_kernel:
+                tick_fused()
+            else:
+                k1()
+                marks[i][0].record(stream)
+                k2()
+                marks[i][1].record(stream)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        if one_kernel:
+            return ms, None, None
+        a = [(e0 if i == 0 else marks[i - 1][1]).elapsed_time(marks[i][0]) for i in range(args.steps)]
+        b = [marks[i][0].elapsed_time(marks[i][1]) for i in range(args.steps)]
+        return ms, float(np.mean(a)), float(np.mean(b))
+
+    ms_step, k1_ms, k2_ms = timed_ticks(fused)
     tests_per_step = float(N_AGENTS) * N_RAYS * N_WALLS
     value = tests_per_step / (ms_step * 1e-3)
-
-    # per-kernel durations, live, with CUDA events on the launching stream.  All launches of the loop are enqueued
-    # without a host sync in between (events are read afterwards): with a sync per iteration the GPU idles while
-    # Python prepares the next launch and that CPU time lands inside the event interval of the short kernel
-    # (round 1 and the first round-2 lines reported K1c ~45 us too long for this reason).
-    reps = max(args.steps, 20)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
-    for r in range(reps):
-        evs[r][0].record(stream)
-        k1()
-        evs[r][1].record(stream)
-        k2()
-        evs[r][2].record(stream)
-    torch.cuda.synchronize()
-    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs[1:]]))   # the first K1c follows an idle GPU
-    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs[1:]]))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)]]
     ev = evs[0]
     listed = sm.wall_grid_listed((st["X"], st["Y"]), space.walls, BOUNDS, RAY_LEN, active_state=F.active_state)
 
@@ -669,13 +682,13 @@ def run_ours(args):
         other_tick = tick_two if fused else tick_fused
         for _ in range(3):
             other_tick()
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            other_tick()
-        e1.record(stream)
-        barrier()
-        other_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        other_ms, o1, o2 = timed_ticks(not fused)
+        if fused:
+            k1_ms, k2_ms = o1, o2
+    if k1_ms is None:  # --fused-tick --no-other-tick: the two kernels are still needed for the stage blocks
+        for _ in range(2):
+            tick_two()
+        _, k1_ms, k2_ms = timed_ticks(False)
 
     # end to end through the public API with HOST buffers: every step copies the agents' pose and active
     # flags from pinned host memory (H2D), runs the tick and reads back its result (ray distances, hit
