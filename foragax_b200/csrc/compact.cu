@@ -190,62 +190,93 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_scatter_kernel(const __grid_
 }
 
 // Fast path of the common predicate shape -- ONE comparison on a contiguous 4-byte leaf (draw == 1, flag != 0,
-// energy > t, ...) -- for a FULL 256-slot group: one base pointer with immediate offsets, the operator resolved
-// once per group instead of once per slot (~50 instructions per group against ~300 for the general evaluator;
-// at 10 M slots the general form made the select instruction-bound, not bandwidth-bound).
-template <typename Cmp>
-__device__ __forceinline__ unsigned cmp8(const uint32_t* __restrict__ p, Cmp cmp) {
-  uint32_t raw[SEL_ITEMS];
-#pragma unroll
-  for (int r = 0; r < SEL_ITEMS; ++r) raw[r] = __ldg(p + r * 32);
-  unsigned m = 0;
-#pragma unroll
-  for (int r = 0; r < SEL_ITEMS; ++r) m |= (cmp(raw[r]) ? 1u : 0u) << r;
-  return m;
+// energy > t, ...): one base pointer with immediate offsets and the operator resolved to a closed-range test once
+// per thread instead of a switch per slot.  It lives in its own kernel
+// instantiation: with the general evaluator inlined next to a switch over dtype x operator the one-pass kernel was
+// 17 k instructions long and spent 13 % of its 30 us waiting for instruction fetches (ncu: no_instruction).
+// every operator is a closed-range test, possibly negated: EQ [c, c], NE not [c, c], LT [-inf, pred(c)], LE [-inf, c],
+// GT [succ(c), +inf], GE [c, +inf], NONZERO not [0, 0].  Floats: b >= lo && b <= hi is false for a NaN b or a NaN
+// bound, which is exactly what the ordered comparisons give (and NE / NONZERO, negated, then hold); -0 == +0 as in
+// IEEE.  Integers: (uint32)(b - lo) <= (uint32)(hi - lo).
+struct FastRange {
+  uint32_t lo, hi;  // bit patterns (float) or values (int32)
+  bool neg, is_float;
+};
+__device__ __forceinline__ FastRange fast_range(const fgx_pred_term_t& t) {
+  FastRange r;
+  r.is_float = t.dtype == FGX_F32;
+  r.neg = t.op == FGX_OP_NE || t.op == FGX_OP_NONZERO;
+  if (r.is_float) {
+    const float c = t.op == FGX_OP_NONZERO ? 0.0f : __uint_as_float(t.imm_bits);
+    const float inf = __int_as_float(0x7f800000);
+    float lo = c, hi = c;
+    if (t.op == FGX_OP_LT) { lo = -inf; hi = nextafterf(c, -inf); }
+    else if (t.op == FGX_OP_LE) lo = -inf;
+    else if (t.op == FGX_OP_GT) { lo = nextafterf(c, inf); hi = inf; }
+    else if (t.op == FGX_OP_GE) hi = inf;
+    // x < -inf and x > +inf hold for no x: an empty range (lo > hi) -- nextafter(-inf, -inf) would keep -inf in it
+    if ((t.op == FGX_OP_LT && c == -inf) || (t.op == FGX_OP_GT && c == inf)) { lo = 1.0f; hi = 0.0f; }
+    r.lo = __float_as_uint(lo);
+    r.hi = __float_as_uint(hi);
+  } else {
+    const int32_t c = t.op == FGX_OP_NONZERO ? 0 : (int32_t)t.imm_bits;
+    const int32_t mn = (int32_t)0x80000000, mx = 0x7fffffff;
+    int32_t lo = c, hi = c;
+    bool empty = false;
+    if (t.op == FGX_OP_LT) { lo = mn; hi = c - 1; empty = c == mn; }
+    else if (t.op == FGX_OP_LE) lo = mn;
+    else if (t.op == FGX_OP_GT) { lo = c + 1; hi = mx; empty = c == mx; }
+    else if (t.op == FGX_OP_GE) hi = mx;
+    if (empty) { r.neg = !r.neg; lo = mn; hi = mx; }  // nothing matches = not (everything)
+    r.lo = (uint32_t)lo;
+    r.hi = (uint32_t)hi - (uint32_t)lo;  // width
+  }
+  return r;
 }
-__device__ __forceinline__ unsigned fast_flags_full(const fgx_predicate_t& p, int64_t base, int l) {
-  const fgx_pred_term_t& t = p.term[0];
-  const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(t.data) + base + l;
-  unsigned m;
-  if (t.dtype == FGX_F32) {
-    const float c = __uint_as_float(t.imm_bits);
-    switch (t.op) {
-      case FGX_OP_EQ: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) == c; }); break;
-      case FGX_OP_NE: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) != c; }); break;
-      case FGX_OP_LT: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) < c; }); break;
-      case FGX_OP_LE: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) <= c; }); break;
-      case FGX_OP_GT: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) > c; }); break;
-      case FGX_OP_GE: m = cmp8(q, [c](uint32_t b) { return __uint_as_float(b) >= c; }); break;
-      default: m = cmp8(q, [](uint32_t b) { return __uint_as_float(b) != 0.0f; }); break;
+__device__ __forceinline__ unsigned fast_flags(const fgx_predicate_t& p, const FastRange& fr, int64_t base, int64_t n, int l) {
+  const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(p.term[0].data) + base + l;
+  const bool full = base + 32 * SEL_ITEMS <= n;  // warp-uniform
+  uint32_t raw[SEL_ITEMS];
+  unsigned valid = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_ITEMS; ++r) {
+    const bool ok = full || base + r * 32 + l < n;
+    raw[r] = ok ? __ldg(q + r * 32) : 0u;
+    valid |= (ok ? 1u : 0u) << r;
+  }
+  unsigned m = 0;
+  if (fr.is_float) {
+    const float lo = __uint_as_float(fr.lo), hi = __uint_as_float(fr.hi);
+#pragma unroll
+    for (int r = 0; r < SEL_ITEMS; ++r) {
+      const float b = __uint_as_float(raw[r]);
+      m |= ((b >= lo && b <= hi) ? 1u : 0u) << r;
     }
   } else {
-    const int32_t c = (int32_t)t.imm_bits;
-    switch (t.op) {
-      case FGX_OP_EQ: m = cmp8(q, [c](uint32_t b) { return (int32_t)b == c; }); break;
-      case FGX_OP_NE: m = cmp8(q, [c](uint32_t b) { return (int32_t)b != c; }); break;
-      case FGX_OP_LT: m = cmp8(q, [c](uint32_t b) { return (int32_t)b < c; }); break;
-      case FGX_OP_LE: m = cmp8(q, [c](uint32_t b) { return (int32_t)b <= c; }); break;
-      case FGX_OP_GT: m = cmp8(q, [c](uint32_t b) { return (int32_t)b > c; }); break;
-      case FGX_OP_GE: m = cmp8(q, [c](uint32_t b) { return (int32_t)b >= c; }); break;
-      default: m = cmp8(q, [](uint32_t b) { return b != 0u; }); break;
-    }
+#pragma unroll
+    for (int r = 0; r < SEL_ITEMS; ++r) m |= ((raw[r] - fr.lo <= fr.hi) ? 1u : 0u) << r;
   }
-  // 1-term truth table: bit 1 = value when the term holds, bit 0 = value when it does not
-  return ((p.lut & 2u) ? m : 0u) | ((p.lut & 1u) ? (~m & 0xFFu) : 0u);
+  if (fr.neg) m = ~m & 0xFFu;
+  // 1-term truth table: bit 1 = value when the term holds, bit 0 = value when it does not; slots beyond n: 0
+  return (((p.lut & 2u) ? m : 0u) | ((p.lut & 1u) ? (~m & 0xFFu) : 0u)) & valid;
 }
-__device__ __forceinline__ unsigned group_flags(const fgx_predicate_t& p, bool fast, int64_t base, int64_t n, int l) {
-  return fast && base + 32 * SEL_ITEMS <= n ? fast_flags_full(p, base, l) : flags_at<SEL_ITEMS>(p, base, n, l);
+template <bool FAST>
+__device__ __forceinline__ unsigned group_flags(const fgx_predicate_t& p, const FastRange& fr, int64_t base, int64_t n, int l) {
+  if constexpr (FAST) return fast_flags(p, fr, base, n, l);
+  else return flags_at<SEL_ITEMS>(p, base, n, l);
 }
 
 // ---- one pass: cooperative launch, predicate evaluated once, ballots parked in shared memory ----------
 constexpr int OP_GROUP = 32 * SEL_ITEMS;  // 256 slots: lane l holds rows r = 0..7 (slot g*256 + r*32 + l)
 constexpr int OP_MAX_GPW = 32;            // groups per warp the ballots of which fit (8 KB of shared memory)
 
+template <bool FAST>
 __global__ void __launch_bounds__(SEL_BLOCK) select_onepass_kernel(const __grid_constant__ fgx_predicate_t p, int64_t n,
-                                                                  int64_t groups, int gpw, int fast,
+                                                                  int64_t groups, int gpw,
                                                                   int32_t* __restrict__ cta_count,
                                                                   int32_t* __restrict__ perm,
                                                                   int32_t* __restrict__ count_out) {
+  const FastRange relmask = FAST ? fast_range(p.term[0]) : FastRange{};
   __shared__ unsigned balls[SEL_WARPS][OP_MAX_GPW][SEL_ITEMS];
   __shared__ int wcount[SEL_WARPS];
   __shared__ int warp_sums[SEL_WARPS];
@@ -255,8 +286,8 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_onepass_kernel(const __grid_
   int c = 0;
   int k = 0;
   for (; k + 2 <= mine; k += 2) {  // two groups per trip: 16 independent loads per term in flight
-    const unsigned f0 = group_flags(p, fast != 0, (g0 + k) * OP_GROUP, n, l);
-    const unsigned f1 = group_flags(p, fast != 0, (g0 + k + 1) * OP_GROUP, n, l);
+    const unsigned f0 = group_flags<FAST>(p, relmask, (g0 + k) * OP_GROUP, n, l);
+    const unsigned f1 = group_flags<FAST>(p, relmask, (g0 + k + 1) * OP_GROUP, n, l);
 #pragma unroll
     for (int r = 0; r < SEL_ITEMS; ++r) {
       const unsigned b0 = __ballot_sync(0xffffffffu, (f0 >> r) & 1u), b1 = __ballot_sync(0xffffffffu, (f1 >> r) & 1u);
@@ -265,7 +296,7 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_onepass_kernel(const __grid_
     }
   }
   if (k < mine) {
-    const unsigned f0 = group_flags(p, fast != 0, (g0 + k) * OP_GROUP, n, l);
+    const unsigned f0 = group_flags<FAST>(p, relmask, (g0 + k) * OP_GROUP, n, l);
 #pragma unroll
     for (int r = 0; r < SEL_ITEMS; ++r) {
       const unsigned b0 = __ballot_sync(0xffffffffu, (f0 >> r) & 1u);
@@ -396,10 +427,17 @@ int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32
   int32_t* cta_count = reinterpret_cast<int32_t*>(scratch);
   {  // one cooperative pass whenever the ballots of a warp's groups fit in shared memory
     static const bool two_pass = [] { const char* v = getenv("FGX_SELECT_TWO_PASS"); return v && atoi(v) == 1; }();
-    static int per_sm = -1;
+    fgx_predicate_t pred = *pred_host;
+    // one comparison on a contiguous, 4-byte-aligned 4-byte leaf: the compact fast-path kernel
+    const bool fast = pred.n_terms == 1 && pred.term[0].stride == 1 && pred.term[0].dtype != FGX_U8 &&
+                      (reinterpret_cast<uintptr_t>(pred.term[0].data) & 3) == 0;
+    const void* kern = fast ? (const void*)select_onepass_kernel<true> : (const void*)select_onepass_kernel<false>;
+    static int per_sm_of[2] = {-1, -1};
+    int& per_sm = per_sm_of[fast ? 1 : 0];
     if (per_sm < 0) {
       int q = 0;
-      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, select_onepass_kernel, SEL_BLOCK, 0);
+      cudaError_t oe = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, select_onepass_kernel<true>, SEL_BLOCK, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, select_onepass_kernel<false>, SEL_BLOCK, 0);
       per_sm = (oe == cudaSuccess && q >= 1) ? q : 0;
     }
     int64_t coop = (int64_t)sm_count() * per_sm;
@@ -408,14 +446,9 @@ int fgx_select(const fgx_predicate_t* pred_host, int64_t n, int32_t* perm, int32
     if (!two_pass && coop >= 1 && ceil_div(groups, coop * SEL_WARPS) <= OP_MAX_GPW) {
       int gpw = (int)ceil_div(groups, coop * SEL_WARPS);
       const int grid = (int)ceil_div(groups, (int64_t)gpw * SEL_WARPS);
-      fgx_predicate_t pred = *pred_host;
       int64_t n_arg = n, groups_arg = groups;
-      // one comparison on a contiguous, 4-byte-aligned 4-byte leaf: the per-group fast evaluator
-      int fast = pred.n_terms == 1 && pred.term[0].stride == 1 && pred.term[0].dtype != FGX_U8 &&
-                 (reinterpret_cast<uintptr_t>(pred.term[0].data) & 3) == 0;
-      void* args[] = {&pred, &n_arg, &groups_arg, &gpw, &fast, &cta_count, &perm, &count};
-      cudaError_t e = cudaLaunchCooperativeKernel((const void*)select_onepass_kernel, dim3((unsigned)grid),
-                                                  dim3(SEL_BLOCK), args, 0, s);
+      void* args[] = {&pred, &n_arg, &groups_arg, &gpw, &cta_count, &perm, &count};
+      cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(SEL_BLOCK), args, 0, s);
       if (e != cudaSuccess) return fail(FGX_ERR_CUDA, "fgx_select: cooperative launch: %s", cudaGetErrorString(e));
       return check_launch("fgx_select(one pass)");
     }

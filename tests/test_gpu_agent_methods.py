@@ -140,6 +140,48 @@ def test_select_fused_predicates(cuda):
         np.testing.assert_array_equal(perm.cpu().numpy(), rp)
 
 
+@pytest.mark.parametrize("n", [20_000, 70_001])
+def test_select_single_term_operators(cuda, n):
+    """The one-term fast path of fgx_select (a closed-range test per operator, compact.cu::fast_range) for every
+    operator, on float and int32 leaves with the edge immediates: +-0, +-inf, NaN, INT_MIN / INT_MAX; leaves contain
+    NaN, +-inf, +-0 and the extreme integers.  Both the cooperative one-pass kernel (n > 16384) and its partial last
+    group are exercised; the reference is NumPy's comparison."""
+    import operator
+
+    import foragax_b200.base.agent_methods as fgx_methods
+    from foragax_b200.base.predicates import P
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal(n).astype(np.float32)
+    f[rng.integers(0, n, 50)] = np.nan
+    f[rng.integers(0, n, 50)] = np.inf
+    f[rng.integers(0, n, 50)] = -np.inf
+    f[rng.integers(0, n, 50)] = 0.0
+    f[rng.integers(0, n, 50)] = -0.0
+    f[rng.integers(0, n, 50)] = 1.5
+    i = rng.integers(-5, 6, n).astype(np.int32)
+    i[rng.integers(0, n, 50)] = np.iinfo(np.int32).min
+    i[rng.integers(0, n, 50)] = np.iinfo(np.int32).max
+    F, I = torch.from_numpy(f).to(cuda), torch.from_numpy(i).to(cuda)
+    ops = [operator.eq, operator.ne, operator.lt, operator.le, operator.gt, operator.ge]
+
+    def check(pred, mask):
+        cnt, perm = fgx_methods.select_agents(lambda a, p: pred, None, None)
+        rc, rp = oam.select_from_mask(mask)
+        assert int(cnt) == int(rc)
+        np.testing.assert_array_equal(perm.cpu().numpy(), rp)
+
+    with np.errstate(invalid="ignore"):
+        for c in (0.0, -0.0, 1.5, -0.25, float("inf"), float("-inf"), float("nan")):
+            for op in ops:
+                check(op(P(F), c), op(f, np.float32(c)))
+                check(~op(P(F), c), ~op(f, np.float32(c)))
+        for c in (0, 2, -5, 5, int(np.iinfo(np.int32).min), int(np.iinfo(np.int32).max)):
+            for op in ops:
+                check(op(P(I), c), op(i, np.int32(c)))
+    check(P(F).nonzero(), f != 0)
+    check(P(I).nonzero(), i != 0)
+
+
 @pytest.mark.parametrize("n", [1, 2, 100, 256, 257, 1000, 1025, 4096, 6000, 16384, 16385, 50000, 1 << 20, 3_000_017])
 @pytest.mark.parametrize("kind", ["flag", "float", "float_special", "int", "int_small", "const"])
 @pytest.mark.parametrize("ascend", [True, False])
