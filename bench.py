@@ -872,7 +872,8 @@ def run_ours(args):
         listed_pairs = float(listed_host[0]) * N_RAYS            # (ray, wall) tests the kernel has to evaluate
         floor_bytes_ms = rc_bytes / (hbm * 1e9) * 1e3
         floor_inst_ms = listed_pairs * 16 / (peak_tflops * 1e12) * 1e3
-        roof_rc = {"kernel": "raycast_walls_grid_kernel (wall lists built once, cached)", "kernel_ms": k1_ms,
+        roof_rc = {"kernel": "raycast_walls_grid_warp32_kernel (fgx_raycast_walls_grid, 32 rays: a warp per agent; wall lists built "
+                             "once, cached)", "kernel_ms": k1_ms,
                    "share_of_step": k1_ms / (k1_ms + k2_ms),
                    "algorithmic_bytes": rc_bytes, "gbs": rc_bytes / (k1_ms * 1e-3) / 1e9,
                    "traffic": measured_traffic("raycast_walls_grid_kernel", n_local),
